@@ -1,0 +1,239 @@
+"""Config system: flat dotted-key YAML, three-level merge, typed schema.
+
+Parity target: the reference merges ``params_default.yaml`` <- dataset yaml <- ``--extra_config``
+JSON and asserts that every overriding key already exists (reference ``train.py:30-44``), then
+post-processes two comma-strings into int lists (``train.py:54-55``).  The merged dict doubles as
+a runtime blackboard (logger, tb_writer, ranks).  We keep the *format* (so a ``params.yaml``
+written by either system is readable by the other) but make the schema explicit:
+
+* every known key has a type and a default (``SCHEMA``) - unknown keys raise ``ConfigError``
+  with the offending name, instead of a bare ``assert``;
+* keys that the reference ships but never reads ("dead keys") are accepted so that
+  upstream yaml files load unchanged (including ``params_dtu.yaml``'s ``model.decoder_type``,
+  which crashes the reference - SURVEY 2.8 item 2);
+* ``mpi.is_bg_depth_inf`` is honoured (the reference reads a never-defined key instead,
+  SURVEY 2.8 item 1); the legacy spelling ``mpi.render_tgt_rgb_depth`` is accepted as an alias.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+from typing import Any, Dict, Iterable, Mapping, Optional
+
+import yaml
+
+
+class ConfigError(KeyError):
+    pass
+
+
+# key -> (type tag, default).  Type tags: int, float, bool, str, "intlist", "any"
+SCHEMA: Dict[str, tuple] = {
+    # data
+    "data.img_h": (int, 384),
+    "data.img_w": (int, 512),
+    "data.name": (str, "llff"),
+    "data.img_pre_downsample_ratio": (float, 7.875),
+    "data.num_seq_per_gpu": (int, 4),            # dead in reference
+    "data.per_gpu_batch_size": (int, 4),
+    "data.num_tgt_views": (int, 1),
+    "data.training_set_path": (str, ""),
+    "data.val_set_path": (str, ""),
+    "data.visible_point_count": (int, 256),
+    "data.num_workers": (int, 4),                # dead in reference; used by our pinned loader
+    "data.rotation_pi_ratio": (float, 3),        # dead
+    "data.is_exclude_views": (bool, True),       # dead
+    # lr
+    "lr.backbone_lr": (float, 1e-3),
+    "lr.decoder_lr": (float, 1e-3),
+    "lr.decay_gamma": (float, 0.1),
+    "lr.decay_steps": ("intlist", [5, 10]),
+    "lr.weight_decay": (float, 4e-5),
+    # model
+    "model.backbone_normalization": (bool, True),    # dead
+    "model.decoder_normalization": (bool, True),     # dead
+    "model.decoder_type": (str, "batch_decoder"),    # dead; present only in params_dtu.yaml
+    "model.pos_encoding_multires": (int, 10),
+    "model.imagenet_pretrained": (bool, True),
+    # mpi
+    "mpi.disparity_start": (float, 1.0),
+    "mpi.disparity_end": (float, 0.001),
+    "mpi.is_bg_depth_inf": (bool, False),
+    "mpi.num_bins_coarse": (int, 32),
+    "mpi.num_bins_fine": (int, 0),
+    "mpi.valid_mask_threshold": (float, 2),
+    "mpi.fix_disparity": (bool, False),
+    "mpi.use_alpha": (bool, False),
+    # loss
+    "loss.smoothness_lambda_v1": (float, 0.0),
+    "loss.smoothness_lambda_v2": (float, 0.01),
+    "loss.smoothness_gmin": (float, 2.0),
+    "loss.smoothness_grad_ratio": (float, 0.1),
+    # training
+    "training.epochs": (int, 15),
+    "training.eval_interval": (int, 10000),
+    "training.fine_tune": (bool, False),            # dead
+    "training.gpus": ("intlist", [0]),
+    "training.pretrained_checkpoint_path": ("any", None),
+    "training.sample_interval": (int, 30),          # dead
+    "training.src_rgb_blending": (bool, True),
+    "training.use_multi_scale": (bool, True),
+    "testing.frames_apart": ("any", "random"),      # dead
+    # ---- extensions of this framework (absent upstream; all optional) ----
+    "engine.compute_dtype": (str, "bf16"),          # conv stack compute dtype on the CUDA path
+    "engine.cuda_graph": (bool, False),
+    "engine.comm": (str, "p2p"),                    # p2p (own kernels over NVLink) | nccl (baseline)
+    "engine.resume": (bool, True),                  # restore step/epoch/scheduler/RNG if present
+    "training.seed": (int, 0),
+    "training.checkpoint_interval": (int, 5000),
+    "training.log_interval": (int, 10),
+    "training.all_rank_eval": (bool, True),
+    "training.max_steps": (int, 0),                 # 0 = no cap (used by tests / smoke runs)
+}
+
+ALIASES = {"mpi.render_tgt_rgb_depth": "mpi.is_bg_depth_inf"}
+
+# Runtime blackboard entries the reference stores inside the same dict.
+RUNTIME_KEYS = {
+    "current_epoch", "global_rank", "local_rank", "world_size", "log_file", "logger", "tb_writer",
+    "local_workspace", "hdfs_workspace", "mpi.disparity_list",
+}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_CONFIG_DIR = os.path.join(os.path.dirname(_HERE), "configs")
+
+DATASET_YAML = {
+    "llff": "params_llff.yaml",
+    "flowers": "params_flowers.yaml",
+    "kitti_raw": "params_kitti_raw.yaml",
+    "dtu": "params_dtu.yaml",
+    "realestate10k": "params_realestate.yaml",
+    "realestate": "params_realestate.yaml",
+}
+
+
+def _as_int_list(v: Any) -> list:
+    if isinstance(v, (list, tuple)):
+        return [int(x) for x in v]
+    return [int(s) for s in str(v).replace(" ", "").split(",") if s != ""]
+
+
+def _coerce(key: str, value: Any) -> Any:
+    tag, _ = SCHEMA[key]
+    if value is None or tag == "any":
+        return value
+    if tag == "intlist":
+        return _as_int_list(value)
+    if tag is bool:
+        if isinstance(value, str):
+            return value.strip().lower() in ("1", "true", "yes", "on")
+        return bool(value)
+    if tag is int:
+        if isinstance(value, float) and value != int(value):
+            raise ConfigError(f"{key}: expected an integer, got {value!r}")
+        return int(value)
+    if tag is float:
+        return float(value)
+    if tag is str:
+        return str(value)
+    return value
+
+
+def default_config() -> Dict[str, Any]:
+    return {k: copy.deepcopy(d) for k, (_, d) in SCHEMA.items()}
+
+
+def _merge(base: Dict[str, Any], override: Mapping[str, Any], origin: str) -> None:
+    for k, v in override.items():
+        k = ALIASES.get(k, k)
+        if k in RUNTIME_KEYS:
+            base[k] = v
+            continue
+        if k not in SCHEMA:
+            raise ConfigError(f"unknown config key {k!r} (from {origin})")
+        base[k] = _coerce(k, v)
+
+
+def load_yaml(path: str) -> Dict[str, Any]:
+    with open(path, "r") as f:
+        data = yaml.safe_load(f)
+    return data or {}
+
+
+def build_config(config_path: Optional[str] = None,
+                 extra: Optional[Mapping[str, Any] | str] = None,
+                 default_path: Optional[str] = None) -> Dict[str, Any]:
+    """default <- dataset yaml <- extra (dict or JSON string), with unknown-key checks.
+
+    ``default_path`` defaults to ``params_default.yaml`` next to ``config_path`` (the reference's
+    convention, ``train.py:30``) and falls back to the packaged configs directory.
+    """
+    cfg = default_config()
+    if default_path is None and config_path is not None:
+        cand = os.path.join(os.path.dirname(os.path.abspath(config_path)), "params_default.yaml")
+        default_path = cand if os.path.exists(cand) else None
+    if default_path is None:
+        cand = os.path.join(DEFAULT_CONFIG_DIR, "params_default.yaml")
+        default_path = cand if os.path.exists(cand) else None
+    if default_path is not None:
+        _merge(cfg, load_yaml(default_path), default_path)
+    if config_path is not None:
+        _merge(cfg, load_yaml(config_path), config_path)
+    if extra:
+        if isinstance(extra, str):
+            extra = json.loads(extra)
+        _merge(cfg, extra, "--extra_config")
+    cfg["current_epoch"] = 0
+    return cfg
+
+
+def config_for_dataset(name: str, extra: Optional[Mapping[str, Any] | str] = None) -> Dict[str, Any]:
+    if name not in DATASET_YAML:
+        raise ConfigError(f"unknown dataset {name!r}; known: {sorted(DATASET_YAML)}")
+    return build_config(os.path.join(DEFAULT_CONFIG_DIR, DATASET_YAML[name]), extra)
+
+
+def dump_config(cfg: Mapping[str, Any], path: str) -> None:
+    """Write the serialisable part of the config in the reference's flat yaml format."""
+    out = {}
+    for k, v in cfg.items():
+        if k in SCHEMA:
+            tag, _ = SCHEMA[k]
+            out[k] = ",".join(str(x) for x in v) if tag == "intlist" and isinstance(v, (list, tuple)) else v
+    os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
+    with open(path, "w") as f:
+        yaml.safe_dump(out, f, sort_keys=True)
+
+
+def load_dumped_config(path: str, extra: Optional[Mapping[str, Any] | str] = None) -> Dict[str, Any]:
+    """Read a ``params.yaml`` stored next to a checkpoint (inference entrypoint)."""
+    cfg = default_config()
+    _merge(cfg, load_yaml(path), path)
+    if extra:
+        if isinstance(extra, str):
+            extra = json.loads(extra)
+        _merge(cfg, extra, "--extra_config")
+    cfg["current_epoch"] = 0
+    return cfg
+
+
+def get(cfg: Mapping[str, Any], key: str, default: Any = None) -> Any:
+    key = ALIASES.get(key, key)
+    if key in cfg:
+        return cfg[key]
+    if key in SCHEMA:
+        return copy.deepcopy(SCHEMA[key][1])
+    return default
+
+
+def validate_resolution(cfg: Mapping[str, Any]) -> None:
+    """The reference silently requires H, W % 128 == 0; we size-match upsamples, so
+    any multiple of 32 works, and we say so explicitly otherwise."""
+    h, w = int(cfg["data.img_h"]), int(cfg["data.img_w"])
+    if h % 32 or w % 32:
+        raise ConfigError(f"data.img_h/img_w must be multiples of 32, got {h}x{w}")
+
+
+def known_keys() -> Iterable[str]:
+    return SCHEMA.keys()

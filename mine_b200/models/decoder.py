@@ -1,0 +1,190 @@
+"""Disparity-conditioned MPI decoder, evaluated in *factorised* form.
+
+Capability parity: reference ``network/monodepth2/depth_decoder.py:35-148`` (receptive-field
+extension block, 5-level U-Net over the B*S plane batch conditioned on a 21-d positional encoding
+of the plane disparity, RGB-sigma heads at 4 scales).  The reference tiles every encoder feature
+S times, concatenates the spatially-constant embedding and convolves the lot (717 GFLOP forward
+for LLFF 384x256, S=32, B=2).  Convolution is linear, the skip features are identical for all S
+planes of an image and the embedding channels are constant over space (also under reflection
+padding), hence for every concat-conv
+
+    conv(cat[x_plane, feat, emb]) = conv_p(x_plane) + conv_f(feat)[b] + (sum_taps W_e) emb[b,s]
+
+exactly (SURVEY 2.5 note; verified to 1e-15 in fp64).  We store weights in the reference layout
+``[C_out, C_plane + C_feat + E, 3, 3]`` (checkpoint and optimizer-state compatible) and evaluate
+the three terms separately: 3.1x fewer FLOPs, no S-fold feature tiling, MMA-friendly channel counts
+(256/128/64/32/16 per-plane).  BatchNorm statistics are still taken over the full B*S x H x W
+output, so semantics are unchanged.
+
+Resolution: upsamples are size-matched to their skip tensors, so any H, W multiple of 32 works
+(the reference needs multiples of 128).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..spec.embedder import embedding_dim, positional_encoding
+from .norm import BatchNorm
+
+NUM_CH_DEC = (16, 32, 64, 128, 256)
+SIGMA_FLOOR = 1e-4
+
+
+def _reflect_conv3x3(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
+    return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), weight, bias)
+
+
+class ConvBNLeaky(nn.Sequential):
+    """conv(k, zero pad, no bias) + BN + LeakyReLU(0.1); children named ``0`` / ``1`` like the
+    reference's ``nn.Sequential`` (``depth_decoder.py:17-32``)."""
+
+    def __init__(self, cin: int, cout: int, k: int):
+        super().__init__(nn.Conv2d(cin, cout, k, padding=(k - 1) // 2, bias=False), BatchNorm(cout))
+
+    def forward(self, x):
+        return F.leaky_relu(self[1](self[0](x)), 0.1)
+
+
+class PlaneConvBlock(nn.Module):
+    """ReflPad + Conv3x3(bias) + BN + ELU over ``cat[per-plane, shared skip, embedding]``.
+
+    ``c_plane`` channels vary per plane, ``c_shared`` are per-image features broadcast over S,
+    ``c_emb`` are the per-plane embedding scalars broadcast over space.  Parameter names mirror the
+    reference ``ConvBlock`` (``conv.conv.{weight,bias}``, ``bn.*``).
+    """
+
+    def __init__(self, c_plane: int, c_shared: int, c_emb: int, cout: int):
+        super().__init__()
+        self.c_plane, self.c_shared, self.c_emb, self.cout = c_plane, c_shared, c_emb, cout
+        self.conv = nn.Module()
+        self.conv.conv = nn.Conv2d(c_plane + c_shared + c_emb, cout, 3)
+        self.bn = BatchNorm(cout)
+
+    def split_weights(self):
+        w = self.conv.conv.weight
+        cp, cs = self.c_plane, self.c_shared
+        return w[:, :cp], w[:, cp:cp + cs], w[:, cp + cs:]
+
+    def pre_activation(self, x_plane, shared, emb, b: int, s: int) -> torch.Tensor:
+        """Factorised conv output before BN.  ``x_plane``: [B*S,Cp,h,w] or None; ``shared``:
+        [B,Cs,h,w] or None; ``emb``: [B*S,E] or None."""
+        wp, ws, we = self.split_weights()
+        bias = self.conv.conv.bias
+        y = None
+        if x_plane is not None:
+            y = _reflect_conv3x3(x_plane, wp)
+        if shared is not None:
+            ysh = _reflect_conv3x3(shared, ws)                                   # B,Co,h,w
+            ysh = ysh[:, None].expand(-1, s, -1, -1, -1).reshape(b * s, *ysh.shape[1:])
+            y = ysh if y is None else y + ysh
+        per_plane = bias[None, :]
+        if emb is not None and self.c_emb > 0:
+            per_plane = per_plane + emb.to(we.dtype) @ we.sum(dim=(2, 3)).t()      # BS,Co
+        return y + per_plane[:, :, None, None]
+
+    def forward(self, x_plane, shared, emb, b: int, s: int) -> torch.Tensor:
+        return F.elu(self.bn(self.pre_activation(x_plane, shared, emb, b, s)))
+
+
+class HeadConv(nn.Module):
+    """ReflPad + Conv3x3 C -> 4 (reference ``Conv3x3``; key ``conv.{weight,bias}``)."""
+
+    def __init__(self, cin: int, cout: int = 4):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 3)
+
+    def forward(self, x):
+        return _reflect_conv3x3(x, self.conv.weight, self.conv.bias)
+
+
+def upsample_to(x: torch.Tensor, size: Sequence[int]) -> torch.Tensor:
+    """Nearest upsample to an explicit size (== x2 nearest whenever the reference works)."""
+    if tuple(x.shape[-2:]) == tuple(size):
+        return x
+    return F.interpolate(x, size=tuple(size), mode="nearest")
+
+
+class DepthDecoder(nn.Module):
+    """``DepthDecoder(num_ch_enc, embedder, embedder_out_dim, use_alpha, scales, ...)``.
+
+    ``forward(features, disparity[B,S]) -> {("disp", s): [B,S,4,H/2^s,W/2^s]}`` with channels
+    ``(r,g,b in (0,1) via sigmoid, sigma = |x| + 1e-4)`` (or sigmoid alpha when ``use_alpha``).
+    """
+
+    def __init__(self, num_ch_enc: Sequence[int] = (64, 256, 512, 1024, 2048), embedder=None,
+                 embedder_out_dim: int | None = None, use_alpha: bool = False, scales=range(4),
+                 num_output_channels: int = 4, use_skips: bool = True, sigma_dropout_rate: float = 0.0,
+                 multires: int = 10, **kwargs):
+        super().__init__()
+        self.multires = multires
+        self.E = embedder_out_dim if embedder_out_dim is not None else embedding_dim(multires)
+        self.embedder = embedder
+        self.use_alpha, self.scales = use_alpha, list(scales)
+        self.num_output_channels, self.use_skips = num_output_channels, use_skips
+        self.sigma_dropout_rate = sigma_dropout_rate
+        self.num_ch_enc = list(num_ch_enc)
+        c_top = self.num_ch_enc[-1]
+        self.conv_down1 = ConvBNLeaky(c_top, 512, 1)
+        self.conv_down2 = ConvBNLeaky(512, 256, 3)
+        self.conv_up1 = ConvBNLeaky(256, 256, 3)
+        self.conv_up2 = ConvBNLeaky(256, c_top, 1)
+        self.blocks = nn.ModuleDict()
+        for i in range(4, -1, -1):
+            if i == 4:
+                self.blocks[f"upconv_{i}_0"] = PlaneConvBlock(0, c_top, self.E, NUM_CH_DEC[i])
+            else:
+                self.blocks[f"upconv_{i}_0"] = PlaneConvBlock(NUM_CH_DEC[i + 1], 0, 0, NUM_CH_DEC[i])
+            if use_skips and i > 0:
+                self.blocks[f"upconv_{i}_1"] = PlaneConvBlock(NUM_CH_DEC[i], self.num_ch_enc[i - 1], self.E,
+                                                              NUM_CH_DEC[i])
+            else:
+                self.blocks[f"upconv_{i}_1"] = PlaneConvBlock(NUM_CH_DEC[i], 0, 0, NUM_CH_DEC[i])
+        self.heads = nn.ModuleDict({f"dispconv_{s}": HeadConv(NUM_CH_DEC[s], num_output_channels)
+                                    for s in self.scales})
+
+    # -- pieces shared by the spec path and the CUDA engine ------------------------------------
+    def embed(self, disparity: torch.Tensor) -> torch.Tensor:
+        b, s = disparity.shape
+        x = disparity.reshape(b * s, 1)
+        return self.embedder(x) if self.embedder is not None else positional_encoding(x, self.multires)
+
+    def receptive_field_extension(self, top: torch.Tensor) -> torch.Tensor:
+        d1 = self.conv_down1(F.max_pool2d(top, 3, 2, 1))
+        d2 = self.conv_down2(F.max_pool2d(d1, 3, 2, 1))
+        u1 = self.conv_up1(upsample_to(d2, d1.shape[-2:]))
+        return self.conv_up2(upsample_to(u1, top.shape[-2:]))
+
+    def activate_head(self, raw: torch.Tensor, b: int, s: int) -> torch.Tensor:
+        mpi = raw.reshape(b, s, self.num_output_channels, *raw.shape[-2:])
+        rgb = torch.sigmoid(mpi[:, :, 0:3])
+        sig = torch.sigmoid(mpi[:, :, 3:]) if self.use_alpha else mpi[:, :, 3:].abs() + SIGMA_FLOOR
+        if self.sigma_dropout_rate > 0.0 and self.training:
+            sig = F.dropout2d(sig, p=self.sigma_dropout_rate)
+        return torch.cat([rgb, sig], dim=2)
+
+    def forward(self, input_features: Sequence[torch.Tensor], disparity: torch.Tensor) -> Dict[Tuple[str, int], torch.Tensor]:
+        b, s = disparity.shape
+        emb = self.embed(disparity)                                              # BS,E
+        feats = list(input_features)
+        top = self.receptive_field_extension(feats[-1])
+        outputs: Dict[Tuple[str, int], torch.Tensor] = {}
+        x = None
+        for i in range(4, -1, -1):
+            if i == 4:
+                x = self.blocks["upconv_4_0"](None, top, emb, b, s)
+            else:
+                x = self.blocks[f"upconv_{i}_0"](x, None, None, b, s)
+            if self.use_skips and i > 0:
+                skip = feats[i - 1]
+                x = upsample_to(x, skip.shape[-2:])
+                x = self.blocks[f"upconv_{i}_1"](x, skip, emb, b, s)
+            else:
+                x = upsample_to(x, (x.shape[-2] * 2, x.shape[-1] * 2))
+                x = self.blocks[f"upconv_{i}_1"](x, None, None, b, s)
+            if i in self.scales:
+                outputs[("disp", i)] = self.activate_head(self.heads[f"dispconv_{i}"](x), b, s)
+        return outputs

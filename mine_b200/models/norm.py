@@ -1,0 +1,116 @@
+"""Batch normalisation with cross-replica statistics (SyncBN semantics) and a pluggable reducer.
+
+The reference converts every BatchNorm to ``nn.SyncBatchNorm`` over all ranks
+(``synthesis_task.py:106-113``): 67 layers -> 67 forward all_gathers + 67 backward all_reduces
+of <=16 KiB per step.  Here one module owns both behaviours:
+
+* statistics are reduced through ``reducer(tensor)`` - an in-place SUM all-reduce supplied by
+  ``mine_b200.parallel`` (own NVLink one-shot kernel on CUDA, ``torch.distributed`` on CPU/gloo)
+  - a single fused vector ``[sum(C), sumsq(C), count]`` forward and ``[sum_dy(C), sum_dy_xhat(C)]``
+  backward;
+* parameter / buffer names equal ``nn.BatchNorm2d`` (``weight, bias, running_mean, running_var,
+  num_batches_tracked``) so reference checkpoints load unchanged.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+
+Reducer = Optional[Callable[[torch.Tensor], torch.Tensor]]
+
+
+def _acc_dtype(t: torch.Tensor) -> torch.dtype:
+    return torch.float64 if t.dtype == torch.float64 else torch.float32
+
+
+class _BatchNormTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, reducer):
+        c = x.shape[1]
+        dims = [0] + list(range(2, x.dim()))
+        acc = _acc_dtype(x)
+        xf = x.to(acc)
+        stats = torch.empty(2 * c + 1, dtype=acc, device=x.device)
+        stats[:c] = xf.sum(dim=dims)
+        stats[c:2 * c] = (xf * xf).sum(dim=dims)
+        stats[2 * c] = float(x.numel() // c)
+        if reducer is not None:
+            stats = reducer(stats)
+        n = stats[2 * c]
+        mean = stats[:c] / n
+        var = (stats[c:2 * c] / n - mean * mean).clamp_min(0.0)
+        invstd = torch.rsqrt(var + eps)
+        if running_mean is not None:
+            with torch.no_grad():
+                unbiased = var * (n / (n - 1.0).clamp_min(1.0))
+                running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1 - momentum).add_(unbiased.to(running_var.dtype), alpha=momentum)
+        shape = [1, c] + [1] * (x.dim() - 2)
+        xhat = (xf - mean.view(shape)) * invstd.view(shape)
+        y = xhat * weight.to(acc).view(shape) + bias.to(acc).view(shape)
+        ctx.save_for_backward(x, weight, mean, invstd, n)
+        ctx.reducer = reducer
+        return y.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, invstd, n = ctx.saved_tensors
+        c = x.shape[1]
+        dims = [0] + list(range(2, x.dim()))
+        shape = [1, c] + [1] * (x.dim() - 2)
+        acc = _acc_dtype(x)
+        dyf = dy.to(acc)
+        xhat = (x.to(acc) - mean.view(shape)) * invstd.view(shape)
+        red = torch.empty(2 * c, dtype=acc, device=x.device)
+        red[:c] = dyf.sum(dim=dims)
+        red[c:] = (dyf * xhat).sum(dim=dims)
+        dbias = red[:c].clone()
+        dweight = red[c:].clone()
+        if ctx.reducer is not None:
+            red = ctx.reducer(red)
+        m_dy = (red[:c] / n).view(shape)
+        m_dyx = (red[c:] / n).view(shape)
+        dx = (dyf - m_dy - xhat * m_dyx) * (invstd * weight.to(acc)).view(shape)
+        return dx.to(x.dtype), dweight.to(weight.dtype), dbias.to(weight.dtype), None, None, None, None, None
+
+
+class BatchNorm(nn.Module):
+    """Drop-in for ``nn.BatchNorm2d`` / ``nn.SyncBatchNorm`` (same state-dict keys)."""
+
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self.reducer: Reducer = None
+
+    def scale_shift(self):
+        """Eval-mode affine ``y = x * a + b`` (used by fused kernels and weight folding)."""
+        acc = _acc_dtype(self.weight)
+        a = self.weight.to(acc) * torch.rsqrt(self.running_var.to(acc) + self.eps)
+        return a, self.bias.to(acc) - self.running_mean.to(acc) * a
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            with torch.no_grad():
+                self.num_batches_tracked += 1
+            return _BatchNormTrain.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                         self.momentum, self.eps, self.reducer)
+        a, b = self.scale_shift()
+        shape = [1, self.num_features] + [1] * (x.dim() - 2)
+        acc = _acc_dtype(x)
+        return (x.to(acc) * a.to(acc).view(shape) + b.to(acc).view(shape)).to(x.dtype)
+
+    def extra_repr(self):
+        return f"{self.num_features}, eps={self.eps}, momentum={self.momentum}"
+
+
+def set_stat_reducer(module: nn.Module, reducer: Reducer) -> None:
+    for m in module.modules():
+        if isinstance(m, BatchNorm):
+            m.reducer = reducer
