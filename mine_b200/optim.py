@@ -1,0 +1,115 @@
+"""Adam over a flat parameter arena + MultiStepLR.
+
+Reference: ``torch.optim.Adam(params=[backbone group, decoder group], weight_decay=4e-5)`` with
+``MultiStepLR`` stepped once per epoch (``synthesis_task.py:83-87,116-118,666``).  In torch 1.8
+that is a per-tensor Python loop (221 tensors x ~8 launches).  Here all parameters, gradients and
+both moment buffers are contiguous fp32 arenas, so one step is ONE fused multi-tensor kernel
+(``mine_b200/ops/csrc/adam_fused.cu``) per learning-rate group - or a handful of flat torch ops on
+CPU.  ``state_dict()`` / ``load_state_dict()`` speak ``torch.optim.Adam``'s format (per-parameter
+``step / exp_avg / exp_avg_sq``) so optimizer state is interchangeable with reference checkpoints.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, List, Sequence
+
+import torch
+
+from .parallel.grad_sync import FlatArena
+
+
+class ArenaAdam:
+    def __init__(self, arena: FlatArena, group_sizes: Sequence[int], lrs: Sequence[float],
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        assert sum(group_sizes) == len(arena.params)
+        self.arena = arena
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(arena.data)
+        self.exp_avg_sq = torch.zeros_like(arena.data)
+        self.step_count = 0
+        self.param_groups: List[Dict] = []
+        first = 0
+        for n, lr in zip(group_sizes, lrs):
+            lo, hi = arena.slice_of(first, first + n - 1)
+            if first + n < len(arena.params):
+                hi = arena.offsets[first + n]              # include alignment padding
+            self.param_groups.append({"lr": float(lr), "initial_lr": float(lr), "betas": betas, "eps": eps,
+                                      "weight_decay": weight_decay, "amsgrad": False,
+                                      "params": list(range(first, first + n)), "_range": (lo, hi)})
+            first += n
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.arena.zero_grad()
+
+    @torch.no_grad()
+    def step(self) -> None:
+        self.step_count += 1
+        b1, b2 = self.betas
+        bc1 = 1.0 - b1 ** self.step_count
+        bc2 = 1.0 - b2 ** self.step_count
+        use_kernel = self.arena.data.is_cuda and os.environ.get("MINE_B200_FORCE_SPEC", "0") != "1"
+        for g in self.param_groups:
+            lo, hi = g["_range"]
+            p, gr = self.arena.data[lo:hi], self.arena.grad[lo:hi]
+            m, v = self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi]
+            if use_kernel:
+                from .ops import cuda as C
+                C.fused_adam_(p, gr, m, v, g["lr"], b1, b2, self.eps, self.weight_decay, bc1, bc2)
+                continue
+            grad = gr.add(p, alpha=self.weight_decay) if self.weight_decay != 0 else gr
+            m.mul_(b1).add_(grad, alpha=1 - b1)
+            v.mul_(b2).addcmul_(grad, grad, value=1 - b2)
+            denom = (v.sqrt() / math.sqrt(bc2)).add_(self.eps)
+            p.addcdiv_(m, denom, value=-g["lr"] / bc1)
+
+    # ---- torch.optim.Adam-compatible (de)serialisation --------------------------------------
+    def state_dict(self) -> Dict:
+        state = {}
+        if self.step_count > 0:
+            for i, (p, o) in enumerate(zip(self.arena.params, self.arena.offsets)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[o:o + n].view(p.shape).detach().cpu().clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).detach().cpu().clone()}
+        groups = [{k: v for k, v in g.items() if k != "_range"} for g in self.param_groups]
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        steps = []
+        for i, st in sd.get("state", {}).items():
+            i = int(i)
+            p, o = self.arena.params[i], self.arena.offsets[i]
+            n = p.numel()
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.append(int(float(st["step"])))
+        self.step_count = max(steps) if steps else 0
+        for g, saved in zip(self.param_groups, sd.get("param_groups", [])):
+            g["lr"] = float(saved.get("lr", g["lr"]))
+            g["initial_lr"] = float(saved.get("initial_lr", g["initial_lr"]))
+
+
+class MultiStepLR:
+    """lr = initial_lr * gamma^(#milestones <= epoch); ``step()`` once per epoch."""
+
+    def __init__(self, optimizer, milestones: Sequence[int], gamma: float = 0.1, last_epoch: int = 0):
+        self.optimizer, self.milestones, self.gamma = optimizer, sorted(int(m) for m in milestones), gamma
+        self.last_epoch = last_epoch
+        self._apply()
+
+    def _apply(self):
+        k = sum(1 for m in self.milestones if m <= self.last_epoch)
+        for g in self.optimizer.param_groups:
+            g["lr"] = g.get("initial_lr", g["lr"]) * (self.gamma ** k)
+
+    def step(self):
+        self.last_epoch += 1
+        self._apply()
+
+    def state_dict(self):
+        return {"last_epoch": self.last_epoch}
+
+    def load_state_dict(self, sd):
+        self.last_epoch = int(sd["last_epoch"])
+        self._apply()

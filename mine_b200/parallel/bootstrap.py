@@ -1,0 +1,95 @@
+"""Process bootstrap: one process per GPU, ``torch.distributed`` for rendezvous only.
+
+Reference: ``train.py:59-63,152`` (``CUDA_VISIBLE_DEVICES`` = one GPU, ``init_process_group("nccl")``,
+one ``dist.barrier()``).  Here the device is selected with ``torch.cuda.set_device(LOCAL_RANK)``
+(all GPUs stay visible, which peer-to-peer mapping over NVLink needs), NCCL is used on CUDA and
+gloo on CPU, and a world of 1 needs no process group at all.
+"""
+from __future__ import annotations
+
+import datetime
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class DistContext:
+    rank: int = 0
+    world_size: int = 1
+    local_rank: int = 0
+    device: torch.device = torch.device("cpu")
+    backend: Optional[str] = None
+
+    @property
+    def is_main(self) -> bool:
+        return self.rank == 0
+
+    @property
+    def distributed(self) -> bool:
+        return self.world_size > 1
+
+
+def init_distributed(local_rank: Optional[int] = None, backend: Optional[str] = None, device: Optional[str] = None,
+                     timeout_s: int = 600) -> DistContext:
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if local_rank is None:
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    use_cuda = torch.cuda.is_available() and device != "cpu"
+    if use_cuda:
+        torch.cuda.set_device(local_rank % max(torch.cuda.device_count(), 1))
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = torch.device("cpu")
+    if backend is None:
+        backend = "nccl" if use_cuda else "gloo"
+    if world > 1 or "MASTER_ADDR" in os.environ and os.environ.get("MINE_FORCE_PG", "0") == "1":
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            kw = {}
+            if backend == "nccl":
+                kw["device_id"] = dev
+            dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                    timeout=datetime.timedelta(seconds=timeout_s), **kw)
+    return DistContext(rank, world, local_rank, dev, backend if dist.is_initialized() else None)
+
+
+def barrier() -> None:
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def shutdown() -> None:
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def broadcast_module_state(*modules: torch.nn.Module, src: int = 0) -> None:
+    """One-off parameter + buffer broadcast from ``src`` (what the DDP constructor does, SURVEY N4:
+    this is how the rank-0-only checkpoint restore reaches the other ranks).  Cold path -> NCCL/gloo."""
+    if world_size() == 1:
+        return
+    for m in modules:
+        for t in list(m.parameters()) + list(m.buffers()):
+            dist.broadcast(t.data, src=src)
+
+
+def broadcast_object(obj, src: int = 0):
+    if world_size() == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]

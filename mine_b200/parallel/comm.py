@@ -1,0 +1,74 @@
+"""Communicators: SUM all-reduce for small statistic vectors and for flat gradient buckets.
+
+Two implementations behind one interface:
+
+* :class:`TorchDistComm` - ``torch.distributed`` collectives (NCCL on GPU, gloo on CPU).  This is
+  the *baseline* path (what the reference does through DDP/SyncBN) and the CPU test path.
+* :class:`mine_b200.parallel.p2p.P2PComm` - our own sm_100a kernels over NVLink peer memory
+  (one-shot all-reduce for <=64 KiB statistic vectors, two-shot reduce-scatter/all-gather fused
+  with the 1/world scaling for gradient buckets).  Selected with ``engine.comm: p2p`` on CUDA.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+class Communicator:
+    world_size: int = 1
+    rank: int = 0
+    name = "local"
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place SUM over ranks on the current stream; returns ``t``."""
+        return t
+
+    def allreduce_mean_(self, t: torch.Tensor, stream=None) -> torch.Tensor:
+        """In-place mean over ranks (gradient buckets): SUM fused with the 1/world scaling."""
+        return t
+
+    def barrier(self) -> None:
+        pass
+
+    def close(self) -> None:
+        pass
+
+
+class TorchDistComm(Communicator):
+    name = "torch.distributed"
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def allreduce_sum_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allreduce_mean_(self, t, stream=None):
+        if stream is not None and t.is_cuda:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                t.mul_(1.0 / self.world_size)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.mul_(1.0 / self.world_size)
+        return t
+
+    def barrier(self):
+        dist.barrier(group=self.group)
+
+
+def make_communicator(kind: str = "auto", device: Optional[torch.device] = None) -> Communicator:
+    """``kind``: ``p2p`` (own NVLink kernels; CUDA only), ``nccl``/``torch`` (library baseline),
+    ``auto`` (p2p on CUDA, torch.distributed otherwise)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return Communicator()
+    on_cuda = device is not None and torch.device(device).type == "cuda"
+    if kind in ("p2p", "auto") and on_cuda:
+        from .p2p import P2PComm
+        return P2PComm(device)
+    return TorchDistComm()

@@ -1,0 +1,1 @@
+from mine_b200.spec.losses import edge_aware_loss, edge_aware_loss_v2, psnr  # noqa: F401

@@ -1,0 +1,220 @@
+"""Single-image -> novel-view video (inference entry point).
+
+Same CLI as upstream ``visualizations/image_to_video.py``: ``--checkpoint_path --data_path
+--output_dir --gpus [--extra_config]``; reads ``params.yaml`` next to the checkpoint; writes
+``<img>_{zoom-in,swing}_{rgb,disp}.mp4``.  One encoder/decoder pass builds the S-plane MPI, then the
+per-pose loop is ONE fused warp+composite kernel per frame on a packed MPI; disparity
+normalisation and uint8 conversion happen on the device and frames return through a pinned ring
+buffer (the reference moves ~1.5-2 GiB through HBM in ~60 launches + a host sync per frame,
+SURVEY 3.5).  Trajectory presets exist for every dataset name (upstream raises for LLFF/flowers/dtu).
+"""
+import argparse
+import logging
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from mine_b200 import config as cfglib  # noqa: E402
+from mine_b200 import geometry as geo  # noqa: E402
+from mine_b200.ops import api as ops  # noqa: E402
+from mine_b200.utils.misc import disparity_normalization_vis  # noqa: E402
+from mine_b200.utils.video_io import img_tensor_to_np, write_img_to_disk, write_video  # noqa: E402,F401
+
+TRAJECTORY_PRESETS = {
+    # dataset -> (x range, y range, z range) for (zoom-in, swing)
+    "kitti_raw": ([0.0, -0.8], [0.0, -0.0], [-1.5, -1.0]),
+    "realestate10k": ([0.0, -0.16], [0.0, -0.0], [-0.30, -0.2]),
+    "nyu": ([0.0, -0.16], [0.0, -0.0], [-0.30, -0.2]),
+    "ibims": ([0.0, -0.16], [0.0, -0.0], [-0.30, -0.2]),
+    "llff": ([0.0, -0.16], [0.0, -0.0], [-0.30, -0.2]),
+    "flowers": ([0.0, -0.05], [0.0, -0.0], [-0.10, -0.06]),
+    "dtu": ([0.0, -0.16], [0.0, -0.0], [-0.30, -0.2]),
+}
+
+
+def path_planning(num_frames, x, y, z, path_type="", s=0.3):
+    """Camera-centre trajectories: 'straight-line' (quadratic through the midpoint),
+    'double-straight-line' (out to -p and back from s*p), 'circle' (two turns in x/y, one in z)."""
+    if path_type == "straight-line":
+        t = np.linspace(0, 1, num_frames)
+        # quadratic interpolation through (0, p/2, p) at t = (0, .5, 1) is the straight line t*p
+        xs, ys, zs = t * x, t * y, t * z
+    elif path_type == "double-straight-line":
+        t = np.linspace(0, 1, int(num_frames * 0.5))
+        a, b = np.array([s * x, s * y, s * z]), np.array([-x, -y, -z])
+        half = a[None] * (1 - t[:, None]) + b[None] * t[:, None]
+        full = np.concatenate([half, half[::-1]], 0)
+        xs, ys, zs = full[:, 0], full[:, 1], full[:, 2]
+    elif path_type == "circle":
+        ph = np.arange(-2.0, 2.0, 4.0 / num_frames)
+        xs, ys, zs = np.cos(ph * np.pi) * x, np.sin(ph * np.pi) * y, np.cos(ph * np.pi / 2.0) * z - s * z
+    else:
+        raise ValueError(f"unknown path type {path_type!r}")
+    return xs, ys, zs
+
+
+class VideoGenerator:
+    def __init__(self, synthesis_task, config, logger, img, output_dir):
+        self.synthesis_task, self.config, self.logger, self.output_dir = synthesis_task, config, logger, output_dir
+        task = synthesis_task
+        task.global_step = config["training.eval_interval"]
+        task.backbone.eval()
+        task.decoder.eval()
+        dev = task.device
+        if isinstance(img, np.ndarray):
+            import cv2
+            img = cv2.resize(img, (config["data.img_w"], config["data.img_h"]), interpolation=cv2.INTER_LINEAR)
+            img = torch.from_numpy(img).to(dev).permute(2, 0, 1).contiguous()[None].float() / 255.0
+        self.img = img.to(dev)
+        self.tgts_poses, self.traj_config = self.traj_generation()
+        with torch.no_grad():
+            self.infer_network()
+
+    def infer_network(self):
+        task = self.synthesis_task
+        B, _, H, W = self.img.shape
+        self.K = self.compute_camera_intrinsic(H, W).to(self.img.device)[None]
+        self.K_inv = geo.inv3x3(self.K)
+        n_pt = 128
+        ones = torch.ones((B, 3, n_pt))
+        src = {"img": self.img, "K": self.K, "K_inv": self.K_inv, "xyzs": ones}
+        tgt = {"img": self.img[:, None], "K": self.K[:, None], "K_inv": self.K_inv[:, None], "xyzs": ones[:, None],
+               "G_src_tgt": torch.eye(4)[None, None]}
+        task.set_data((src, tgt))
+        endpoints = task.network_forward()
+        self.disparity_all_src = endpoints["disparity_all_src"]
+        packed = ops.pack_mpi(endpoints["mpi_all_src_list"][0])
+        src_out = ops.render_src(packed, self.disparity_all_src, self.K_inv, self.img,
+                                 bool(self.config.get("mpi.use_alpha", False)),
+                                 bool(cfglib.get(self.config, "mpi.is_bg_depth_inf", False)), blend=True)
+        self.mpi_packed = src_out["mpi"].contiguous()            # source-blended colours + sigma
+        view = ops.unpack_mpi(self.mpi_packed)
+        self.mpi_all_rgb_src, self.mpi_all_sigma_src = view[:, :, 0:3], view[:, :, 3:]
+
+    def traj_generation(self):
+        name = self.config["data.name"]
+        if name not in TRAJECTORY_PRESETS:
+            raise RuntimeError("Unsupported dataset.")
+        xr, yr, zr = TRAJECTORY_PRESETS[name]
+        traj = {"fps": 30, "num_frames": 90, "x_shift_range": xr, "y_shift_range": yr, "z_shift_range": zr,
+                "traj_types": ["double-straight-line", "circle"], "name": ["zoom-in", "swing"]}
+        poses = []
+        for i, kind in enumerate(traj["traj_types"]):
+            xs, ys, zs = path_planning(traj["num_frames"], xr[i], yr[i], zr[i], path_type=kind)
+            seq = []
+            for x, y, z in zip(xs, ys, zs):
+                g = np.eye(4)
+                g[:3, 3] = (x, y, z)
+                seq.append(g)
+            poses.append(seq)
+        return poses, traj
+
+    @staticmethod
+    def compute_camera_intrinsic(H, W, fov=90):
+        return geo.fov_intrinsics(H, W, fov)
+
+    def render_pose(self, G_tgt_src_np):
+        """Render one pose and write ``0_0_tgt_{rgb,disp}.png`` (fixed version of upstream's dead helper)."""
+        G = torch.from_numpy(np.asarray(G_tgt_src_np, dtype=np.float32))[None].to(self.img.device)
+        with torch.no_grad():
+            res = self.synthesis_task.render_novel_view(self.mpi_all_rgb_src, self.mpi_all_sigma_src,
+                                                        self.disparity_all_src, G, self.K_inv, self.K, scale=0,
+                                                        scale_factor=torch.ones(1, device=G.device))
+        write_img_to_disk(res["tgt_imgs_syn"], 0, "tgt_rgb", self.output_dir)
+        write_img_to_disk(disparity_normalization_vis(res["tgt_disparity_syn"]), 0, "tgt_disp", self.output_dir)
+        return res
+
+    def render_frames(self, poses):
+        """Yield ``(rgb uint8 HxWx3, disparity uint8 HxW)`` per pose; D2H is async through pinned buffers."""
+        dev = self.img.device
+        H, W = self.img.shape[-2:]
+        ring = [(torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() if dev.type == "cuda" else None,
+                 torch.empty((H, W), dtype=torch.uint8).pin_memory() if dev.type == "cuda" else None) for _ in range(2)]
+        pending = None
+        one = torch.ones(1, device=dev)
+        G_all = torch.from_numpy(np.stack(poses).astype(np.float32)).to(dev)
+        for i in range(G_all.shape[0]):
+            res = self.synthesis_task.render_novel_view(self.mpi_all_rgb_src, self.mpi_all_sigma_src,
+                                                        self.disparity_all_src, G_all[i:i + 1], self.K_inv, self.K,
+                                                        scale=0, scale_factor=one)
+            rgb8 = (res["tgt_imgs_syn"][0].clamp(0, 1) * 255.0).round().to(torch.uint8).permute(1, 2, 0)
+            disp8 = (disparity_normalization_vis(res["tgt_disparity_syn"])[0, 0] * 255.0).round().to(torch.uint8)
+            if dev.type == "cuda":
+                slot = ring[i % 2]
+                slot[0].copy_(rgb8, non_blocking=True)
+                slot[1].copy_(disp8, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[0].synchronize()
+                    yield pending[1][0].numpy().copy(), pending[1][1].numpy().copy()
+                pending = (ev, slot)
+            else:
+                yield rgb8.numpy(), disp8.numpy()
+        if pending is not None:
+            pending[0].synchronize()
+            yield pending[1][0].numpy().copy(), pending[1][1].numpy().copy()
+
+    def render_video(self, output_name):
+        import cv2
+        outputs = []
+        for i, name in enumerate(self.traj_config["name"]):
+            self.logger.info("Processing trajectory %s ..." % name)
+            rgbs, disps = [], []
+            for rgb, disp in self.render_frames(self.tgts_poses[i]):
+                rgbs.append(rgb)
+                disps.append(cv2.cvtColor(cv2.applyColorMap(disp, cv2.COLORMAP_HOT), cv2.COLOR_BGR2RGB))
+            fps = self.traj_config["fps"]
+            outputs.append(write_video(os.path.join(self.output_dir, f"{output_name}_{name}_rgb.mp4"), rgbs, fps))
+            outputs.append(write_video(os.path.join(self.output_dir, f"{output_name}_{name}_disp.mp4"), disps, fps))
+        return outputs
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser(description="Inference")
+    p.add_argument("--checkpoint_path", type=str, required=True)
+    p.add_argument("--data_path", type=str, required=True)
+    p.add_argument("--output_dir", type=str, required=True)
+    p.add_argument("--gpus", type=str, required=True)
+    p.add_argument("--extra_config", type=str, default="{}")
+    args = p.parse_args(argv)
+
+    if args.gpus not in ("", "cpu"):
+        os.environ["CUDA_VISIBLE_DEVICES"] = args.gpus
+    config = cfglib.load_dumped_config(os.path.join(os.path.dirname(args.checkpoint_path), "params.yaml"),
+                                       args.extra_config)
+    config.update({"global_rank": 0, "training.pretrained_checkpoint_path": args.checkpoint_path,
+                   "mpi.disparity_list": np.zeros((1), dtype=np.float32), "tb_writer": None,
+                   "data.val_set_path": args.data_path, "data.per_gpu_batch_size": 1, "engine.resume": False})
+    os.makedirs(args.output_dir, exist_ok=True)
+    config["local_workspace"] = args.output_dir
+    config["log_file"] = os.path.join(args.output_dir, "inference.log")
+    logger = logging.getLogger("graph_view_synthesis_inference")
+    logger.setLevel(logging.INFO)
+    h = logging.StreamHandler(sys.stdout)
+    h.setFormatter(logging.Formatter("[%(asctime)s %(filename)s] %(message)s"))
+    logger.handlers, logger.propagate = [h], False
+    config["logger"] = logger
+    if args.gpus == "cpu" or not torch.cuda.is_available():
+        config["device"] = torch.device("cpu")
+
+    import cv2
+    from synthesis_task import SynthesisTask
+    task = SynthesisTask(config=config, logger=logger, is_val=True)
+    img = cv2.imread(args.data_path, cv2.IMREAD_COLOR)
+    if img is None:
+        raise FileNotFoundError(args.data_path)
+    img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    gen = VideoGenerator(task, config, logger, img, args.output_dir)
+    with torch.no_grad():
+        outs = gen.render_video(os.path.splitext(os.path.basename(args.data_path))[0])
+    logger.info("wrote: %s" % outs)
+
+
+if __name__ == "__main__":
+    main()
