@@ -101,7 +101,11 @@ def isolated_reference_imports(root: str):
     ref_mods = getattr(isolated_reference_imports, "_ref_modules", {}).get(root, {})
     sys.modules.update(ref_mods)
     saved_path = list(sys.path)
-    sys.path.insert(0, root)
+    repo = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    # this repository ships same-named shim packages (regular packages would shadow the reference's
+    # namespace packages), so hide the repo root while importing the oracle
+    sys.path[:] = [root] + [p for p in sys.path
+                            if os.path.abspath(p or os.getcwd()) not in (repo, os.path.abspath(root))]
     real_sync = torch.cuda.synchronize
     if not torch.cuda.is_available():
         torch.cuda.synchronize = lambda *a, **k: None

@@ -23,10 +23,11 @@ class ModelRunner:
         self.backbone, self.decoder, self.config = backbone, decoder, config
         self.device = torch.device(device)
         mode = os.environ.get("MINE_B200_CONV", config.get("engine.conv", "auto"))
-        if self.device.type != "cuda" or os.environ.get("MINE_B200_FORCE_SPEC", "0") == "1":
+        if self.device.type != "cuda":
             mode = "spec"
         elif mode == "auto":
-            mode = "tcgen05"
+            from .ops import conv_engine
+            mode = "tcgen05" if conv_engine.AVAILABLE else "cudnn"
         self.mode = mode
         self._engine = None
         if mode == "tcgen05":
@@ -36,11 +37,15 @@ class ModelRunner:
     def predict(self, src_imgs: torch.Tensor, disparity: torch.Tensor) -> List[torch.Tensor]:
         if self.mode == "tcgen05":
             return self._engine.predict(src_imgs, disparity)
+        if self.mode == "cudnn_fp32":          # library convs in fp32 (numerics tests)
+            feats = self.backbone(src_imgs)
+            out = self.decoder(feats, disparity)
+            return [ops.pack_mpi(out[("disp", s)]).contiguous() for s in range(4)]
         if self.mode == "cudnn":
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 feats = self.backbone(src_imgs.contiguous(memory_format=torch.channels_last))
                 out = self.decoder(feats, disparity)
-            return [ops.pack_mpi(out[("disp", s)].float()) for s in range(4)]
+            return [ops.pack_mpi(out[("disp", s)].float()).contiguous() for s in range(4)]
         feats = self.backbone(src_imgs)
         out = self.decoder(feats, disparity)
         return [ops.pack_mpi(out[("disp", s)]) for s in range(4)]

@@ -1,0 +1,153 @@
+// Python bindings: tensor validation + raw-pointer launchers on the current CUDA stream.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "kernels.h"
+
+namespace {
+
+inline void check_f32(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kFloat, name, " must be float32");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+}
+inline const float* opt_ptr(const c10::optional<at::Tensor>& t, const char* name) {
+  if (!t.has_value() || !t->defined()) return nullptr;
+  check_f32(*t, name);
+  return t->data_ptr<float>();
+}
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+// mpi: [B,S,H,W,4]
+std::vector<at::Tensor> render_src_fwd(const at::Tensor& mpi, const at::Tensor& disparity, const at::Tensor& kinv,
+                                       const c10::optional<at::Tensor>& src_img, bool use_alpha, bool blend,
+                                       int64_t depth_mode, bool write_mpi) {
+  check_f32(mpi, "mpi"); check_f32(disparity, "disparity"); check_f32(kinv, "k_src_inv");
+  TORCH_CHECK(mpi.dim() == 5 && mpi.size(4) == 4, "mpi must be [B,S,H,W,4]");
+  const int B = mpi.size(0), S = mpi.size(1), H = mpi.size(2), W = mpi.size(3);
+  TORCH_CHECK(S <= 256, "at most 256 planes");
+  c10::cuda::CUDAGuard guard(mpi.device());
+  auto o = mpi.options();
+  at::Tensor rgb = at::empty({B, 3, H, W}, o), depth = at::empty({B, 1, H, W}, o), wsum = at::empty({B, 1, H, W}, o);
+  at::Tensor out_mpi = write_mpi ? at::empty_like(mpi) : at::Tensor();
+  mine::launch_render_src_fwd(mpi.data_ptr<float>(), disparity.data_ptr<float>(), kinv.data_ptr<float>(),
+                              opt_ptr(src_img, "src_img"), write_mpi ? out_mpi.data_ptr<float>() : nullptr,
+                              rgb.data_ptr<float>(), depth.data_ptr<float>(), wsum.data_ptr<float>(), B, S, H, W,
+                              use_alpha, blend, (int)depth_mode, cur_stream());
+  return {rgb, depth, wsum, out_mpi};
+}
+
+at::Tensor render_src_bwd(const at::Tensor& mpi, const at::Tensor& disparity, const at::Tensor& kinv,
+                          const c10::optional<at::Tensor>& src_img, const at::Tensor& depth_fwd,
+                          const at::Tensor& wsum_fwd, const c10::optional<at::Tensor>& g_rgb,
+                          const c10::optional<at::Tensor>& g_depth, const c10::optional<at::Tensor>& g_blend,
+                          bool use_alpha, bool blend, int64_t depth_mode) {
+  check_f32(mpi, "mpi");
+  const int B = mpi.size(0), S = mpi.size(1), H = mpi.size(2), W = mpi.size(3);
+  c10::cuda::CUDAGuard guard(mpi.device());
+  at::Tensor g_mpi = at::empty_like(mpi);
+  mine::launch_render_src_bwd(mpi.data_ptr<float>(), disparity.data_ptr<float>(), kinv.data_ptr<float>(),
+                              opt_ptr(src_img, "src_img"), depth_fwd.data_ptr<float>(), wsum_fwd.data_ptr<float>(),
+                              opt_ptr(g_rgb, "g_rgb"), opt_ptr(g_depth, "g_depth"), opt_ptr(g_blend, "g_blend"),
+                              g_mpi.data_ptr<float>(), B, S, H, W, use_alpha, blend, (int)depth_mode, cur_stream());
+  return g_mpi;
+}
+
+std::vector<at::Tensor> render_tgt_fwd(const at::Tensor& mpi, const at::Tensor& disparity, const at::Tensor& g_tgt_src,
+                                       const at::Tensor& kinv, const at::Tensor& ktgt, bool use_alpha,
+                                       int64_t depth_mode) {
+  check_f32(mpi, "mpi"); check_f32(disparity, "disparity"); check_f32(g_tgt_src, "G_tgt_src");
+  check_f32(kinv, "k_src_inv"); check_f32(ktgt, "k_tgt");
+  TORCH_CHECK(mpi.dim() == 5 && mpi.size(4) == 4, "mpi must be [B,S,H,W,4]");
+  const int B = mpi.size(0), S = mpi.size(1), H = mpi.size(2), W = mpi.size(3);
+  c10::cuda::CUDAGuard guard(mpi.device());
+  auto o = mpi.options();
+  at::Tensor rgb = at::empty({B, 3, H, W}, o), depth = at::empty({B, 1, H, W}, o), mask = at::empty({B, 1, H, W}, o),
+             wsum = at::empty({B, 1, H, W}, o);
+  mine::launch_render_tgt_fwd(mpi.data_ptr<float>(), disparity.data_ptr<float>(), g_tgt_src.data_ptr<float>(),
+                              kinv.data_ptr<float>(), ktgt.data_ptr<float>(), rgb.data_ptr<float>(),
+                              depth.data_ptr<float>(), mask.data_ptr<float>(), wsum.data_ptr<float>(), B, S, H, W,
+                              use_alpha, (int)depth_mode, cur_stream());
+  return {rgb, depth, mask, wsum};
+}
+
+at::Tensor render_tgt_bwd(const at::Tensor& mpi, const at::Tensor& disparity, const at::Tensor& g_tgt_src,
+                          const at::Tensor& kinv, const at::Tensor& ktgt, const at::Tensor& rgb_fwd,
+                          const at::Tensor& depth_fwd, const at::Tensor& wsum_fwd,
+                          const c10::optional<at::Tensor>& g_rgb, const c10::optional<at::Tensor>& g_depth,
+                          bool use_alpha, int64_t depth_mode) {
+  check_f32(mpi, "mpi");
+  const int B = mpi.size(0), S = mpi.size(1), H = mpi.size(2), W = mpi.size(3);
+  c10::cuda::CUDAGuard guard(mpi.device());
+  at::Tensor g_mpi = at::zeros_like(mpi);
+  mine::launch_render_tgt_bwd(mpi.data_ptr<float>(), disparity.data_ptr<float>(), g_tgt_src.data_ptr<float>(),
+                              kinv.data_ptr<float>(), ktgt.data_ptr<float>(), rgb_fwd.data_ptr<float>(),
+                              depth_fwd.data_ptr<float>(), wsum_fwd.data_ptr<float>(), opt_ptr(g_rgb, "g_rgb"),
+                              opt_ptr(g_depth, "g_depth"), g_mpi.data_ptr<float>(), B, S, H, W, use_alpha,
+                              (int)depth_mode, cur_stream());
+  return g_mpi;
+}
+
+std::vector<at::Tensor> ssim_fwd(const at::Tensor& a, const at::Tensor& b, bool need_grad) {
+  check_f32(a, "a"); check_f32(b, "b");
+  TORCH_CHECK(a.dim() == 4 && a.sizes() == b.sizes(), "ssim expects two [N,C,H,W] tensors");
+  const int planes = a.size(0) * a.size(1), H = a.size(2), W = a.size(3);
+  c10::cuda::CUDAGuard guard(a.device());
+  at::Tensor sum = at::zeros({}, a.options());
+  at::Tensor partials = need_grad ? at::empty({planes, 3, H, W}, a.options()) : at::Tensor();
+  mine::launch_ssim_fwd(a.data_ptr<float>(), b.data_ptr<float>(), sum.data_ptr<float>(),
+                        need_grad ? partials.data_ptr<float>() : nullptr, planes, H, W, cur_stream());
+  return {sum, partials};
+}
+
+at::Tensor ssim_bwd(const at::Tensor& a, const at::Tensor& b, const at::Tensor& partials, const at::Tensor& scale,
+                    double scale_mul) {
+  check_f32(a, "a"); check_f32(b, "b"); check_f32(partials, "partials"); check_f32(scale, "scale");
+  const int planes = a.size(0) * a.size(1), H = a.size(2), W = a.size(3);
+  c10::cuda::CUDAGuard guard(a.device());
+  at::Tensor grad = at::empty_like(a);
+  mine::launch_ssim_bwd(a.data_ptr<float>(), b.data_ptr<float>(), partials.data_ptr<float>(), scale.data_ptr<float>(),
+                        (float)scale_mul, grad.data_ptr<float>(), planes, H, W, cur_stream());
+  return grad;
+}
+
+std::vector<at::Tensor> masked_l1_fwd(const at::Tensor& a, const at::Tensor& b, const at::Tensor& mask, double thr,
+                                      bool need_grad) {
+  check_f32(a, "a"); check_f32(b, "b"); check_f32(mask, "mask");
+  const int B = a.size(0), C = a.size(1), HW = a.size(2) * a.size(3);
+  c10::cuda::CUDAGuard guard(a.device());
+  at::Tensor sum = at::zeros({}, a.options());
+  at::Tensor sign = need_grad ? at::empty_like(a) : at::Tensor();
+  mine::launch_masked_l1_fwd(a.data_ptr<float>(), b.data_ptr<float>(), mask.data_ptr<float>(), (float)thr,
+                             sum.data_ptr<float>(), need_grad ? sign.data_ptr<float>() : nullptr, B, C, HW,
+                             cur_stream());
+  return {sum, sign};
+}
+
+void fused_adam(at::Tensor p, const at::Tensor& g, at::Tensor m, at::Tensor v, double lr, double beta1, double beta2,
+                double eps, double wd, double bc1, double bc2) {
+  check_f32(p, "p"); check_f32(g, "g"); check_f32(m, "m"); check_f32(v, "v");
+  c10::cuda::CUDAGuard guard(p.device());
+  mine::launch_fused_adam(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                          p.numel(), (float)lr, (float)beta1, (float)beta2, (float)eps, (float)wd, (float)bc1,
+                          (float)bc2, cur_stream());
+}
+
+}  // namespace
+
+void register_conv(pybind11::module_& m);     // conv_bindings.cpp
+void register_comm(pybind11::module_& m);     // comm_bindings.cpp
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("render_src_fwd", &render_src_fwd);
+  m.def("render_src_bwd", &render_src_bwd);
+  m.def("render_tgt_fwd", &render_tgt_fwd);
+  m.def("render_tgt_bwd", &render_tgt_bwd);
+  m.def("ssim_fwd", &ssim_fwd);
+  m.def("ssim_bwd", &ssim_bwd);
+  m.def("masked_l1_fwd", &masked_l1_fwd);
+  m.def("fused_adam", &fused_adam);
+  register_conv(m);
+  register_comm(m);
+}

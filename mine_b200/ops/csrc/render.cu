@@ -1,0 +1,555 @@
+// Fused MPI rendering kernels for sm_100a (forward + analytic backward).
+//
+// What the reference does per scale with ~60 ATen/cuBLAS launches and several full-size temporaries
+// (meshgrid repeat + batched GEMM for xyz, 7-channel cat, grid_sample on NCHW,
+// cumprod, weighted sums, cuSOLVER inverse with host syncs) is here:
+//
+//   render_src_fwd : one pass over the packed MPI [B,S,H,W,4]: transmittance scan in registers,
+//                    source-colour blending, composite rgb / depth, writes the blended MPI.
+//   render_tgt_fwd : per target pixel, per plane: closed-form inverse homography (computed once per
+//                    block into shared memory), validity mask, border-clamped bilinear gather of one
+//                    16-byte texel per tap, analytic target-frame xyz, z<0 gating, front-to-back composite.
+//   *_bwd          : gradients by recomputation; the reverse-order transmittance dependency is
+//                    resolved with suffix = total - prefix sums, so no S-sized state is stored and no
+//                    cumprod tensor ever exists.  The target backward scatters with 16-byte vector
+//                    reductions (red.global.add.v4.f32) into the blended-MPI gradient.
+//
+// Semantics: mine_b200/spec/render.py (tested against it and against the upstream ops).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace mine {
+
+constexpr float kLastDelta = 1.0e3f;
+constexpr float kTEps = 1.0e-6f;
+constexpr float kWEps = 1.0e-5f;
+constexpr float kBgDepth = 1000.0f;
+constexpr int kMaxPlanes = 256;
+
+struct Mat3 {
+  float m[9];
+};
+
+__device__ __forceinline__ Mat3 load_mat3(const float* p) {
+  Mat3 r;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.m[i] = p[i];
+  return r;
+}
+
+__device__ __forceinline__ Mat3 matmul3(const Mat3& a, const Mat3& b) {
+  Mat3 r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      r.m[i * 3 + j] = a.m[i * 3] * b.m[j] + a.m[i * 3 + 1] * b.m[3 + j] + a.m[i * 3 + 2] * b.m[6 + j];
+  return r;
+}
+
+__device__ __forceinline__ Mat3 inverse3(const Mat3& a) {
+  const float* m = a.m;
+  float c00 = m[4] * m[8] - m[5] * m[7];
+  float c01 = m[2] * m[7] - m[1] * m[8];
+  float c02 = m[1] * m[5] - m[2] * m[4];
+  float c10 = m[5] * m[6] - m[3] * m[8];
+  float c11 = m[0] * m[8] - m[2] * m[6];
+  float c12 = m[2] * m[3] - m[0] * m[5];
+  float c20 = m[3] * m[7] - m[4] * m[6];
+  float c21 = m[1] * m[6] - m[0] * m[7];
+  float c22 = m[0] * m[4] - m[1] * m[3];
+  float det = m[0] * c00 + m[1] * c10 + m[2] * c20;
+  float inv = 1.0f / det;
+  Mat3 r;
+  r.m[0] = c00 * inv; r.m[1] = c01 * inv; r.m[2] = c02 * inv;
+  r.m[3] = c10 * inv; r.m[4] = c11 * inv; r.m[5] = c12 * inv;
+  r.m[6] = c20 * inv; r.m[7] = c21 * inv; r.m[8] = c22 * inv;
+  return r;
+}
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// source view
+// ------------------------------------------------------------------------------------------------
+template <bool kAlpha, bool kBlend, int kDepthMode>
+__global__ void __launch_bounds__(256) render_src_fwd_kernel(
+    const float4* __restrict__ mpi, const float* __restrict__ disparity, const float* __restrict__ kinv,
+    const float* __restrict__ src_img, float4* __restrict__ mpi_out, float* __restrict__ rgb_out,
+    float* __restrict__ depth_out, float* __restrict__ wsum_out, int S, int H, int W) {
+  __shared__ float s_depth[kMaxPlanes];
+  const int b = blockIdx.z;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) s_depth[i] = 1.0f / disparity[b * S + i];
+  __syncthreads();
+  const int HW = H * W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const int v = pix / W, u = pix - v * W;
+  const float* k = kinv + b * 9;
+  const float rx = k[0] * u + k[1] * v + k[2];
+  const float ry = k[3] * u + k[4] * v + k[5];
+  const float rz = k[6] * u + k[7] * v + k[8];
+  const float rlen = sqrtf(rx * rx + ry * ry + rz * rz);
+  float ir = 0.f, ig = 0.f, ib = 0.f;
+  if (kBlend) {
+    ir = src_img[(b * 3 + 0) * HW + pix];
+    ig = src_img[(b * 3 + 1) * HW + pix];
+    ib = src_img[(b * 3 + 2) * HW + pix];
+  }
+  const float4* p = mpi + (size_t)b * S * HW + pix;
+  float4* po = mpi_out ? mpi_out + (size_t)b * S * HW + pix : nullptr;
+  float A = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_z = 0.f, acc_w = 0.f;
+  float4 t = ldg4(p);
+  for (int s = 0; s < S; ++s) {
+    float4 nxt = (s + 1 < S) ? ldg4(p + (size_t)(s + 1) * HW) : t;   // software prefetch of plane s+1
+    const float d = s_depth[s];
+    float w, a_next;
+    if (kAlpha) {
+      w = t.w * A;
+      a_next = A * (1.0f - t.w);
+    } else {
+      const float delta = (s + 1 < S) ? rlen * fabsf(s_depth[s + 1] - d) : kLastDelta;
+      const float T = __expf(-t.w * delta);
+      w = A * (1.0f - T);
+      a_next = A * (T + kTEps);
+    }
+    float cr = t.x, cg = t.y, cb = t.z;
+    if (kBlend && !kAlpha) {
+      cr = A * ir + (1.0f - A) * cr;
+      cg = A * ig + (1.0f - A) * cg;
+      cb = A * ib + (1.0f - A) * cb;
+    }
+    acc_r += w * cr; acc_g += w * cg; acc_b += w * cb;
+    acc_z += w * (rz * d);
+    acc_w += w;
+    if (po) po[(size_t)s * HW] = make_float4(cr, cg, cb, t.w);
+    A = a_next;
+    t = nxt;
+  }
+  rgb_out[(b * 3 + 0) * HW + pix] = acc_r;
+  rgb_out[(b * 3 + 1) * HW + pix] = acc_g;
+  rgb_out[(b * 3 + 2) * HW + pix] = acc_b;
+  float depth;
+  if (kDepthMode == 2) depth = acc_z;
+  else if (kDepthMode == 1) depth = acc_z + (1.0f - acc_w) * kBgDepth;
+  else depth = acc_z / (acc_w + kWEps);
+  depth_out[b * HW + pix] = depth;
+  if (wsum_out) wsum_out[b * HW + pix] = acc_w;
+}
+
+// Backward of the source pass.  Inputs: upstream grads of the composited rgb (optional), depth
+// (optional) and of the blended MPI (optional; produced by the target pass).  Two sweeps over S:
+// sweep 1 accumulates Q = sum_s a_s A_s (a_s = dL/dA_s), sweep 2 emits gradients with
+// suffix_j = Q - prefix_j.
+template <bool kAlpha, bool kBlend, int kDepthMode>
+__global__ void __launch_bounds__(256) render_src_bwd_kernel(
+    const float4* __restrict__ mpi, const float* __restrict__ disparity, const float* __restrict__ kinv,
+    const float* __restrict__ src_img, const float* __restrict__ depth_fwd, const float* __restrict__ wsum_fwd,
+    const float* __restrict__ g_rgb, const float* __restrict__ g_depth, const float4* __restrict__ g_blend,
+    float4* __restrict__ g_mpi, int S, int H, int W) {
+  __shared__ float s_depth[kMaxPlanes];
+  const int b = blockIdx.z;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) s_depth[i] = 1.0f / disparity[b * S + i];
+  __syncthreads();
+  const int HW = H * W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const int v = pix / W, u = pix - v * W;
+  const float* k = kinv + b * 9;
+  const float rx = k[0] * u + k[1] * v + k[2];
+  const float ry = k[3] * u + k[4] * v + k[5];
+  const float rz = k[6] * u + k[7] * v + k[8];
+  const float rlen = sqrtf(rx * rx + ry * ry + rz * rz);
+  float ir = 0.f, ig = 0.f, ib = 0.f;
+  if (kBlend) {
+    ir = src_img[(b * 3 + 0) * HW + pix];
+    ig = src_img[(b * 3 + 1) * HW + pix];
+    ib = src_img[(b * 3 + 2) * HW + pix];
+  }
+  float Gr = 0.f, Gg = 0.f, Gb = 0.f, Gd = 0.f;
+  if (g_rgb) {
+    Gr = g_rgb[(b * 3 + 0) * HW + pix];
+    Gg = g_rgb[(b * 3 + 1) * HW + pix];
+    Gb = g_rgb[(b * 3 + 2) * HW + pix];
+  }
+  if (g_depth) Gd = g_depth[b * HW + pix];
+  // d depth / d w_s = dz_scale * z_s + dz_off
+  float dz_scale, dz_off;
+  if (kDepthMode == 2) { dz_scale = 1.0f; dz_off = 0.0f; }
+  else if (kDepthMode == 1) { dz_scale = 1.0f; dz_off = -kBgDepth; }
+  else {
+    const float inv = 1.0f / (wsum_fwd[b * HW + pix] + kWEps);
+    dz_scale = inv; dz_off = -depth_fwd[b * HW + pix] * inv;
+  }
+  const float4* p = mpi + (size_t)b * S * HW + pix;
+  const float4* pg = g_blend ? g_blend + (size_t)b * S * HW + pix : nullptr;
+  float4* po = g_mpi + (size_t)b * S * HW + pix;
+
+  // sweep 1: Q
+  float Q = 0.f;
+  {
+    float A = 1.0f;
+    for (int s = 0; s < S; ++s) {
+      const float4 t = ldg4(p + (size_t)s * HW);
+      float4 gb = pg ? ldg4(pg + (size_t)s * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float d = s_depth[s];
+      float alpha, a_next;
+      if (kAlpha) { alpha = t.w; a_next = A * (1.0f - t.w); }
+      else {
+        const float delta = (s + 1 < S) ? rlen * fabsf(s_depth[s + 1] - d) : kLastDelta;
+        const float T = __expf(-t.w * delta);
+        alpha = 1.0f - T; a_next = A * (T + kTEps);
+      }
+      const float w = A * alpha;
+      float cr = t.x, cg = t.y, cb = t.z;
+      if (kBlend && !kAlpha) { cr = A * ir + (1.f - A) * cr; cg = A * ig + (1.f - A) * cg; cb = A * ib + (1.f - A) * cb; }
+      const float dLdw = Gr * cr + Gg * cg + Gb * cb + Gd * (dz_scale * rz * d + dz_off);
+      float a_s = dLdw * alpha;
+      if (kBlend && !kAlpha) {
+        const float qr = Gr * w + gb.x, qg = Gg * w + gb.y, qb = Gb * w + gb.z;
+        a_s += qr * (ir - t.x) + qg * (ig - t.y) + qb * (ib - t.z);
+      }
+      Q += a_s * A;
+      A = a_next;
+    }
+  }
+  // sweep 2: gradients
+  {
+    float A = 1.0f, prefix = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float4 t = ldg4(p + (size_t)s * HW);
+      float4 gb = pg ? ldg4(pg + (size_t)s * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float d = s_depth[s];
+      float alpha, a_next, T = 0.f, delta = 0.f;
+      if (kAlpha) { alpha = t.w; a_next = A * (1.0f - t.w); }
+      else {
+        delta = (s + 1 < S) ? rlen * fabsf(s_depth[s + 1] - d) : kLastDelta;
+        T = __expf(-t.w * delta);
+        alpha = 1.0f - T; a_next = A * (T + kTEps);
+      }
+      const float w = A * alpha;
+      float cr = t.x, cg = t.y, cb = t.z;
+      if (kBlend && !kAlpha) { cr = A * ir + (1.f - A) * cr; cg = A * ig + (1.f - A) * cg; cb = A * ib + (1.f - A) * cb; }
+      const float dLdw = Gr * cr + Gg * cg + Gb * cb + Gd * (dz_scale * rz * d + dz_off);
+      const float qr = Gr * w + gb.x, qg = Gg * w + gb.y, qb = Gb * w + gb.z;
+      float a_s = dLdw * alpha;
+      float keep = 1.0f;
+      if (kBlend && !kAlpha) {
+        a_s += qr * (ir - t.x) + qg * (ig - t.y) + qb * (ib - t.z);
+        keep = 1.0f - A;
+      }
+      prefix += a_s * A;
+      const float suffix = (s + 1 < S) ? (Q - prefix) : 0.0f;
+      float gsig;
+      if (kAlpha) {
+        gsig = dLdw * A - suffix / (1.0f - t.w) + gb.w;
+      } else {
+        const float dLdT = -dLdw * A + suffix / (T + kTEps);
+        gsig = dLdT * (-delta * T) + gb.w;
+      }
+      po[(size_t)s * HW] = make_float4(qr * keep, qg * keep, qb * keep, gsig);
+      A = a_next;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// target view
+// ------------------------------------------------------------------------------------------------
+struct PlaneGeom {      // per (image, plane), built once per block in shared memory
+  float h[9];           // inverse homography: target pixel -> source pixel (homogeneous)
+};
+
+struct TgtBlockGeom {
+  float m[9];           // R * K_src^-1
+  float t[3];
+};
+
+__device__ __forceinline__ void build_plane_geometry(const float* __restrict__ g_tgt_src /*4x4*/,
+                                                     const float* __restrict__ kinv, const float* __restrict__ ktgt,
+                                                     const float* __restrict__ disparity, int S, PlaneGeom* s_geom,
+                                                     float* s_depth, TgtBlockGeom* s_blk) {
+  Mat3 R, Ki = load_mat3(kinv), Kt = load_mat3(ktgt);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R.m[i * 3 + j] = g_tgt_src[i * 4 + j];
+  const float tx = g_tgt_src[3], ty = g_tgt_src[7], tz = g_tgt_src[11];
+  if (threadIdx.x == 0) {
+    Mat3 M = matmul3(R, Ki);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s_blk->m[i] = M.m[i];
+    s_blk->t[0] = tx; s_blk->t[1] = ty; s_blk->t[2] = tz;
+  }
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float depth = 1.0f / disparity[s];
+    s_depth[s] = depth;
+    Mat3 Rt = R;                       // R + t n^T / d,  n = (0,0,1)
+    Rt.m[2] += tx / depth; Rt.m[5] += ty / depth; Rt.m[8] += tz / depth;
+    Mat3 Hts = matmul3(Kt, matmul3(Rt, Ki));
+    Mat3 Hst = inverse3(Hts);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s_geom[s].h[i] = Hst.m[i];
+  }
+}
+
+struct Sample {
+  float xc, yc;         // clamped continuous source coordinates
+  int valid;
+  float px, py, pz;     // xyz in the target frame
+};
+
+__device__ __forceinline__ Sample plane_sample(const PlaneGeom& g, const TgtBlockGeom& blk, float depth, float x,
+                                               float y, int W, int H) {
+  Sample o;
+  const float hx = g.h[0] * x + g.h[1] * y + g.h[2];
+  const float hy = g.h[3] * x + g.h[4] * y + g.h[5];
+  const float hz = g.h[6] * x + g.h[7] * y + g.h[8];
+  const float sx = hx / hz, sy = hy / hz;
+  o.valid = (sx > -1.0f) && (sx < (float)W) && (sy > -1.0f) && (sy < (float)H);
+  o.xc = fminf(fmaxf(sx, 0.0f), (float)(W - 1));
+  o.yc = fminf(fmaxf(sy, 0.0f), (float)(H - 1));
+  if (!(sx == sx)) o.xc = 0.0f;       // NaN guards (degenerate homography): sample the corner, invalid
+  if (!(sy == sy)) o.yc = 0.0f;
+  const float qx = blk.m[0] * o.xc + blk.m[1] * o.yc + blk.m[2];
+  const float qy = blk.m[3] * o.xc + blk.m[4] * o.yc + blk.m[5];
+  const float qz = blk.m[6] * o.xc + blk.m[7] * o.yc + blk.m[8];
+  o.px = qx * depth + blk.t[0];
+  o.py = qy * depth + blk.t[1];
+  o.pz = qz * depth + blk.t[2];
+  return o;
+}
+
+struct Taps {
+  int i00, i01, i10, i11;
+  float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ Taps make_taps(float xc, float yc, int W, int H) {
+  Taps t;
+  const float x0f = floorf(xc), y0f = floorf(yc);
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  const float fx = xc - x0f, fy = yc - y0f;
+  t.i00 = y0 * W + x0; t.i01 = y0 * W + x1; t.i10 = y1 * W + x0; t.i11 = y1 * W + x1;
+  t.w00 = (1.f - fx) * (1.f - fy); t.w01 = fx * (1.f - fy); t.w10 = (1.f - fx) * fy; t.w11 = fx * fy;
+  return t;
+}
+
+__device__ __forceinline__ float4 bilerp(const float4* __restrict__ plane, const Taps& t) {
+  const float4 a = ldg4(plane + t.i00), b = ldg4(plane + t.i01), c = ldg4(plane + t.i10), d = ldg4(plane + t.i11);
+  float4 r;
+  r.x = a.x * t.w00 + b.x * t.w01 + c.x * t.w10 + d.x * t.w11;
+  r.y = a.y * t.w00 + b.y * t.w01 + c.y * t.w10 + d.y * t.w11;
+  r.z = a.z * t.w00 + b.z * t.w01 + c.z * t.w10 + d.z * t.w11;
+  r.w = a.w * t.w00 + b.w * t.w01 + c.w * t.w10 + d.w * t.w11;
+  return r;
+}
+
+template <bool kAlpha, int kDepthMode>
+__global__ void __launch_bounds__(256) render_tgt_fwd_kernel(
+    const float4* __restrict__ mpi, const float* __restrict__ disparity, const float* __restrict__ g_tgt_src,
+    const float* __restrict__ kinv, const float* __restrict__ ktgt, float* __restrict__ rgb_out,
+    float* __restrict__ depth_out, float* __restrict__ mask_out, float* __restrict__ wsum_out, int S, int H, int W) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PlaneGeom* s_geom = reinterpret_cast<PlaneGeom*>(smem_raw);
+  float* s_depth = reinterpret_cast<float*>(s_geom + S);
+  TgtBlockGeom* s_blk = reinterpret_cast<TgtBlockGeom*>(s_depth + S);
+  const int b = blockIdx.z;
+  build_plane_geometry(g_tgt_src + b * 16, kinv + b * 9, ktgt + b * 9, disparity + b * S, S, s_geom, s_depth, s_blk);
+  __syncthreads();
+  const int HW = H * W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const int yi = pix / W, xi = pix - yi * W;
+  const float x = (float)xi, y = (float)yi;
+  const TgtBlockGeom blk = *s_blk;
+  const float4* base = mpi + (size_t)b * S * HW;
+
+  float A = 1.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_z = 0.f, acc_w = 0.f, mask = 0.f;
+  Sample cur = plane_sample(s_geom[0], blk, s_depth[0], x, y, W, H);
+  for (int s = 0; s < S; ++s) {
+    Sample nxt = cur;
+    if (s + 1 < S) nxt = plane_sample(s_geom[s + 1], blk, s_depth[s + 1], x, y, W, H);
+    const Taps tp = make_taps(cur.xc, cur.yc, W, H);
+    const float4 v = bilerp(base + (size_t)s * HW, tp);
+    const float sig = (cur.pz >= 0.0f) ? v.w : 0.0f;
+    float w, a_next;
+    if (kAlpha) {
+      w = sig * A; a_next = A * (1.0f - sig);
+    } else {
+      float delta = kLastDelta;
+      if (s + 1 < S) {
+        const float dx = nxt.px - cur.px, dy = nxt.py - cur.py, dz = nxt.pz - cur.pz;
+        delta = sqrtf(dx * dx + dy * dy + dz * dz);
+      }
+      const float T = __expf(-sig * delta);
+      w = A * (1.0f - T); a_next = A * (T + kTEps);
+    }
+    acc_r += w * v.x; acc_g += w * v.y; acc_b += w * v.z;
+    acc_z += w * cur.pz; acc_w += w;
+    mask += (float)cur.valid;
+    A = a_next;
+    cur = nxt;
+  }
+  rgb_out[(b * 3 + 0) * HW + pix] = acc_r;
+  rgb_out[(b * 3 + 1) * HW + pix] = acc_g;
+  rgb_out[(b * 3 + 2) * HW + pix] = acc_b;
+  float depth;
+  if (kDepthMode == 2) depth = acc_z;
+  else if (kDepthMode == 1) depth = acc_z + (1.0f - acc_w) * kBgDepth;
+  else depth = acc_z / (acc_w + kWEps);
+  depth_out[b * HW + pix] = depth;
+  mask_out[b * HW + pix] = mask;
+  if (wsum_out) wsum_out[b * HW + pix] = acc_w;
+}
+
+// Backward of the target pass: single forward-order sweep; suffix sums from the saved totals
+// (rgb, depth, wsum).  Writes into g_mpi (pre-zeroed) with 16-byte vector reductions.
+template <bool kAlpha, int kDepthMode>
+__global__ void __launch_bounds__(256) render_tgt_bwd_kernel(
+    const float4* __restrict__ mpi, const float* __restrict__ disparity, const float* __restrict__ g_tgt_src,
+    const float* __restrict__ kinv, const float* __restrict__ ktgt, const float* __restrict__ rgb_fwd,
+    const float* __restrict__ depth_fwd, const float* __restrict__ wsum_fwd, const float* __restrict__ g_rgb,
+    const float* __restrict__ g_depth, float4* __restrict__ g_mpi, int S, int H, int W) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PlaneGeom* s_geom = reinterpret_cast<PlaneGeom*>(smem_raw);
+  float* s_depth = reinterpret_cast<float*>(s_geom + S);
+  TgtBlockGeom* s_blk = reinterpret_cast<TgtBlockGeom*>(s_depth + S);
+  const int b = blockIdx.z;
+  build_plane_geometry(g_tgt_src + b * 16, kinv + b * 9, ktgt + b * 9, disparity + b * S, S, s_geom, s_depth, s_blk);
+  __syncthreads();
+  const int HW = H * W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const int yi = pix / W, xi = pix - yi * W;
+  const float x = (float)xi, y = (float)yi;
+  const TgtBlockGeom blk = *s_blk;
+  const float4* base = mpi + (size_t)b * S * HW;
+  float4* gbase = g_mpi + (size_t)b * S * HW;
+
+  float Gr = 0.f, Gg = 0.f, Gb = 0.f, Gd = 0.f;
+  if (g_rgb) {
+    Gr = g_rgb[(b * 3 + 0) * HW + pix]; Gg = g_rgb[(b * 3 + 1) * HW + pix]; Gb = g_rgb[(b * 3 + 2) * HW + pix];
+  }
+  if (g_depth) Gd = g_depth[b * HW + pix];
+  const float tot_r = rgb_fwd[(b * 3 + 0) * HW + pix], tot_g = rgb_fwd[(b * 3 + 1) * HW + pix],
+              tot_b = rgb_fwd[(b * 3 + 2) * HW + pix];
+  const float wsum = wsum_fwd[b * HW + pix];
+  const float depth = depth_fwd[b * HW + pix];
+  float dz_scale, dz_off, tot_z;
+  if (kDepthMode == 2) { dz_scale = 1.f; dz_off = 0.f; tot_z = depth; }
+  else if (kDepthMode == 1) { dz_scale = 1.f; dz_off = -kBgDepth; tot_z = depth - (1.0f - wsum) * kBgDepth; }
+  else { const float inv = 1.0f / (wsum + kWEps); dz_scale = inv; dz_off = -depth * inv; tot_z = depth * (wsum + kWEps); }
+  // total of sum_s dLdw_s * w_s
+  const float Q = Gr * tot_r + Gg * tot_g + Gb * tot_b + Gd * (dz_scale * tot_z + dz_off * wsum);
+
+  float A = 1.f, prefix = 0.f;
+  Sample cur = plane_sample(s_geom[0], blk, s_depth[0], x, y, W, H);
+  for (int s = 0; s < S; ++s) {
+    Sample nxt = cur;
+    if (s + 1 < S) nxt = plane_sample(s_geom[s + 1], blk, s_depth[s + 1], x, y, W, H);
+    const Taps tp = make_taps(cur.xc, cur.yc, W, H);
+    const float4 v = bilerp(base + (size_t)s * HW, tp);
+    const bool front = cur.pz >= 0.0f;
+    const float sig = front ? v.w : 0.0f;
+    float w, a_next, T = 0.f, delta = kLastDelta;
+    if (kAlpha) { w = sig * A; a_next = A * (1.0f - sig); }
+    else {
+      if (s + 1 < S) {
+        const float dx = nxt.px - cur.px, dy = nxt.py - cur.py, dz = nxt.pz - cur.pz;
+        delta = sqrtf(dx * dx + dy * dy + dz * dz);
+      }
+      T = __expf(-sig * delta);
+      w = A * (1.0f - T); a_next = A * (T + kTEps);
+    }
+    const float dLdw = Gr * v.x + Gg * v.y + Gb * v.z + Gd * (dz_scale * cur.pz + dz_off);
+    prefix += dLdw * w;
+    const float suffix = (s + 1 < S) ? (Q - prefix) : 0.0f;
+    float gsig;
+    if (kAlpha) gsig = dLdw * A - suffix / (1.0f - sig);
+    else gsig = (-dLdw * A + suffix / (T + kTEps)) * (-delta * T);
+    if (!front) gsig = 0.0f;
+    const float4 gv = make_float4(Gr * w, Gg * w, Gb * w, gsig);
+    float4* gp = gbase + (size_t)s * HW;
+    if (tp.w00 != 0.f) red_add_v4(gp + tp.i00, make_float4(gv.x * tp.w00, gv.y * tp.w00, gv.z * tp.w00, gv.w * tp.w00));
+    if (tp.w01 != 0.f) red_add_v4(gp + tp.i01, make_float4(gv.x * tp.w01, gv.y * tp.w01, gv.z * tp.w01, gv.w * tp.w01));
+    if (tp.w10 != 0.f) red_add_v4(gp + tp.i10, make_float4(gv.x * tp.w10, gv.y * tp.w10, gv.z * tp.w10, gv.w * tp.w10));
+    if (tp.w11 != 0.f) red_add_v4(gp + tp.i11, make_float4(gv.x * tp.w11, gv.y * tp.w11, gv.z * tp.w11, gv.w * tp.w11));
+    A = a_next;
+    cur = nxt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+#define DEPTH_SWITCH(MODE_, ...)            \
+  do {                                      \
+    if ((MODE_) == 0) { constexpr int DM = 0; __VA_ARGS__; }      \
+    else if ((MODE_) == 1) { constexpr int DM = 1; __VA_ARGS__; } \
+    else { constexpr int DM = 2; __VA_ARGS__; }                   \
+  } while (0)
+
+void launch_render_src_fwd(const float* mpi, const float* disparity, const float* kinv, const float* src_img,
+                           float* mpi_out, float* rgb, float* depth, float* wsum, int B, int S, int H, int W,
+                           bool use_alpha, bool blend, int depth_mode, cudaStream_t stream) {
+  dim3 block(256), grid((H * W + 255) / 256, 1, B);
+  const bool bl = blend && !use_alpha && src_img != nullptr;
+#define SRC_FWD_ARGS <<<grid, block, 0, stream>>>((const float4*)mpi, disparity, kinv, src_img, (float4*)mpi_out, rgb, depth, wsum, S, H, W)
+  DEPTH_SWITCH(depth_mode,
+               if (use_alpha) render_src_fwd_kernel<true, false, DM> SRC_FWD_ARGS;
+               else if (bl) render_src_fwd_kernel<false, true, DM> SRC_FWD_ARGS;
+               else render_src_fwd_kernel<false, false, DM> SRC_FWD_ARGS);
+#undef SRC_FWD_ARGS
+}
+
+void launch_render_src_bwd(const float* mpi, const float* disparity, const float* kinv, const float* src_img,
+                           const float* depth_fwd, const float* wsum_fwd, const float* g_rgb, const float* g_depth,
+                           const float* g_blend, float* g_mpi, int B, int S, int H, int W, bool use_alpha, bool blend,
+                           int depth_mode, cudaStream_t stream) {
+  dim3 block(256), grid((H * W + 255) / 256, 1, B);
+  const bool bl = blend && !use_alpha && src_img != nullptr;
+#define SRC_BWD_ARGS <<<grid, block, 0, stream>>>((const float4*)mpi, disparity, kinv, src_img, depth_fwd, wsum_fwd, g_rgb, g_depth, (const float4*)g_blend, (float4*)g_mpi, S, H, W)
+  DEPTH_SWITCH(depth_mode,
+               if (use_alpha) render_src_bwd_kernel<true, false, DM> SRC_BWD_ARGS;
+               else if (bl) render_src_bwd_kernel<false, true, DM> SRC_BWD_ARGS;
+               else render_src_bwd_kernel<false, false, DM> SRC_BWD_ARGS);
+#undef SRC_BWD_ARGS
+}
+
+static size_t tgt_smem_bytes(int S) { return S * (sizeof(PlaneGeom) + sizeof(float)) + sizeof(TgtBlockGeom) + 16; }
+
+void launch_render_tgt_fwd(const float* mpi, const float* disparity, const float* g_tgt_src, const float* kinv,
+                           const float* ktgt, float* rgb, float* depth, float* mask, float* wsum, int B, int S, int H,
+                           int W, bool use_alpha, int depth_mode, cudaStream_t stream) {
+  dim3 block(256), grid((H * W + 255) / 256, 1, B);
+  const size_t smem = tgt_smem_bytes(S);
+#define TGT_FWD_ARGS <<<grid, block, smem, stream>>>((const float4*)mpi, disparity, g_tgt_src, kinv, ktgt, rgb, depth, mask, wsum, S, H, W)
+  DEPTH_SWITCH(depth_mode,
+               if (use_alpha) render_tgt_fwd_kernel<true, DM> TGT_FWD_ARGS;
+               else render_tgt_fwd_kernel<false, DM> TGT_FWD_ARGS);
+#undef TGT_FWD_ARGS
+}
+
+void launch_render_tgt_bwd(const float* mpi, const float* disparity, const float* g_tgt_src, const float* kinv,
+                           const float* ktgt, const float* rgb_fwd, const float* depth_fwd, const float* wsum_fwd,
+                           const float* g_rgb, const float* g_depth, float* g_mpi, int B, int S, int H, int W,
+                           bool use_alpha, int depth_mode, cudaStream_t stream) {
+  dim3 block(256), grid((H * W + 255) / 256, 1, B);
+  const size_t smem = tgt_smem_bytes(S);
+#define TGT_BWD_ARGS <<<grid, block, smem, stream>>>((const float4*)mpi, disparity, g_tgt_src, kinv, ktgt, rgb_fwd, depth_fwd, wsum_fwd, g_rgb, g_depth, (float4*)g_mpi, S, H, W)
+  DEPTH_SWITCH(depth_mode,
+               if (use_alpha) render_tgt_bwd_kernel<true, DM> TGT_BWD_ARGS;
+               else render_tgt_bwd_kernel<false, DM> TGT_BWD_ARGS);
+#undef TGT_BWD_ARGS
+}
+
+}  // namespace mine

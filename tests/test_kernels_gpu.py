@@ -1,0 +1,181 @@
+"""sm_100a kernels vs the PyTorch fp32/fp64 specification (forward + backward)."""
+import math
+
+import pytest
+import torch
+
+from mine_b200 import geometry as geo
+from mine_b200.spec import losses as L
+from mine_b200.spec import render as R
+from mine_b200.spec import sampling as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _cams(b, h, w, seed, rot, trans, device):
+    g = torch.Generator().manual_seed(seed)
+    f = 0.8 * w
+    k = torch.tensor([[f, 0, w / 2], [0, f * 1.1, h / 2], [0, 0, 1.0]]).repeat(b, 1, 1)
+    ang = (torch.rand(b, 3, generator=g) - 0.5) * 2 * rot
+    gm = torch.eye(4).repeat(b, 1, 1)
+    for i, a in enumerate(ang):
+        cx, sx, cy, sy, cz, sz = [f(float(v)) for v in a for f in (math.cos, math.sin)]
+        rx = torch.tensor([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        ry = torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        rz = torch.tensor([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]])
+        gm[i, :3, :3] = rz @ ry @ rx
+    gm[:, :3, 3] = (torch.rand(b, 3, generator=g) - 0.5) * 2 * trans
+    return k.to(device), gm.to(device)
+
+
+def _mpi(b, s, h, w, seed, device, alpha=False):
+    g = torch.Generator().manual_seed(seed)
+    mpi = torch.rand(b, s, h, w, 4, generator=g)
+    if not alpha:
+        mpi[..., 3] = mpi[..., 3] * 3 + 1e-4
+    else:
+        mpi[..., 3] = mpi[..., 3] * 0.9
+    disp = S.stratified_disparity_linspace(b, s, 1.0, 0.01, generator=g)
+    return mpi.to(device), disp.to(device)
+
+
+def _spec_src(mpi, disp, kinv, img, alpha, bg, blend):
+    u = mpi.permute(0, 1, 4, 2, 3)
+    o = R.render_src(u[:, :, :3], u[:, :, 3:], disp, kinv, img, alpha, bg, blend)
+    blended = torch.cat([o["mpi_rgb"], u[:, :, 3:]], 2).permute(0, 1, 3, 4, 2)
+    return o["rgb"], o["depth"], blended
+
+
+@pytest.mark.parametrize("b,s,h,w", [(2, 8, 32, 48), (1, 32, 64, 96), (2, 5, 40, 72)])
+@pytest.mark.parametrize("alpha,bg,blend", [(False, False, True), (False, True, True), (False, False, False), (True, False, True)])
+def test_render_src_matches_spec(b, s, h, w, alpha, bg, blend):
+    from mine_b200.ops import cuda as C
+    dev = torch.device("cuda")
+    mpi, disp = _mpi(b, s, h, w, 0, dev, alpha)
+    k, _ = _cams(b, h, w, 1, 0.0, 0.0, dev)
+    kinv = geo.inv3x3(k)
+    img = torch.rand(b, 3, h, w, device=dev)
+    mpi_a = mpi.clone().requires_grad_(True)
+    mpi_b = mpi.double().clone().requires_grad_(True)
+    out = C.render_src(mpi_a, disp, kinv, img, alpha, bg, blend)
+    rgb_s, depth_s, blended_s = _spec_src(mpi_b, disp.double(), kinv.double(), img.double(), alpha, bg, blend)
+    assert torch.allclose(out["rgb"], rgb_s.float(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(out["depth"], depth_s.float(), rtol=2e-4, atol=1e-4)
+    assert torch.allclose(out["mpi"], blended_s.float(), rtol=1e-4, atol=1e-5)
+    g = torch.Generator().manual_seed(5)
+    wr, wd, wm = (torch.rand(out["rgb"].shape, generator=g).to(dev), torch.rand(out["depth"].shape, generator=g).to(dev),
+                  torch.rand(out["mpi"].shape, generator=g).to(dev))
+    wd = wd / depth_s.detach().float().abs().clamp(min=1.0)        # keep depth-term gradients O(1)
+    ((out["rgb"] * wr).sum() + (out["depth"] * wd).sum() + (out["mpi"] * wm).sum()).backward()
+    ((rgb_s * wr.double()).sum() + (depth_s * wd.double()).sum() + (blended_s * wm.double()).sum()).backward()
+    ga, gb = mpi_a.grad, mpi_b.grad.float()
+    err = (ga - gb).abs().max().item()
+    assert err <= 2e-3 * gb.abs().max().item() + 1e-5, (err, gb.abs().max().item())
+
+
+@pytest.mark.parametrize("b,s,h,w", [(2, 8, 32, 48), (1, 32, 64, 96), (2, 6, 128, 384)])
+@pytest.mark.parametrize("rot,trans", [(0.0, 0.0), (0.03, 0.1), (0.3, 0.6)])
+@pytest.mark.parametrize("alpha,bg", [(False, False), (False, True), (True, False)])
+def test_render_tgt_matches_spec(b, s, h, w, rot, trans, alpha, bg):
+    from mine_b200.ops import cuda as C
+    dev = torch.device("cuda")
+    mpi, disp = _mpi(b, s, h, w, 2, dev, alpha)
+    k, g = _cams(b, h, w, 3, rot, trans, dev)
+    kinv = geo.inv3x3(k)
+    mpi_a = mpi.clone().requires_grad_(True)
+    mpi_b = mpi.double().clone().requires_grad_(True)
+    rgb, depth, mask = C.render_tgt(mpi_a, disp, g, kinv, k, alpha, bg)
+    u = mpi_b.permute(0, 1, 4, 2, 3)
+    rgb_s, depth_s, mask_s = R.render_tgt(u[:, :, :3], u[:, :, 3:], disp.double(), g.double(), kinv.double(), k.double(), alpha, bg)
+    # pixels whose sample sits within 1e-3 px of a validity / integer boundary may legitimately differ
+    frac_bad_mask = (mask != mask_s.float()).float().mean().item()
+    assert frac_bad_mask < 2e-3
+    close = (rgb - rgb_s.float()).abs() <= 2e-3 + 1e-3 * rgb_s.float().abs()
+    assert close.float().mean().item() > 0.999
+    dclose = (depth - depth_s.float()).abs() <= 1e-3 * depth_s.float().abs() + 1e-3
+    assert dclose.float().mean().item() > 0.999
+    gen = torch.Generator().manual_seed(7)
+    wr = torch.rand(rgb.shape, generator=gen).to(dev)
+    wd = torch.rand(depth.shape, generator=gen).to(dev) / depth_s.detach().float().abs().clamp(min=1.0)
+    ((rgb * wr).sum() + (depth * wd).sum()).backward()
+    ((rgb_s * wr.double()).sum() + (depth_s * wd.double()).sum()).backward()
+    ga, gb = mpi_a.grad, mpi_b.grad.float()
+    rel = (ga - gb).abs().sum().item() / (gb.abs().sum().item() + 1e-12)
+    assert rel < 5e-3, rel
+    if rot == 0.0 and trans == 0.0:
+        assert torch.all(mask == s)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 32, 48), (1, 3, 256, 384), (2, 3, 50, 70)])
+def test_ssim_matches_spec(shape):
+    from mine_b200.ops import cuda as C
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand(shape, generator=g).to(dev)
+    b = (a + 0.1 * torch.randn(shape, generator=g).to(dev)).clamp(0, 1)
+    a1 = a.clone().requires_grad_(True)
+    a2 = a.double().clone().requires_grad_(True)
+    v1 = C.ssim(a1, b)
+    v2 = L.ssim(a2, b.double())
+    assert abs(v1.item() - v2.item()) < 2e-5
+    (1 - v1).backward()
+    (1 - v2).backward()
+    err = (a1.grad - a2.grad.float()).abs().max().item()
+    assert err <= 1e-3 * a2.grad.abs().max().item() + 1e-9
+
+
+def test_masked_l1_matches_spec():
+    from mine_b200.ops import cuda as C
+    dev = torch.device("cuda")
+    a = torch.rand(2, 3, 40, 56, device=dev, requires_grad=True)
+    a2 = a.detach().clone().requires_grad_(True)
+    b = torch.rand(2, 3, 40, 56, device=dev)
+    m = torch.randint(0, 5, (2, 1, 40, 56), device=dev).float()
+    v1 = C.masked_l1(a, b, m, 2.0)
+    v2 = L.masked_l1(a2, b, m, 2.0)
+    assert abs(v1.item() - v2.item()) < 1e-6
+    v1.backward(), v2.backward()
+    assert torch.allclose(a.grad, a2.grad, atol=1e-9)
+
+
+def test_fused_adam_matches_torch():
+    from mine_b200.ops import cuda as C
+    dev = torch.device("cuda")
+    n = 100003
+    p = torch.randn(n, device=dev)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=4e-5)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(n, device=dev)
+        ref.grad = g.clone()
+        opt.step()
+        C.fused_adam_(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 4e-5, 1 - 0.9 ** step, 1 - 0.999 ** step)
+    assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_task_step_kernels_vs_spec(monkeypatch):
+    """Whole training step: kernel path == spec path on the same weights and batch (cuDNN convs in both)."""
+    import copy
+    from mine_b200 import config as C
+    from mine_b200.data.synthetic import config_batch
+    from mine_b200.task import SynthesisTask
+    cfg = C.config_for_dataset("llff", {"data.img_w": 128, "data.img_h": 128, "mpi.num_bins_coarse": 8,
+                                         "data.visible_point_count": 64, "model.imagenet_pretrained": False,
+                                         "mpi.fix_disparity": True, "loss.smoothness_lambda_v2": 0.01})
+    monkeypatch.setenv("MINE_B200_CONV", "cudnn_fp32")
+    torch.manual_seed(0)
+    t1 = SynthesisTask(copy.deepcopy(cfg), None)
+    items = config_batch(cfg)
+    monkeypatch.setenv("MINE_B200_FORCE_SPEC", "1")
+    torch.manual_seed(0)
+    t2 = SynthesisTask(copy.deepcopy(cfg), None)
+    t2.arena.data.copy_(t1.arena.data)
+    l2 = t2.train_step(items)
+    monkeypatch.setenv("MINE_B200_FORCE_SPEC", "0")
+    l1 = t1.train_step(items)
+    for k in ("loss", "loss_rgb_tgt", "loss_ssim_tgt", "loss_disp_pt3dsrc", "loss_disp_pt3dtgt"):
+        assert abs(l1[k].item() - l2[k].item()) <= 2e-3 * abs(l2[k].item()) + 1e-4, (k, l1[k].item(), l2[k].item())
+    g1, g2 = t1.arena.grad, t2.arena.grad
+    rel = (g1 - g2).norm().item() / (g2.norm().item() + 1e-12)
+    assert rel < 2e-2, rel
