@@ -76,6 +76,46 @@ class _BatchNormTrain(torch.autograd.Function):
         return dx.to(x.dtype), dweight.to(weight.dtype), dbias.to(weight.dtype), None, None, None, None, None
 
 
+class _SyncBatchNormCUDA(torch.autograd.Function):
+    """Cross-replica BN on CUDA built from ATen's fused batch_norm_* kernels (the ones
+    ``nn.SyncBatchNorm`` uses) with OUR reducer in place of the all_gather / all_reduce collectives:
+    one [2C] SUM forward (sum, sum of squares) and one [2C] SUM backward.  Used by the encoder
+    (library convs, 4 % of the FLOPs); the decoder's BN lives inside the tcgen05 conv engine."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, reducer, world):
+        c = x.shape[1]
+        x = x.contiguous(memory_format=torch.channels_last) if x.dim() == 4 and not x.is_contiguous() else x
+        mean_l, invstd_l = torch.batch_norm_stats(x, eps)
+        n_l = float(x.numel() // c)
+        var_l = (1.0 / (invstd_l * invstd_l) - eps).clamp_min(0.0)
+        packed = torch.cat([mean_l * n_l, (var_l + mean_l * mean_l) * n_l])
+        packed = reducer(packed)
+        n = n_l * world
+        mean = packed[:c] / n
+        var = (packed[c:] / n - mean * mean).clamp_min(0.0)
+        invstd = torch.rsqrt(var + eps)
+        if running_mean is not None:
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1 - momentum).add_((var * (n / max(n - 1.0, 1.0))).to(running_var.dtype), alpha=momentum)
+        y = torch.batch_norm_elemt(x, weight, bias, mean, invstd, eps)
+        ctx.save_for_backward(x, weight, mean, invstd)
+        ctx.reducer, ctx.n = reducer, n
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, invstd = ctx.saved_tensors
+        dy = dy.contiguous(memory_format=torch.channels_last) if dy.dim() == 4 and not dy.is_contiguous() else dy
+        sum_dy, sum_dy_xmu, gw, gb = torch.batch_norm_backward_reduce(dy, x, mean, invstd, weight, True, True, True)
+        c = sum_dy.numel()
+        packed = ctx.reducer(torch.cat([sum_dy, sum_dy_xmu]))
+        count = torch.full((1,), ctx.n, dtype=torch.int32, device=x.device)
+        dx = torch.batch_norm_backward_elemt(dy, x, mean, invstd, weight, packed[:c], packed[c:], count)
+        return dx, gw, gb, None, None, None, None, None, None
+
+
 class BatchNorm(nn.Module):
     """Drop-in for ``nn.BatchNorm2d`` / ``nn.SyncBatchNorm`` (same state-dict keys)."""
 
@@ -99,8 +139,18 @@ class BatchNorm(nn.Module):
         if self.training:
             with torch.no_grad():
                 self.num_batches_tracked += 1
+            if x.is_cuda and x.dtype != torch.float64:
+                if self.reducer is None:        # single replica: ATen/cuDNN fused training BN
+                    return torch.nn.functional.batch_norm(x, self.running_mean, self.running_var, self.weight,
+                                                          self.bias, True, self.momentum, self.eps)
+                world = int(getattr(getattr(self.reducer, "__self__", None), "world_size", 1))
+                return _SyncBatchNormCUDA.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                                self.momentum, self.eps, self.reducer, world)
             return _BatchNormTrain.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
                                          self.momentum, self.eps, self.reducer)
+        if x.is_cuda and x.dtype != torch.float64:
+            return torch.nn.functional.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias,
+                                                  False, self.momentum, self.eps)
         a, b = self.scale_shift()
         shape = [1, self.num_features] + [1] * (x.dim() - 2)
         acc = _acc_dtype(x)

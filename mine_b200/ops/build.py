@@ -99,7 +99,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if jobs or force or _newer(objs, SO_PATH):
         link = ["g++", "-shared", "-o", SO_PATH] + objs + [
             "-L" + torch_lib, "-L" + os.path.join(cuda_home, "lib64"), "-Wl,-rpath," + torch_lib,
-            "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart", "-lcuda"]
+            "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart"]
         _run(link, verbose)
     if verbose:
         print(f"built {SO_PATH} ({len(jobs)} objects, {time.time() - t0:.1f}s)")

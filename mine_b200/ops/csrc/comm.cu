@@ -1,0 +1,125 @@
+// Hand-written all-reduce kernels over NVLink peer memory (symmetric heap), sm_100a.
+//
+// Replaces the two NCCL paths of the reference's data parallelism:
+//   N6/N7  134 tiny SyncBatchNorm collectives per step  -> allreduce_small_oneshot: every rank publishes
+//          its <=64 Ki-float vector in its own symmetric slot, one flag round over NVLink, every rank then
+//          pulls all peers' vectors with P2P loads and sums them in RANK ORDER (bit-identical on all
+//          ranks, so BN running statistics never diverge).  One kernel, latency ~ a flag round trip.
+//   N8     DDP bucketed gradient all-reduce (+ divide by world) -> allreduce_mean_twoshot, IN PLACE on the
+//          symmetric gradient arena: rank r owns slice r of the bucket, reads that slice from every peer
+//          (16-byte P2P loads), fuses the 1/world scaling (and optionally a bf16 mirror for the next
+//          forward), and stores the result into EVERY peer's arena (P2P stores) - reduce-scatter and
+//          all-gather in one kernel with device-side flag barriers before and after.  With an NVSwitch
+//          multicast mapping the same kernel uses multimem.ld_reduce / multimem.st (in-switch reduction).
+// No NCCL call is made on either path; launched on a side stream so it overlaps the rest of backward.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace mine {
+
+__device__ __forceinline__ void st_release_sys(uint32_t* addr, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_v4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer_v4(float4* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_v4(const float4* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_v4(float4* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Flag barrier between the same-numbered CTA of every rank.  flags: [channels][world] uint32 per rank
+// (symmetric).  Thread p < world signals peer p and waits for peer p's signal; values only grow.
+__device__ __forceinline__ void peer_barrier(const PeerTable& flags, int rank, int world, int channel, uint32_t epoch) {
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    const int p = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(flags.ptr[p]) + channel * world + rank, epoch);
+    const uint32_t* mine_flag = reinterpret_cast<const uint32_t*>(flags.ptr[rank]) + channel * world + p;
+    while ((int32_t)(ld_acquire_sys(mine_flag) - epoch) < 0) { }
+  }
+  __syncthreads();
+}
+
+// ---- small one-shot SUM (BN statistics) -------------------------------------------------------------
+// data: [2 slots][cap] floats per rank (symmetric); slot = epoch & 1
+__global__ void __launch_bounds__(256) allreduce_small_oneshot_kernel(float* __restrict__ inout, int n, PeerTable data,
+                                                                      PeerTable flags, int rank, int world, int cap,
+                                                                      uint32_t epoch, int channel) {
+  float* my_slot = reinterpret_cast<float*>(data.ptr[rank]) + (size_t)(epoch & 1) * cap;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) my_slot[i] = inout[i];
+  peer_barrier(flags, rank, world, channel, epoch);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float acc = 0.f;
+    for (int p = 0; p < world; ++p) {
+      const float* src = reinterpret_cast<const float*>(data.ptr[p]) + (size_t)(epoch & 1) * cap;
+      float v;
+      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(src + i) : "memory");
+      acc += v;
+    }
+    inout[i] = acc;
+  }
+}
+
+// ---- two-shot mean, in place on the symmetric arena ---------------------------------------------------
+// Elements [lo, hi) of every rank's arena (float offsets, multiples of 4).  Rank r reduces its 1/world slice.
+__global__ void __launch_bounds__(512) allreduce_mean_twoshot_kernel(PeerTable arena, PeerTable flags, float* mc_arena,
+                                                                     int64_t lo, int64_t hi, int rank, int world,
+                                                                     float scale, uint32_t epoch, int use_multimem) {
+  const int channel = blockIdx.x + 1;                       // channel 0 belongs to the small one-shot kernel
+  peer_barrier(flags, rank, world, channel, epoch);         // every rank's gradients for [lo, hi) are final
+  const int64_t n4 = (hi - lo) / 4;
+  const int64_t per = (n4 + world - 1) / world;
+  const int64_t s4 = rank * per, e4 = (s4 + per < n4) ? s4 + per : n4;
+  const int64_t base4 = lo / 4;
+  for (int64_t i = s4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc;
+    if (use_multimem) {
+      acc = multimem_ld_reduce_v4(reinterpret_cast<const float4*>(mc_arena) + base4 + i);
+    } else {
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < world; ++p) {                   // fixed order: identical bits on every rank
+        const float4 v = ld_peer_v4(reinterpret_cast<const float4*>(arena.ptr[p]) + base4 + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+    if (use_multimem) {
+      multimem_st_v4(reinterpret_cast<float4*>(mc_arena) + base4 + i, acc);
+    } else {
+      for (int p = 0; p < world; ++p) st_peer_v4(reinterpret_cast<float4*>(arena.ptr[p]) + base4 + i, acc);
+    }
+  }
+  peer_barrier(flags, rank, world, channel, epoch + 1);     // all slices have landed everywhere
+}
+
+void launch_allreduce_small(float* inout, int n, const PeerTable& data, const PeerTable& flags, int rank, int world,
+                            int cap, uint32_t epoch, cudaStream_t stream) {
+  allreduce_small_oneshot_kernel<<<1, 256, 0, stream>>>(inout, n, data, flags, rank, world, cap, epoch, 0);
+}
+
+void launch_allreduce_mean(const PeerTable& arena, const PeerTable& flags, float* mc_arena, int64_t lo, int64_t hi,
+                           int rank, int world, uint32_t epoch, int blocks, cudaStream_t stream) {
+  allreduce_mean_twoshot_kernel<<<blocks, 512, 0, stream>>>(arena, flags, mc_arena, lo, hi, rank, world, 1.0f / world,
+                                                            epoch, mc_arena != nullptr ? 1 : 0);
+}
+
+}  // namespace mine

@@ -1,2 +1,170 @@
+// Bindings of the tcgen05 conv engine and its elementwise companions.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
-void register_conv(pybind11::module_& m) {}
+
+#include "conv_engine.h"
+#include "kernels.h"
+
+namespace {
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+inline void check_bf16_nhwc(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.is_contiguous() && t.dim() == 4, name,
+              " must be a contiguous CUDA bf16 [N,H,W,C] tensor");
+  TORCH_CHECK(t.size(3) % 8 == 0, name, ": channels must be a multiple of 8");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, name, " must be 16-byte aligned");
+}
+inline const float* opt_f32(const c10::optional<at::Tensor>& t, const char* name) {
+  if (!t.has_value() || !t->defined()) return nullptr;
+  TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kFloat && t->is_contiguous(), name, " must be contiguous CUDA fp32");
+  return t->data_ptr<float>();
+}
+
+void conv_taps(const at::Tensor& x, const at::Tensor& wpack, at::Tensor out, int64_t Hg, int64_t Wg, int64_t G, int64_t T,
+               std::vector<int64_t> tap_y, std::vector<int64_t> tap_x, int64_t in_stride, int64_t Co, int64_t out_sy,
+               int64_t out_sx, std::vector<int64_t> out_oy, std::vector<int64_t> out_ox, bool accumulate,
+               const c10::optional<at::Tensor>& chan_bias, const c10::optional<at::Tensor>& plane_bias,
+               const c10::optional<at::Tensor>& shared_map, int64_t planes_per_image,
+               const c10::optional<at::Tensor>& stats, int64_t act, bool head_alpha,
+               const c10::optional<at::Tensor>& raw_out, int64_t TH, int64_t TW) {
+  check_bf16_nhwc(x, "x");
+  TORCH_CHECK(wpack.is_cuda() && wpack.scalar_type() == at::kBFloat16 && wpack.is_contiguous() && wpack.dim() == 3,
+              "wpack must be bf16 [G*T, BN, Ci]");
+  TORCH_CHECK(wpack.size(0) == G * T && wpack.size(2) == x.size(3), "wpack shape mismatch");
+  TORCH_CHECK((int64_t)tap_y.size() == G * T && (int64_t)tap_x.size() == G * T, "tap table size");
+  TORCH_CHECK((int64_t)out_oy.size() == G && (int64_t)out_ox.size() == G, "group offset size");
+  TORCH_CHECK(out.is_cuda() && out.is_contiguous(), "out must be contiguous CUDA");
+  c10::cuda::CUDAGuard guard(x.device());
+  mine::ConvLaunch L{};
+  mine::ConvParams& p = L.p;
+  p.N = x.size(0); p.Hg = Hg; p.Wg = Wg; p.TH = TH; p.TW = TW;
+  p.G = G; p.T = T; p.Ci = x.size(3);
+  p.KB = p.Ci >= 64 ? 64 : p.Ci;
+  p.in_stride = in_stride;
+  for (int g = 0; g < G; ++g) {
+    for (int t = 0; t < T; ++t) { p.tap_y[g][t] = (int16_t)tap_y[g * T + t]; p.tap_x[g][t] = (int16_t)tap_x[g * T + t]; }
+    p.out_oy[g] = (int16_t)out_oy[g]; p.out_ox[g] = (int16_t)out_ox[g];
+  }
+  p.Co = Co; p.BN = wpack.size(1);
+  p.out_sy = out_sy; p.out_sx = out_sx;
+  p.out = out.data_ptr();
+  p.act = act; p.head_alpha = head_alpha;
+  if (act == 1) {
+    TORCH_CHECK(out.scalar_type() == at::kFloat && out.size(-1) == 4, "head output must be fp32 [...,4]");
+    p.Ho = out.size(-3); p.Wo = out.size(-2);
+    TORCH_CHECK(out.numel() == (int64_t)p.N * p.Ho * p.Wo * 4, "head output shape");
+  } else {
+    TORCH_CHECK(out.dim() == 4 && out.size(0) == p.N && out.size(3) == Co, "out must be [N,Ho,Wo,Co]");
+    p.Ho = out.size(1); p.Wo = out.size(2);
+    TORCH_CHECK(out.scalar_type() == at::kBFloat16 || out.scalar_type() == at::kFloat, "out dtype");
+    p.out_fp32 = out.scalar_type() == at::kFloat;
+    TORCH_CHECK(Co % 16 == 0, "Co must be a multiple of 16 for tensor outputs");
+  }
+  p.accumulate = accumulate;
+  p.chan_bias = opt_f32(chan_bias, "chan_bias");
+  p.plane_bias = opt_f32(plane_bias, "plane_bias");
+  p.shared_map = opt_f32(shared_map, "shared_map");
+  p.planes_per_image = planes_per_image > 0 ? planes_per_image : 1;
+  if (p.shared_map) TORCH_CHECK(shared_map->numel() == (int64_t)(p.N / p.planes_per_image) * p.Ho * p.Wo * Co, "shared_map shape");
+  if (p.plane_bias) TORCH_CHECK(plane_bias->numel() == (int64_t)p.N * Co, "plane_bias shape");
+  p.stats = const_cast<float*>(opt_f32(stats, "stats"));
+  if (p.stats) TORCH_CHECK(stats->numel() == 2 * Co, "stats must be [2, Co]");
+  p.raw_out = (raw_out.has_value() && raw_out->defined()) ? raw_out->data_ptr() : nullptr;
+  L.x = x.data_ptr(); L.Hi = x.size(1); L.Wi = x.size(2);
+  L.w = wpack.data_ptr();
+  const char* err = mine::launch_conv_taps(L, cur_stream());
+  TORCH_CHECK(err == nullptr, "conv_taps: ", err ? err : "");
+}
+
+void wgrad_taps(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_t Hg, int64_t Wg, int64_t G, int64_t T,
+                std::vector<int64_t> tap_y, std::vector<int64_t> tap_x, int64_t dy_stride, std::vector<int64_t> dy_oy,
+                std::vector<int64_t> dy_ox, int64_t TH, int64_t TW) {
+  check_bf16_nhwc(dy, "dy"); check_bf16_nhwc(x, "x");
+  TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.is_contiguous() && dw.dim() == 3, "dw must be fp32 [G*T,Co,Ci]");
+  TORCH_CHECK(dw.size(0) == G * T && dw.size(1) == dy.size(3) && dw.size(2) == x.size(3), "dw shape");
+  TORCH_CHECK(dy.size(0) == x.size(0), "batch mismatch");
+  c10::cuda::CUDAGuard guard(x.device());
+  mine::WgradLaunch L{};
+  mine::WgradParams& p = L.p;
+  p.N = x.size(0); p.Hg = Hg; p.Wg = Wg; p.TH = TH; p.TW = TW; p.KP = TH * TW;
+  p.G = G; p.T = T; p.Co = dy.size(3); p.Ci = x.size(3);
+  p.dy_stride = dy_stride;
+  for (int g = 0; g < G; ++g) {
+    for (int t = 0; t < T; ++t) { p.tap_y[g][t] = (int16_t)tap_y[g * T + t]; p.tap_x[g][t] = (int16_t)tap_x[g * T + t]; }
+    p.dy_oy[g] = (int16_t)dy_oy[g]; p.dy_ox[g] = (int16_t)dy_ox[g];
+  }
+  p.dw = dw.data_ptr<float>();
+  L.dy = dy.data_ptr(); L.dyH = dy.size(1); L.dyW = dy.size(2);
+  L.x = x.data_ptr(); L.xH = x.size(1); L.xW = x.size(2);
+  const char* err = mine::launch_wgrad_taps(L, cur_stream());
+  TORCH_CHECK(err == nullptr, "wgrad_taps: ", err ? err : "");
+}
+
+at::Tensor bn_act_pad_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
+                          int64_t pad_mode, double count, double eps) {
+  check_bf16_nhwc(y, "y");
+  c10::cuda::CUDAGuard guard(y.device());
+  const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
+  at::Tensor out = at::empty({N, H + 2, W + 2, C}, y.options());
+  mine::launch_bn_act_pad_fwd(y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(),
+                              out.data_ptr(), N, H, W, C, (int)pad_mode, (float)(1.0 / count), (float)eps, cur_stream());
+  return out;
+}
+
+std::vector<at::Tensor> bn_act_bwd_reduce(const at::Tensor& dapad, const at::Tensor& y, const at::Tensor& stats,
+                                          const at::Tensor& gamma, const at::Tensor& beta, int64_t pad_mode, double count,
+                                          double eps) {
+  check_bf16_nhwc(dapad, "dapad"); check_bf16_nhwc(y, "y");
+  c10::cuda::CUDAGuard guard(y.device());
+  const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
+  TORCH_CHECK(dapad.size(1) == H + 2 && dapad.size(2) == W + 2 && dapad.size(3) == C, "dapad shape");
+  at::Tensor g = at::empty_like(y);
+  at::Tensor sums = at::zeros({2, C}, stats.options());
+  mine::launch_bn_act_bwd_reduce(dapad.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(),
+                                 beta.data_ptr<float>(), g.data_ptr(), sums.data_ptr<float>(), N, H, W, C, (int)pad_mode,
+                                 (float)(1.0 / count), (float)eps, cur_stream());
+  return {g, sums};
+}
+
+std::vector<at::Tensor> bn_bwd_apply(const at::Tensor& g, const at::Tensor& y, const at::Tensor& stats,
+                                     const at::Tensor& gamma, const at::Tensor& sums, int64_t planes_per_image,
+                                     bool want_shared, bool want_plane_bias, double count, double eps) {
+  check_bf16_nhwc(g, "g"); check_bf16_nhwc(y, "y");
+  c10::cuda::CUDAGuard guard(y.device());
+  const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
+  const int S = planes_per_image, B = N / S;
+  at::Tensor dy = at::empty_like(y);
+  at::Tensor dshared = want_shared ? at::empty({B, H, W, C}, stats.options()) : at::Tensor();
+  at::Tensor dpb = want_plane_bias ? at::zeros({N, C}, stats.options()) : at::Tensor();
+  mine::launch_bn_bwd_apply(g.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(),
+                            sums.data_ptr<float>(), dy.data_ptr(), want_shared ? dshared.data_ptr<float>() : nullptr,
+                            want_plane_bias ? dpb.data_ptr<float>() : nullptr, B, S, H, W, C, (float)(1.0 / count),
+                            (float)eps, cur_stream());
+  return {dy, dshared, dpb};
+}
+
+std::vector<at::Tensor> head_bwd(const at::Tensor& g_mpi, const at::Tensor& mpi, const at::Tensor& sign, bool use_alpha) {
+  TORCH_CHECK(g_mpi.is_cuda() && g_mpi.scalar_type() == at::kFloat && g_mpi.is_contiguous(), "g_mpi");
+  TORCH_CHECK(mpi.is_contiguous() && mpi.scalar_type() == at::kFloat && sign.scalar_type() == at::kChar, "mpi/sign");
+  c10::cuda::CUDAGuard guard(mpi.device());
+  const int64_t npix = mpi.numel() / 4;
+  auto sizes = sign.sizes().vec();           // [N, H, W]
+  at::Tensor dz = at::empty({sizes[0], sizes[1], sizes[2], 16}, mpi.options().dtype(at::kBFloat16));
+  at::Tensor dbias = at::zeros({4}, mpi.options());
+  mine::launch_head_bwd(g_mpi.data_ptr<float>(), mpi.data_ptr<float>(), sign.data_ptr<int8_t>(), dz.data_ptr(),
+                        dbias.data_ptr<float>(), (size_t)npix, use_alpha ? 1 : 0, cur_stream());
+  return {dz, dbias};
+}
+
+}  // namespace
+
+void register_conv(pybind11::module_& m) {
+  m.def("conv_taps", &conv_taps);
+  m.def("wgrad_taps", &wgrad_taps);
+  m.def("bn_act_pad_fwd", &bn_act_pad_fwd);
+  m.def("bn_act_bwd_reduce", &bn_act_bwd_reduce);
+  m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("head_bwd", &head_bwd);
+}

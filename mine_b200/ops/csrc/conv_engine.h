@@ -1,0 +1,58 @@
+// Parameter blocks of the tcgen05 convolution engine (shared by conv_tcgen05.cu and the bindings).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mine {
+
+struct ConvParams {
+  // logical GEMM pixel grid (per image) and its 128-pixel tiling
+  int N, Hg, Wg, TH, TW, tiles_x, tiles_y;
+  // reduction: G groups (sub-pixel phases) x T taps x (Ci / KB) channel blocks
+  int G, T, Ci, KB, kblocks;
+  int in_stride;                         // 1, or 2 for the strided gather of the phase-conv dgrad
+  int16_t tap_y[4][16], tap_x[4][16];    // input offset of every (group, tap), in input pixels
+  // output tensor [N, Ho, Wo, Co]; GEMM pixel (oy, ox) of group g lands on (oy*out_sy + out_oy[g], ox*out_sx + out_ox[g])
+  int Co, BN, Ho, Wo, out_sy, out_sx;
+  int16_t out_oy[4], out_ox[4];
+  void* out;
+  int out_fp32, accumulate;
+  // epilogue extras
+  const float* chan_bias;                // [Co] or null
+  const float* plane_bias;               // [N, Co] or null (embedding term + conv bias)
+  const float* shared_map;               // [N / planes_per_image, Ho, Wo, Co] fp32 or null (shared-skip conv)
+  int planes_per_image;
+  float* stats;                          // [2, Co] fp32 (sum, sum of squares) or null
+  int act, head_alpha;                   // act = 1: MPI head (packed fp32 [.,4] output)
+  void* raw_out;                         // head: sign of the sigma pre-activation, int8 [N, Ho, Wo] or null
+  // filled by the launcher
+  int stages, tmem_cols;
+};
+
+struct ConvLaunch {
+  ConvParams p;
+  const void* x; int Hi, Wi;             // NHWC bf16 input [N, Hi, Wi, Ci]
+  const void* w;                         // packed bf16 weights [G*T, BN, Ci]
+};
+
+struct WgradParams {
+  int N, Hg, Wg, TH, TW, KP, tiles_x, tiles_y;
+  int G, T, Co, Ci;
+  int dy_stride;                         // 1, or 2 when dy is addressed through sub-pixel phases
+  int16_t dy_oy[4], dy_ox[4];            // phase offsets into dy
+  int16_t tap_y[4][16], tap_x[4][16];    // offsets into x
+  float* dw;                             // fp32 [G*T, Co, Ci], accumulated with atomics
+  // filled by the launcher
+  int a_cb, b_cb, a_slabs, b_slabs, co_blocks, ci_blocks, NB, taps_per_chunk, tap_chunks, stages, tmem_cols;
+};
+
+struct WgradLaunch {
+  WgradParams p;
+  const void* dy; int dyH, dyW;          // NHWC bf16 [N, dyH, dyW, Co]
+  const void* x; int xH, xW;             // NHWC bf16 [N, xH, xW, Ci]
+};
+
+const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream);
+const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream);
+
+}  // namespace mine

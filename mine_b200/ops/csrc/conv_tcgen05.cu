@@ -1,0 +1,606 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution engine for sm_100a.
+//
+// One kernel family serves every 3x3 convolution of the per-plane MPI decoder (the >95 % FLOP share
+// of MINE) in all three directions:
+//
+//   conv_taps  : D[128 pixels, Co] = sum_taps sum_kblk  X_tap[128 px, KB ch] * W_tap[Co, KB ch]^T
+//                - fprop (9 taps on a pre-padded NHWC input),
+//                - fused nearest-x2-upsample + 3x3 conv as 4 sub-pixel phases x 4 taps on the
+//                  replicate-padded LOW-resolution input (4/9 of the FLOPs, no upsampled tensor),
+//                - dgrad (same kernel, transposed tap table / weight pack; zero padding and the
+//                  stride-2 gather of the phase form come from TMA out-of-bounds fill and TMA
+//                  element strides).
+//                A operand = TMA 4-D box {KB ch, TW, TH, 1} of the NHWC tensor shifted by the tap
+//                offset -> a K-major 128-row smem tile (hardware swizzle 32/64/128 B);
+//                B operand = TMA box of the packed weights [group*tap][Co][Ci]; accumulator in TMEM;
+//                one elected thread issues tcgen05.mma; a 4..6-stage mbarrier ring decouples TMA and MMA.
+//                Epilogue (4 warps, tcgen05.ld): + shared-skip map (per image, broadcast over planes)
+//                + per-plane embedding bias, BatchNorm partial statistics (sum, sum^2 per channel ->
+//                smem -> one atomic per channel per CTA), bf16 NHWC store (strided for the phase form),
+//                or the MPI head activation (sigmoid rgb, |x|+1e-4 sigma) written straight into the
+//                packed [B,S,H,W,4] fp32 MPI the render kernels consume.
+//   wgrad_taps : dW[tap][Co, Ci] = sum_pixels dY[px, Co]^T X_tap[px, Ci]  (both operands MN-major smem
+//                tiles straight from TMA, all taps of a chunk accumulate side by side in TMEM,
+//                persistent over pixel tiles, fp32 vector atomics into the packed weight gradient).
+//
+// SASS evidence (cuobjdump -sass): UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "conv_engine.h"
+
+namespace mine {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell).
+//   K-major  : rows (M/N index) are `row_bytes` (=swizzle span) apart, 8-row groups SBO apart.
+//   MN-major : K rows are `row_bytes` apart, 8-K-row groups SBO apart, 64/32/16-element MN blocks LBO apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t layout_type_for(int swizzle_bytes) {
+  return swizzle_bytes == 128 ? 2u : (swizzle_bytes == 64 ? 4u : 6u);     // SWIZZLE_128B / 64B / 32B
+}
+// Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float warp_sum32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kConvThreads = 192;     // warp0: TMA producer, warp1: TMEM alloc + MMA issue, warps 2..5: epilogue
+constexpr int kMaxStages = 8;
+
+// ------------------------------------------------------------------------------------------------
+// conv_taps: fprop / phase-upsample fprop / dgrad
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                 const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_stats[2][256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, n_img = blockIdx.y, g = blockIdx.z;
+  const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+  const int oy0 = tile_y * p.TH, ox0 = tile_x * p.TW;
+
+  const int row_bytes = p.KB * 2;                     // == swizzle span
+  const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
+  const uint32_t stage_bytes = ((a_bytes + b_bytes + 1023u) / 1024u) * 1024u;
+  uint8_t* smem_aligned = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_stats[0][0])[i] = 0.f;
+  if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int iters = p.T * p.kblocks;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages, round = it / p.stages;
+        if (it >= p.stages) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        const int t = it / p.kblocks, kb = it - t * p.kblocks;
+        uint8_t* a_dst = smem_aligned + (size_t)s * stage_bytes;
+        uint8_t* b_dst = a_dst + a_bytes;
+        mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+        const int iy = oy0 * p.in_stride + p.tap_y[g][t], ix = ox0 * p.in_stride + p.tap_x[g][t];
+        tma_load_4d(&map_x, &full_bar[s], a_dst, kb * p.KB, ix, iy, n_img);
+        tma_load_3d(&map_w, &full_bar[s], b_dst, kb * p.KB, 0, g * p.T + t);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
+      const uint32_t lt = layout_type_for(row_bytes);
+      const uint32_t sbo = 8u * row_bytes;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages, round = it / p.stages;
+        mbar_wait(&full_bar[s], round & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int k = 0; k < p.KB / 16; ++k) {
+          const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, lt);
+          const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, lt);
+          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
+      }
+      umma_commit(&accum_bar);                // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) ----------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                       // row of the 128-pixel tile
+    const int ty = r / p.TW, tx = r - ty * p.TW;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    const bool valid = (oy < p.Hg) && (ox < p.Wg);
+    const int out_y = oy * p.out_sy + p.out_oy[g], out_x = ox * p.out_sx + p.out_ox[g];
+    const size_t out_pix = ((size_t)n_img * p.Ho + out_y) * p.Wo + out_x;
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const float* pbias = p.plane_bias ? p.plane_bias + (size_t)n_img * p.Co : nullptr;
+    const float* smap = nullptr;
+    if (p.shared_map && valid) smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (c0 >= p.Co) continue;
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.chan_bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (c0 + j < p.Co) f[j] += p.chan_bias[c0 + j];
+      }
+      if (pbias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (c0 + j < p.Co) f[j] += pbias[c0 + j];
+      }
+      if (smap) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 m = *reinterpret_cast<const float4*>(smap + c0 + j);
+          f[j] += m.x; f[j + 1] += m.y; f[j + 2] += m.z; f[j + 3] += m.w;
+        }
+      }
+      if (p.stats) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float x = valid ? f[j] : 0.f;
+          const float s1 = warp_sum32(x), s2 = warp_sum32(x * x);
+          if (lane == 0) { atomicAdd(&s_stats[0][c0 + j], s1); atomicAdd(&s_stats[1][c0 + j], s2); }
+        }
+      }
+      if (valid) {
+      if (p.act == 1) {                       // MPI head: 4 real channels -> packed fp32 MPI (+ raw pre-activation)
+        float4 o;
+        o.x = 1.f / (1.f + __expf(-f[0])); o.y = 1.f / (1.f + __expf(-f[1])); o.z = 1.f / (1.f + __expf(-f[2]));
+        o.w = p.head_alpha ? 1.f / (1.f + __expf(-f[3])) : fabsf(f[3]) + 1e-4f;
+        reinterpret_cast<float4*>(p.out)[out_pix] = o;
+        if (p.raw_out) reinterpret_cast<int8_t*>(p.raw_out)[out_pix] = f[3] >= 0.f ? (int8_t)1 : (int8_t)-1;
+      } else if (p.out_fp32) {
+        float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + c0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          if (p.accumulate) { const float4 e = *reinterpret_cast<float4*>(dst + j); o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
+      } else {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + c0;
+        if (p.accumulate) {
+          const uint4 e0 = *reinterpret_cast<const uint4*>(dst), e1 = *reinterpret_cast<const uint4*>(dst + 8);
+          const __nv_bfloat16* eb0 = reinterpret_cast<const __nv_bfloat16*>(&e0);
+          const __nv_bfloat16* eb1 = reinterpret_cast<const __nv_bfloat16*>(&e1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { f[j] += __bfloat162float(eb0[j]); f[8 + j] += __bfloat162float(eb1[j]); }
+        }
+        uint4 o0, o1;
+        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          h1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+        }
+        *reinterpret_cast<uint4*>(dst) = o0;
+        *reinterpret_cast<uint4*>(dst + 8) = o1;
+      }
+    }   // valid
+      __syncwarp();
+    }
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // epilogue warps only
+      const int e = threadIdx.x - 64;                        // 0..127
+      for (int c = e; c < p.Co; c += 128) {
+        atomicAdd(p.stats + c, s_stats[0][c]);
+        atomicAdd(p.stats + p.Co + c, s_stats[1][c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad_taps
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kConvThreads, 1)
+wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                  const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.y enumerates (group, tap chunk, co block, ci block)
+  int rem = blockIdx.y;
+  const int nb = rem % p.ci_blocks; rem /= p.ci_blocks;
+  const int mb = rem % p.co_blocks; rem /= p.co_blocks;
+  const int tc = rem % p.tap_chunks; rem /= p.tap_chunks;
+  const int g = rem;
+  const int t0 = tc * p.taps_per_chunk;
+  const int ntaps = min(p.taps_per_chunk, p.T - t0);
+
+  const int a_row = p.a_cb * 2, b_row = p.b_cb * 2;          // bytes per pixel row in the A / B slabs
+  const uint32_t a_slab = (uint32_t)p.KP * a_row, b_slab = (uint32_t)p.KP * b_row;
+  const uint32_t a_bytes = a_slab * p.a_slabs;
+  const uint32_t b_tap_bytes = b_slab * p.b_slabs;
+  const uint32_t stage_bytes = ((a_bytes + b_tap_bytes * p.taps_per_chunk + 1023u) / 1024u) * 1024u;
+  uint8_t* smem_aligned = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // pixel tiles handled by this CTA: tile ids blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int total_tiles = tiles_per_img * p.N;
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tid = blockIdx.x + i * gridDim.x;
+        const int n_img = tid / tiles_per_img, tt = tid - n_img * tiles_per_img;
+        const int tile_y = tt / p.tiles_x, tile_x = tt - tile_y * p.tiles_x;
+        const int oy0 = tile_y * p.TH, ox0 = tile_x * p.TW;
+        const int s = i % p.stages, round = i / p.stages;
+        if (i >= p.stages) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        uint8_t* a_dst = smem_aligned + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], a_bytes + b_tap_bytes * ntaps);
+        const int dy_y = oy0 * p.dy_stride + p.dy_oy[g], dy_x = ox0 * p.dy_stride + p.dy_ox[g];
+        for (int sl = 0; sl < p.a_slabs; ++sl)
+          tma_load_4d(&map_dy, &full_bar[s], a_dst + sl * a_slab, (mb * p.a_slabs + sl) * p.a_cb, dy_x, dy_y, n_img);
+        for (int t = 0; t < ntaps; ++t) {
+          uint8_t* b_dst = a_dst + a_bytes + (size_t)t * b_tap_bytes;
+          const int iy = oy0 + p.tap_y[g][t0 + t], ix = ox0 + p.tap_x[g][t0 + t];
+          for (int sl = 0; sl < p.b_slabs; ++sl)
+            tma_load_4d(&map_x, &full_bar[s], b_dst + sl * b_slab, (nb * p.b_slabs + sl) * p.b_cb, ix, iy, n_img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, p.NB, 1, 1);
+      const uint32_t lta = layout_type_for(a_row), ltb = layout_type_for(b_row);
+      // A: when Co < 128 the missing MN blocks alias block 0 (LBO = 0): rows >= Co are copies and never stored
+      const uint32_t a_lbo = (p.a_slabs > 1) ? a_slab : 0u;
+      const uint32_t b_lbo = (p.b_slabs > 1) ? b_slab : 0u;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % p.stages, round = i / p.stages;
+        mbar_wait(&full_bar[s], round & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
+        for (int t = 0; t < ntaps; ++t) {
+          const uint32_t b_addr = a_addr + a_bytes + t * b_tap_bytes;
+          for (int k = 0; k < p.KP / 16; ++k) {
+            // 16 K rows (pixels) per instruction = two 8-row groups, SBO apart
+            const uint64_t da = make_smem_desc(a_addr + k * 16 * a_row, a_lbo, 8u * a_row, lta);
+            const uint64_t db = make_smem_desc(b_addr + k * 16 * b_row, b_lbo, 8u * b_row, ltb);
+            umma_bf16(tmem_base + t * p.NB, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = mb * 128 + q * 32 + lane;            // TMEM lane == output-channel row
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    if (my_tiles > 0) {
+      for (int t = 0; t < ntaps; ++t) {
+        for (int c0 = 0; c0 < p.NB; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.NB + c0), v);
+          if (co >= p.Co) continue;
+          const int ci = nb * p.NB + c0;
+          if (ci >= p.Ci) continue;
+          float* dst = p.dw + (((size_t)(g * p.T + t0 + t) * p.Co + co) * p.Ci + ci);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps (cached) + launchers
+// ------------------------------------------------------------------------------------------------
+// The driver API is resolved at run time (cudaGetDriverEntryPoint) so the extension links against
+// libcudart only and can be imported on machines without libcuda.so.1 (the CPU build check).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+struct MapKey {
+  const void* ptr; int d0, d1, d2, d3, b0, b1, b2, b3, e1, e2, rank;
+  bool operator<(const MapKey& o) const {
+    return std::tie(ptr, d0, d1, d2, d3, b0, b1, b2, b3, e1, e2, rank) <
+           std::tie(o.ptr, o.d0, o.d1, o.d2, o.d3, o.b0, o.b1, o.b2, o.b3, o.e1, o.e2, o.rank);
+  }
+};
+static std::map<MapKey, CUtensorMap> g_maps;
+static std::mutex g_maps_mu;
+
+// NHWC activation: dims {C, W, H, N}; box {cb, bw, bh, 1}; element stride es on W and H.
+static const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int cb, int bw, int bh, int es) {
+  MapKey key{ptr, C, W, H, N, cb, bw * es, bh * es, 1, es, es, 4};
+  std::lock_guard<std::mutex> lock(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return nullptr; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return "cuTensorMapEncodeTiled is not available from this driver";
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cb * 2),
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (bad shape / stride / alignment)";
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = *out;
+  return nullptr;
+}
+
+// packed weights: dims {Ci, Co_pad, GT}; box {kb, bn, 1}
+static const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop, int GT, int kb, int bn) {
+  MapKey key{ptr, Ci, Cop, GT, 0, kb, bn, 1, 0, 1, 1, 3};
+  std::lock_guard<std::mutex> lock(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return nullptr; }
+  cuuint64_t dims[3] = {(cuuint64_t)Ci, (cuuint64_t)Cop, (cuuint64_t)GT};
+  cuuint64_t strides[2] = {(cuuint64_t)Ci * 2, (cuuint64_t)Cop * Ci * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)bn, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return "cuTensorMapEncodeTiled is not available from this driver";
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kb * 2),
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (bad shape / stride / alignment)";
+  g_maps[key] = *out;
+  return nullptr;
+}
+
+static int next_pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+
+const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
+  ConvParams p = L.p;
+  if (p.TH * p.TW != 128) return "tile must cover 128 pixels";
+  if (p.KB != 16 && p.KB != 32 && p.KB != 64) return "KB must be 16/32/64";
+  if (p.Ci % p.KB) return "Ci must be a multiple of KB";
+  if (p.BN % 16 || p.BN < 16 || p.BN > 256) return "BN must be a multiple of 16 in [16,256]";
+  if (p.T > 16 || p.G > 4) return "too many taps/groups";
+  p.kblocks = p.Ci / p.KB;
+  p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
+  p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
+  p.tmem_cols = next_pow2_cols(p.BN);
+  const uint32_t stage_bytes = ((128u * p.KB * 2 + (uint32_t)p.BN * p.KB * 2 + 1023u) / 1024u) * 1024u;
+  int stages = (int)(100u * 1024u / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  if (stages > p.T * p.kblocks) stages = p.T * p.kblocks;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  CUtensorMap mx, mw;
+  const char* e = nhwc_map(&mx, L.x, p.Ci, L.Wi, L.Hi, p.N, p.KB, p.TW, p.TH, p.in_stride);
+  if (e) return e;
+  e = weight_map(&mw, L.w, p.Ci, p.BN, p.G * p.T, p.KB, p.BN);
+  if (e) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  dim3 grid(p.tiles_x * p.tiles_y, p.N, p.G);
+  conv_taps_kernel<<<grid, kConvThreads, smem, stream>>>(mx, mw, p);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
+}
+
+const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
+  WgradParams p = L.p;
+  if (p.TH * p.TW != p.KP || (p.KP != 32 && p.KP != 64)) return "wgrad pixel tile must be 32 or 64 pixels";
+  // operand slabs: channel block = min(C, 64) with the matching swizzle
+  p.a_cb = p.Co < 64 ? p.Co : 64;
+  p.b_cb = p.Ci < 64 ? p.Ci : 64;
+  if (p.a_cb != 16 && p.a_cb != 32 && p.a_cb != 64) return "Co must be 16/32/multiple of 64";
+  if (p.b_cb != 16 && p.b_cb != 32 && p.b_cb != 64) return "Ci must be 16/32/multiple of 64";
+  p.a_slabs = p.Co >= 128 ? 2 : 1;                       // M = 128 rows: 2 real slabs, or 1 slab aliased by LBO = 0
+  p.co_blocks = (p.Co + 127) / 128;
+  p.NB = p.Ci < 128 ? p.Ci : 128;                        // N per accumulator
+  p.b_slabs = p.NB / p.b_cb;
+  p.ci_blocks = p.Ci / p.NB;
+  p.taps_per_chunk = 512 / p.NB;
+  if (p.taps_per_chunk > p.T) p.taps_per_chunk = p.T;
+  // keep the stage under ~48 KB
+  for (;;) {
+    const uint32_t sb = (uint32_t)p.KP * p.a_cb * 2 * p.a_slabs + (uint32_t)p.KP * p.b_cb * 2 * p.b_slabs * p.taps_per_chunk;
+    if (sb <= 48 * 1024 || p.taps_per_chunk == 1) break;
+    p.taps_per_chunk = (p.taps_per_chunk + 1) / 2;
+  }
+  p.tap_chunks = (p.T + p.taps_per_chunk - 1) / p.taps_per_chunk;
+  p.tmem_cols = next_pow2_cols(p.taps_per_chunk * p.NB);
+  p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
+  p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
+  const uint32_t stage_bytes =
+      (((uint32_t)p.KP * p.a_cb * 2 * p.a_slabs + (uint32_t)p.KP * p.b_cb * 2 * p.b_slabs * p.taps_per_chunk + 1023u) / 1024u) * 1024u;
+  int stages = (int)(192u * 1024u / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  CUtensorMap mdy, mx;
+  const char* e = nhwc_map(&mdy, L.dy, p.Co, L.dyW, L.dyH, p.N, p.a_cb, p.TW, p.TH, p.dy_stride);
+  if (e) return e;
+  e = nhwc_map(&mx, L.x, p.Ci, L.xW, L.xH, p.N, p.b_cb, p.TW, p.TH, 1);
+  if (e) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(wgrad_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const int combos = p.G * p.tap_chunks * p.co_blocks * p.ci_blocks;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.N;
+  int splits = (148 * 2 + combos - 1) / combos;
+  if (splits > total_tiles) splits = total_tiles;
+  if (splits < 1) splits = 1;
+  dim3 grid(splits, combos, 1);
+  wgrad_taps_kernel<<<grid, kConvThreads, smem, stream>>>(mdy, mx, p);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
+}
+
+}  // namespace mine

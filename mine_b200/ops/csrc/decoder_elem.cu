@@ -1,0 +1,313 @@
+// Memory-bound companions of the tcgen05 conv engine (NHWC bf16, 16-byte vectors = 8 channels).
+//
+//   bn_act_pad_fwd    : y (pre-BN conv output) -> ELU(BN(y)) written into a 1-pixel padded buffer with
+//                       reflection or replication borders (what the next conv's TMA boxes read).  Replaces
+//                       ATen batch_norm_elemt + ELU + ReflectionPad2d (+ upsample_nearest2d + cat) of the
+//                       reference: one read, one write.
+//   bn_act_bwd_reduce : folds the padded gradient back (adjoint of reflect/replicate pad), multiplies by
+//                       ELU', accumulates sum(g) and sum(g * xhat) per channel (the two BatchNorm backward
+//                       reductions, all-reduced across GPUs by the caller), stores g.
+//   bn_bwd_apply      : dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); loops over the S planes of an
+//                       image so the shared-skip gradient (sum over planes) stays in registers; per-plane
+//                       embedding-bias gradients are reduced in shared memory.
+//   head_bwd          : gradient of the MPI head activation, emitted as the 16-channel bf16 tensor the
+//                       dgrad/wgrad GEMMs consume.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace mine {
+
+struct V8 {
+  float f[8];
+};
+
+__device__ __forceinline__ V8 load_bf16x8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  V8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    r.f[2 * i] = t.x; r.f[2 * i + 1] = t.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const V8& v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v.f[2 * i], v.f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ int pad_src(int p, int n, int mode) {   // padded index -> source index
+  int s = p - 1;
+  if (mode == 0) { if (s < 0) s = -s; if (s >= n) s = 2 * n - 2 - s; }
+  else { s = s < 0 ? 0 : (s >= n ? n - 1 : s); }
+  return s;
+}
+
+struct BnCoef {      // per-channel affine of training-mode BN from the reduced statistics
+  float a[8], b[8], mean[8], invstd[8];
+};
+__device__ __forceinline__ BnCoef bn_coef(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, int C, int c0, float inv_count, float eps) {
+  BnCoef k;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m = stats[c0 + j] * inv_count;
+    float var = stats[C + c0 + j] * inv_count - m * m;
+    var = var < 0.f ? 0.f : var;
+    const float is = rsqrtf(var + eps);
+    k.mean[j] = m; k.invstd[j] = is;
+    k.a[j] = gamma[c0 + j] * is;
+    k.b[j] = beta[c0 + j] - m * k.a[j];
+  }
+  return k;
+}
+
+__global__ void __launch_bounds__(256) bn_act_pad_fwd_kernel(
+    const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C, int pad_mode,
+    float inv_count, float eps) {
+  const int cg = C >> 3;
+  const int Hp = H + 2, Wp = W + 2;
+  const size_t total = (size_t)N * Hp * Wp * cg;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cg) * 8;
+    size_t pix = i / cg;
+    const int px = (int)(pix % Wp); pix /= Wp;
+    const int py = (int)(pix % Hp);
+    const int n = (int)(pix / Hp);
+    const int sy = pad_src(py, H, pad_mode), sx = pad_src(px, W, pad_mode);
+    const BnCoef k = bn_coef(stats, gamma, beta, C, c0, inv_count, eps);
+    V8 v = load_bf16x8(y + (((size_t)n * H + sy) * W + sx) * C + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float u = v.f[j] * k.a[j] + k.b[j];
+      v.f[j] = u > 0.f ? u : (__expf(u) - 1.f);
+    }
+    store_bf16x8(out + (((size_t)n * Hp + py) * Wp + px) * C + c0, v);
+  }
+}
+
+// g = fold(dapad) * ELU'(bn(y)); sums[0][c] += g, sums[1][c] += g * xhat
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
+    const __nv_bfloat16* __restrict__ dapad, const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ g_out,
+    float* __restrict__ sums, int N, int H, int W, int C, int pad_mode, float inv_count, float eps) {
+  extern __shared__ float s_sum[];     // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
+  __syncthreads();
+  const int cg = C >> 3;
+  const int Hp = H + 2, Wp = W + 2;
+  const size_t total = (size_t)N * H * W * cg;
+  // a thread keeps its channel group for the whole grid-stride loop when the stride is a multiple of cg
+  const size_t stride = ((size_t)gridDim.x * blockDim.x / cg) * cg;
+  float acc1[8], acc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc1[j] = acc2[j] = 0.f;
+  size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 % cg) * 8;
+  const BnCoef k = bn_coef(stats, gamma, beta, C, c0, inv_count, eps);
+  if (i0 < stride) {
+    for (size_t i = i0; i < total; i += stride) {
+      size_t pix = i / cg;
+      const int x = (int)(pix % W); pix /= W;
+      const int yy = (int)(pix % H);
+      const int n = (int)(pix / H);
+      // rows / cols of the padded gradient that map onto this pixel
+      int ry[3], rx[3], ny = 1, nx = 1;
+      ry[0] = yy + 1; rx[0] = x + 1;
+      if (pad_mode == 0) {
+        if (yy == 1) ry[ny++] = 0;
+        if (yy == H - 2) ry[ny++] = H + 1;
+        if (x == 1) rx[nx++] = 0;
+        if (x == W - 2) rx[nx++] = W + 1;
+      } else {
+        if (yy == 0) ry[ny++] = 0;
+        if (yy == H - 1) ry[ny++] = H + 1;
+        if (x == 0) rx[nx++] = 0;
+        if (x == W - 1) rx[nx++] = W + 1;
+      }
+      V8 d;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d.f[j] = 0.f;
+      for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b) {
+          const V8 t = load_bf16x8(dapad + (((size_t)n * Hp + ry[a]) * Wp + rx[b]) * C + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d.f[j] += t.f[j];
+        }
+      const size_t o = (((size_t)n * H + yy) * W + x) * C + c0;
+      const V8 yv = load_bf16x8(y + o);
+      V8 g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float u = yv.f[j] * k.a[j] + k.b[j];
+        const float de = u > 0.f ? 1.f : __expf(u);
+        g.f[j] = d.f[j] * de;
+        const float xhat = (yv.f[j] - k.mean[j]) * k.invstd[j];
+        acc1[j] += g.f[j];
+        acc2[j] += g.f[j] * xhat;
+      }
+      store_bf16x8(g_out + o, g);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[c0 + j], acc1[j]); atomicAdd(&s_sum[C + c0 + j], acc2[j]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], s_sum[i]);
+}
+
+// One thread = 8 channels of one pixel of one IMAGE; loops over its S planes.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ sums, __nv_bfloat16* __restrict__ dy,
+    float* __restrict__ dshared, float* __restrict__ dplane_bias, int B, int S, int H, int W, int C, float inv_count,
+    float eps) {
+  extern __shared__ float s_pb[];      // [S][C] per-plane bias gradient partials
+  const bool want_pb = dplane_bias != nullptr;
+  if (want_pb) {
+    for (int i = threadIdx.x; i < S * C; i += blockDim.x) s_pb[i] = 0.f;
+    __syncthreads();
+  }
+  const int cg = C >> 3;
+  const size_t per_img = (size_t)H * W * cg;
+  const int b = blockIdx.y;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const bool active = i < per_img;
+  const size_t ii = active ? i : 0;
+  const int c0 = (int)(ii % cg) * 8;
+  const size_t pix = ii / cg;
+  float mean[8], invstd[8], coef[8], mg[8], mgx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m = stats[c0 + j] * inv_count;
+    float var = stats[C + c0 + j] * inv_count - m * m;
+    var = var < 0.f ? 0.f : var;
+    mean[j] = m; invstd[j] = rsqrtf(var + eps);
+    coef[j] = gamma[c0 + j] * invstd[j];
+    mg[j] = sums[c0 + j] * inv_count;
+    mgx[j] = sums[C + c0 + j] * inv_count;
+  }
+  float ds[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ds[j] = 0.f;
+  const int lane = threadIdx.x & 31;
+  for (int s = 0; s < S; ++s) {
+    V8 d;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d.f[j] = 0.f;
+    if (active) {
+      const size_t o = (((size_t)(b * S + s) * H * W) + pix) * C + c0;
+      const V8 gv = load_bf16x8(g + o), yv = load_bf16x8(y + o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (yv.f[j] - mean[j]) * invstd[j];
+        d.f[j] = coef[j] * (gv.f[j] - mg[j] - xhat * mgx[j]);
+        ds[j] += d.f[j];
+      }
+      store_bf16x8(dy + o, d);
+    }
+    if (want_pb) {
+      // lanes with equal (lane % cg) own the same channels (blockDim and cg are powers of two)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = d.f[j];
+        for (int o2 = 16; o2 >= cg && o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+        if (lane < cg || cg >= 32) atomicAdd(&s_pb[s * C + c0 + j], v);
+      }
+    }
+  }
+  if (dshared && active) {
+    float* dsp = dshared + ((size_t)b * H * W + pix) * C + c0;
+    *reinterpret_cast<float4*>(dsp) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+    *reinterpret_cast<float4*>(dsp + 4) = make_float4(ds[4], ds[5], ds[6], ds[7]);
+  }
+  if (want_pb) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < S * C; k += blockDim.x) {
+      const float v = s_pb[k];
+      if (v != 0.f) atomicAdd(&dplane_bias[(size_t)b * S * C + k], v);
+    }
+  }
+}
+
+// MPI head backward: g_mpi fp32 [.,4], mpi fp32 [.,4] (activated), sign int8 -> dz bf16 [.,16] (channels 4..15 zero)
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float4* __restrict__ g_mpi, const float4* __restrict__ mpi,
+                                                       const int8_t* __restrict__ sign, __nv_bfloat16* __restrict__ dz,
+                                                       float* __restrict__ dbias, size_t npix, int use_alpha) {
+  __shared__ float s_db[4];
+  if (threadIdx.x < 4) s_db[threadIdx.x] = 0.f;
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 gg = g_mpi[i], o = mpi[i];
+    float d0 = gg.x * o.x * (1.f - o.x), d1 = gg.y * o.y * (1.f - o.y), d2 = gg.z * o.z * (1.f - o.z);
+    float d3 = use_alpha ? gg.w * o.w * (1.f - o.w) : gg.w * (float)sign[i];
+    acc[0] += d0; acc[1] += d1; acc[2] += d2; acc[3] += d3;
+    uint4 lo, hi = make_uint4(0, 0, 0, 0);
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&lo);
+    h[0] = __floats2bfloat162_rn(d0, d1); h[1] = __floats2bfloat162_rn(d2, d3);
+    h[2] = __floats2bfloat162_rn(0.f, 0.f); h[3] = h[2];
+    uint4* dst = reinterpret_cast<uint4*>(dz + i * 16);
+    dst[0] = lo; dst[1] = hi;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v = acc[j];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_db[j], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(&dbias[threadIdx.x], s_db[threadIdx.x]);
+}
+
+// fp32 NCHW image-like tensor -> bf16 NHWC (encoder skip features etc. use torch channels_last instead)
+static int grid_for(size_t total, int cap = 148 * 16) {
+  size_t b = (total + 255) / 256;
+  return (int)(b > (size_t)cap ? cap : (b == 0 ? 1 : b));
+}
+
+void launch_bn_act_pad_fwd(const void* y, const float* stats, const float* gamma, const float* beta, void* out, int N,
+                           int H, int W, int C, int pad_mode, float inv_count, float eps, cudaStream_t stream) {
+  const size_t total = (size_t)N * (H + 2) * (W + 2) * (C / 8);
+  bn_act_pad_fwd_kernel<<<grid_for(total, 148 * 32), 256, 0, stream>>>(
+      (const __nv_bfloat16*)y, stats, gamma, beta, (__nv_bfloat16*)out, N, H, W, C, pad_mode, inv_count, eps);
+}
+
+void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* stats, const float* gamma,
+                              const float* beta, void* g_out, float* sums, int N, int H, int W, int C, int pad_mode,
+                              float inv_count, float eps, cudaStream_t stream) {
+  const size_t total = (size_t)N * H * W * (C / 8);
+  int blocks = grid_for(total, 148 * 8);
+  // the grid-stride must be a multiple of the channel-group count so every thread keeps its channels
+  bn_act_bwd_reduce_kernel<<<blocks, 256, 2 * C * sizeof(float), stream>>>(
+      (const __nv_bfloat16*)dapad, (const __nv_bfloat16*)y, stats, gamma, beta, (__nv_bfloat16*)g_out, sums, N, H, W, C,
+      pad_mode, inv_count, eps);
+}
+
+void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const float* gamma, const float* sums,
+                         void* dy, float* dshared, float* dplane_bias, int B, int S, int H, int W, int C,
+                         float inv_count, float eps, cudaStream_t stream) {
+  const size_t per_img = (size_t)H * W * (C / 8);
+  dim3 grid((unsigned)((per_img + 255) / 256), B);
+  const size_t smem = dplane_bias ? (size_t)S * C * sizeof(float) : 0;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr = true; }
+  bn_bwd_apply_kernel<<<grid, 256, smem, stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y, stats, gamma, sums,
+                                                   (__nv_bfloat16*)dy, dshared, dplane_bias, B, S, H, W, C, inv_count,
+                                                   eps);
+}
+
+void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, void* dz, float* dbias, size_t npix,
+                     int use_alpha, cudaStream_t stream) {
+  head_bwd_kernel<<<grid_for(npix, 148 * 8), 256, 0, stream>>>((const float4*)g_mpi, (const float4*)mpi, sign,
+                                                               (__nv_bfloat16*)dz, dbias, npix, use_alpha);
+}
+
+}  // namespace mine

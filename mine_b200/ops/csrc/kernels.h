@@ -40,3 +40,27 @@ void launch_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, 
                        float eps, float weight_decay, float bias_corr1, float bias_corr2, cudaStream_t stream);
 
 }  // namespace mine
+
+namespace mine {
+// ---- decoder_elem.cu (NHWC bf16) ---------------------------------------------------------------
+// pad_mode: 0 = reflection, 1 = replication (1 pixel); stats = [2, C] global (sum, sum of squares)
+void launch_bn_act_pad_fwd(const void* y, const float* stats, const float* gamma, const float* beta, void* out, int N,
+                           int H, int W, int C, int pad_mode, float inv_count, float eps, cudaStream_t stream);
+void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* stats, const float* gamma,
+                              const float* beta, void* g_out, float* sums, int N, int H, int W, int C, int pad_mode,
+                              float inv_count, float eps, cudaStream_t stream);
+void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const float* gamma, const float* sums,
+                         void* dy, float* dshared, float* dplane_bias, int B, int S, int H, int W, int C,
+                         float inv_count, float eps, cudaStream_t stream);
+void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, void* dz, float* dbias, size_t npix,
+                     int use_alpha, cudaStream_t stream);
+}  // namespace mine
+
+namespace mine {
+// ---- comm.cu (NVLink peer memory) -----------------------------------------------------------------
+struct PeerTable { void* ptr[16]; };
+void launch_allreduce_small(float* inout, int n, const PeerTable& data, const PeerTable& flags, int rank, int world,
+                            int cap, uint32_t epoch, cudaStream_t stream);
+void launch_allreduce_mean(const PeerTable& arena, const PeerTable& flags, float* mc_arena, int64_t lo, int64_t hi,
+                           int rank, int world, uint32_t epoch, int blocks, cudaStream_t stream);
+}  // namespace mine

@@ -69,6 +69,10 @@ def make_communicator(kind: str = "auto", device: Optional[torch.device] = None)
         return Communicator()
     on_cuda = device is not None and torch.device(device).type == "cuda"
     if kind in ("p2p", "auto") and on_cuda:
-        from .p2p import P2PComm
-        return P2PComm(device)
+        try:
+            from .p2p import P2PComm
+            return P2PComm(device)
+        except Exception as e:          # no symmetric memory on this box: say so loudly, use the library baseline
+            import warnings
+            warnings.warn(f"P2P communicator unavailable ({type(e).__name__}: {e}); falling back to NCCL")
     return TorchDistComm()

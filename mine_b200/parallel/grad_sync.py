@@ -26,7 +26,7 @@ from .comm import Communicator
 class FlatArena:
     """Re-homes the given parameters (and their ``.grad``) into contiguous fp32 buffers."""
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], align: int = 64):
+    def __init__(self, params: Sequence[torch.nn.Parameter], align: int = 64, grad_alloc=None):
         self.params = [p for p in params]
         device = self.params[0].device
         self.offsets, off = [], 0
@@ -35,7 +35,9 @@ class FlatArena:
             off += (p.numel() + align - 1) // align * align
         self.numel = off
         self.data = torch.zeros(off, dtype=torch.float32, device=device)
-        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        # ``grad_alloc(numel)`` lets the communicator place the gradient arena on its symmetric heap so
+        # the all-reduce runs in place over NVLink peer mappings
+        self.grad = grad_alloc(off) if grad_alloc is not None else torch.zeros(off, dtype=torch.float32, device=device)
         for p, o in zip(self.params, self.offsets):
             n = p.numel()
             self.data[o:o + n].copy_(p.data.reshape(-1).float())

@@ -82,9 +82,12 @@ class SynthesisTask:
                                     num_output_channels=4, scales=range(4), use_skips=True,
                                     embedder=None, embedder_out_dim=out_dim, multires=multires).to(self.device)
 
-        # flat arenas: parameters, gradients, optimizer moments
+        self.comm = comm if comm is not None else (
+            Communicator() if is_val else make_communicator(cfg_get(config, "engine.comm", "auto"), self.device))
+        # flat arenas: parameters, gradients (on the communicator's symmetric heap when it has one), moments
         n_b, n_d = len(list(self.backbone.parameters())), len(list(self.decoder.parameters()))
-        self.arena = FlatArena(list(self.backbone.parameters()) + list(self.decoder.parameters()))
+        self.arena = FlatArena(list(self.backbone.parameters()) + list(self.decoder.parameters()),
+                               grad_alloc=getattr(self.comm, "alloc_symmetric", None))
         self.optimizer = ArenaAdam(self.arena, [n_b, n_d], [config["lr.backbone_lr"], config["lr.decoder_lr"]],
                                    weight_decay=float(config["lr.weight_decay"]))
 
@@ -110,8 +113,6 @@ class SynthesisTask:
                     self.optimizer.load_state_dict(sd)
                     self.resume_meta = meta
 
-        self.comm = comm if comm is not None else (
-            Communicator() if is_val else make_communicator(cfg_get(config, "engine.comm", "auto"), self.device))
         if not is_val:
             set_stat_reducer(self.backbone, self.comm.allreduce_sum_ if self.comm.world_size > 1 else None)
             set_stat_reducer(self.decoder, self.comm.allreduce_sum_ if self.comm.world_size > 1 else None)
