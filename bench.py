@@ -49,6 +49,7 @@ def parse_args():
     p.add_argument("--shape", default="llff", choices=sorted(BENCH_SHAPES))
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-render", action="store_true")
+    p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA-graph replay per step")
     p.add_argument("--profile-phases", action="store_true", help="per-phase device times (extra syncs; not a bench value)")
     return p.parse_args()
 
@@ -192,7 +193,7 @@ def run_ours(args):
     device = ctx.device
     extra = {"data.img_w": shape["w"], "data.img_h": shape["h"], "mpi.num_bins_coarse": shape["planes"],
              "data.per_gpu_batch_size": shape["batch"], "model.imagenet_pretrained": False,
-             "training.eval_interval": 10 ** 9}
+             "training.eval_interval": 10 ** 9, "engine.cuda_graph": not args.no_graph}
     config = cfglib.config_for_dataset(shape["dataset"], extra)
     config.update({"global_rank": ctx.rank, "local_rank": ctx.local_rank, "world_size": ctx.world_size, "device": device})
     torch.manual_seed(1234 + rank)
@@ -216,6 +217,8 @@ def run_ours(args):
     launches = C.LAUNCHES["count"] - launches0
     # launches during warm-up are included in the counter delta above; subtract them proportionally
     launches = int(round(launches * args.steps / max(args.steps + args.warmup, 1)))
+    if task._graph is not None:                  # replays do not tick the Python-side counter
+        launches = int(task.launches_per_step) * args.steps
     clocks = sampler.stop(t0, t1)
     ms = max_over_ranks(ms, device)
 
@@ -231,6 +234,7 @@ def run_ours(args):
                    "dataset_shape": f"{shape['dataset']} {shape['w']}x{shape['h']} N={shape['planes']}",
                    "global_batch": world * shape["batch"], "per_gpu_batch": shape["batch"], "seq_len": shape["planes"],
                    "parallelism": f"dp{world}", "conv_engine": task.runner.mode, "comm": task.comm.name,
+                   "cuda_graph": task._graph is not None,
                    "l2": "256 MiB buffer rewritten between steps inside the timed region"},
         "clocks": clocks, "gpu_launches": launches,
     }
@@ -249,6 +253,7 @@ def run_ours(args):
                          "api": "SynthesisTask.train_step(batch in pinned host memory) + loss.item()"}
 
     if args.profile_phases:
+        task._graph, task._want_graph = None, False
         task.profiler.enabled = True
         for i in range(5):
             step_dev(i)

@@ -71,6 +71,15 @@ def _pad_co(w_pack: torch.Tensor) -> torch.Tensor:
 
 _PHASE = torch.tensor([[[1.0, 0.0, 0.0], [0.0, 1.0, 1.0]],      # phase 0: taps {k0}, {k1 + k2}
                        [[1.0, 1.0, 0.0], [0.0, 0.0, 1.0]]])     # phase 1: taps {k0 + k1}, {k2}
+_PHASE_CACHE: Dict = {}
+
+
+def _phase(device, dtype) -> torch.Tensor:
+    """Device-resident copy (a host->device copy is illegal inside CUDA-graph capture)."""
+    key = (str(device), dtype)
+    if key not in _PHASE_CACHE:
+        _PHASE_CACHE[key] = _PHASE.to(device, dtype)
+    return _PHASE_CACHE[key]
 
 
 def pack_same(w: torch.Tensor) -> torch.Tensor:
@@ -80,14 +89,14 @@ def pack_same(w: torch.Tensor) -> torch.Tensor:
 
 def pack_up(w: torch.Tensor) -> torch.Tensor:
     """[Co, Ci, 3, 3] -> phase pack [4 (py*2+px), 4 (a*2+b), Co, Ci] of the 2x2 sub-pixel kernels."""
-    m = _PHASE.to(w.device, w.dtype)
+    m = _phase(w.device, w.dtype)
     wp = torch.einsum("pak,qbl,oikl->pqaboi", m, m, w)
     return wp.reshape(4, 4, w.shape[0], w.shape[1])
 
 
 def unpack_up_grad(dwp: torch.Tensor) -> torch.Tensor:
     """adjoint of :func:`pack_up`: [4,4,Co,Ci] -> [Co,Ci,3,3]."""
-    m = _PHASE.to(dwp.device, dwp.dtype)
+    m = _phase(dwp.device, dwp.dtype)
     co, ci = dwp.shape[-2:]
     return torch.einsum("pak,qbl,pqaboi->oikl", m, m, dwp.reshape(2, 2, 2, 2, co, ci))
 

@@ -125,13 +125,14 @@ std::vector<at::Tensor> masked_l1_fwd(const at::Tensor& a, const at::Tensor& b, 
   return {sum, sign};
 }
 
-void fused_adam(at::Tensor p, const at::Tensor& g, at::Tensor m, at::Tensor v, double lr, double beta1, double beta2,
-                double eps, double wd, double bc1, double bc2) {
-  check_f32(p, "p"); check_f32(g, "g"); check_f32(m, "m"); check_f32(v, "v");
+void fused_adam(at::Tensor p, const at::Tensor& g, at::Tensor m, at::Tensor v, const at::Tensor& hyper, double beta1,
+                double beta2, double eps, double wd) {
+  check_f32(p, "p"); check_f32(g, "g"); check_f32(m, "m"); check_f32(v, "v"); check_f32(hyper, "hyper");
+  TORCH_CHECK(hyper.numel() == 2, "hyper = {lr, step}");
   c10::cuda::CUDAGuard guard(p.device());
   mine::launch_fused_adam(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
-                          p.numel(), (float)lr, (float)beta1, (float)beta2, (float)eps, (float)wd, (float)bc1,
-                          (float)bc2, cur_stream());
+                          p.numel(), hyper.data_ptr<float>(), (float)beta1, (float)beta2, (float)eps, (float)wd,
+                          cur_stream());
 }
 
 }  // namespace

@@ -36,8 +36,9 @@ void launch_masked_l1_fwd(const float* a, const float* b, const float* mask, flo
                           float* grad_sign, int B, int C, int HW, cudaStream_t stream);
 
 // ---- adam.cu -------------------------------------------------------------------------------
-void launch_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                       float eps, float weight_decay, float bias_corr1, float bias_corr2, cudaStream_t stream);
+// hyper: device array {lr, step}
+void launch_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1,
+                       float beta2, float eps, float weight_decay, cudaStream_t stream);
 
 }  // namespace mine
 

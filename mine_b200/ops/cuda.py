@@ -159,7 +159,7 @@ def edge_aware_loss_v2(img, disp) -> torch.Tensor:
 
 
 # ---- optimizer -----------------------------------------------------------------------------------
-def fused_adam_(p, g, m, v, lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2) -> None:
-    _ext.fused_adam(p, g, m, v, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
-                    float(bias_corr1), float(bias_corr2))
+def fused_adam_(p, g, m, v, hyper, beta1, beta2, eps, weight_decay) -> None:
+    """``hyper``: device fp32 tensor ``[lr, step]`` (bias corrections are derived in-kernel)."""
+    _ext.fused_adam(p, g, m, v, hyper, float(beta1), float(beta2), float(eps), float(weight_decay))
     _count()

@@ -28,6 +28,7 @@ class ArenaAdam:
         self.exp_avg = torch.zeros_like(arena.data)
         self.exp_avg_sq = torch.zeros_like(arena.data)
         self.step_count = 0
+        self._hyper = None                       # per group device tensor [lr, step] (CUDA path)
         self.param_groups: List[Dict] = []
         first = 0
         for n, lr in zip(group_sizes, lrs):
@@ -42,6 +43,17 @@ class ArenaAdam:
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.arena.zero_grad()
 
+    def sync_hyper(self) -> None:
+        """Push (lr, step) of every group to the device.  Called outside captured regions (after a
+        checkpoint restore or a scheduler step); inside a step only ``step += 1`` happens, on the device."""
+        if not self.arena.data.is_cuda:
+            return
+        if self._hyper is None:
+            self._hyper = [torch.zeros(2, dtype=torch.float32, device=self.arena.data.device) for _ in self.param_groups]
+        for h, g in zip(self._hyper, self.param_groups):
+            h.copy_(torch.tensor([g["lr"], float(self.step_count)], dtype=torch.float32), non_blocking=True)
+            g["_lr_on_device"] = g["lr"]
+
     @torch.no_grad()
     def step(self) -> None:
         self.step_count += 1
@@ -49,13 +61,19 @@ class ArenaAdam:
         bc1 = 1.0 - b1 ** self.step_count
         bc2 = 1.0 - b2 ** self.step_count
         use_kernel = self.arena.data.is_cuda and os.environ.get("MINE_B200_FORCE_SPEC", "0") != "1"
-        for g in self.param_groups:
+        if use_kernel and (self._hyper is None or any(g.get("_lr_on_device") != g["lr"] for g in self.param_groups)):
+            self.step_count -= 1
+            self.sync_hyper()
+            self.step_count += 1
+        for gi, g in enumerate(self.param_groups):
             lo, hi = g["_range"]
             p, gr = self.arena.data[lo:hi], self.arena.grad[lo:hi]
             m, v = self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi]
             if use_kernel:
                 from .ops import cuda as C
-                C.fused_adam_(p, gr, m, v, g["lr"], b1, b2, self.eps, self.weight_decay, bc1, bc2)
+                h = self._hyper[gi]
+                h[1:2].add_(1.0)                 # device-side step counter (graph-replay safe)
+                C.fused_adam_(p, gr, m, v, h, b1, b2, self.eps, self.weight_decay)
                 continue
             grad = gr.add(p, alpha=self.weight_decay) if self.weight_decay != 0 else gr
             m.mul_(b1).add_(grad, alpha=1 - b1)
@@ -72,7 +90,7 @@ class ArenaAdam:
                 state[i] = {"step": torch.tensor(float(self.step_count)),
                             "exp_avg": self.exp_avg[o:o + n].view(p.shape).detach().cpu().clone(),
                             "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).detach().cpu().clone()}
-        groups = [{k: v for k, v in g.items() if k != "_range"} for g in self.param_groups]
+        groups = [{k: v for k, v in g.items() if not k.startswith("_")} for g in self.param_groups]
         return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd: Dict) -> None:
@@ -88,6 +106,7 @@ class ArenaAdam:
         for g, saved in zip(self.param_groups, sd.get("param_groups", [])):
             g["lr"] = float(saved.get("lr", g["lr"]))
             g["initial_lr"] = float(saved.get("initial_lr", g["initial_lr"]))
+        self.sync_hyper()
 
 
 class MultiStepLR:
@@ -102,6 +121,8 @@ class MultiStepLR:
         k = sum(1 for m in self.milestones if m <= self.last_epoch)
         for g in self.optimizer.param_groups:
             g["lr"] = g.get("initial_lr", g["lr"]) * (self.gamma ** k)
+        if hasattr(self.optimizer, "sync_hyper"):
+            self.optimizer.sync_hyper()
 
     def step(self):
         self.last_epoch += 1

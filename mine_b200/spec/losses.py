@@ -30,8 +30,11 @@ def _gauss_1d(size: int, sigma: float) -> Tuple[float, ...]:
 
 def gaussian_window(channels: int, size: int = SSIM_WINDOW, sigma: float = SSIM_SIGMA,
                     dtype=torch.float32, device=None) -> torch.Tensor:
-    g = torch.tensor(_gauss_1d(size, sigma), dtype=dtype, device=device)
-    return torch.outer(g, g)[None, None].expand(channels, 1, size, size).contiguous()
+    key = ("gauss", str(device), dtype, channels, size, sigma)
+    if key not in _CONST_CACHE:
+        g = torch.tensor(_gauss_1d(size, sigma), dtype=dtype)
+        _CONST_CACHE[key] = torch.outer(g, g)[None, None].expand(channels, 1, size, size).contiguous().to(device)
+    return _CONST_CACHE[key]
 
 
 def ssim_map(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -72,14 +75,26 @@ def psnr(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return (20.0 * torch.log10(1.0 / torch.sqrt(mse))).mean()
 
 
+_CONST_CACHE = {}
+
+
+def _sobel_kernels(device: str, dtype, normalized: bool) -> torch.Tensor:
+    """Cached per device: creating constants from Python lists is a host->device copy, which is illegal
+    inside CUDA-graph capture."""
+    key = ("sobel", device, dtype, normalized)
+    if key not in _CONST_CACHE:
+        kx = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]], dtype=dtype)
+        if normalized:
+            kx = kx / 8.0
+        _CONST_CACHE[key] = torch.stack([kx, kx.t()])[:, None].to(device)
+    return _CONST_CACHE[key]
+
+
 def sobel_gradients(x: torch.Tensor, normalized: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """Per-channel Sobel d/dx, d/dy with replicate padding (what kornia's ``spatial_gradient``
     computes; ``normalized`` divides the kernel by its L1 norm = 8)."""
     b, c, h, w = x.shape
-    kx = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]], dtype=x.dtype, device=x.device)
-    if normalized:
-        kx = kx / 8.0
-    k = torch.stack([kx, kx.t()])[:, None]                                       # 2,1,3,3
+    k = _sobel_kernels(str(x.device), x.dtype, bool(normalized))                  # 2,1,3,3
     xp = F.pad(x.reshape(b * c, 1, h, w), (1, 1, 1, 1), mode="replicate")
     g = F.conv2d(xp, k).reshape(b, c, 2, h, w)
     return g[:, :, 0], g[:, :, 1]

@@ -145,6 +145,8 @@ class SynthesisTask:
         self.global_step = 0
         self.profiler = PhaseProfiler(enabled=False)
         self._gen = None
+        self._graph, self._graph_out, self._static = None, None, None
+        self._want_graph = bool(cfg_get(config, "engine.cuda_graph", False)) and not is_val
         if self.resume_meta and cfg_get(config, "engine.resume", True):
             self._apply_resume(self.resume_meta)
 
@@ -321,7 +323,61 @@ class SynthesisTask:
     # training
     # ------------------------------------------------------------------------------------------
     def train_step(self, items) -> Dict[str, torch.Tensor]:
-        """One optimisation step on a batch in the reference format (no host sync)."""
+        """One optimisation step on a batch in the reference format (no host sync).  With
+        ``engine.cuda_graph`` the whole step (forward, losses, backward, Adam) is ONE graph replay."""
+        if self._graph is None and self._want_graph and self.comm.world_size == 1 and self.device.type == "cuda":
+            self.enable_cuda_graph(items)
+        if self._graph is not None:
+            self._load_static(items)
+            self._graph.replay()
+            self.global_step += 1
+            self.optimizer.step_count += 1
+            return self._graph_out
+        return self._train_step_eager(items)
+
+    # -- CUDA graph capture of the full step -------------------------------------------------------
+    def _load_static(self, items) -> None:
+        for dst, src in zip(self._static, items):
+            for k, t in dst.items():
+                t.copy_(src[k], non_blocking=True)
+
+    def enable_cuda_graph(self, example_items, warmup: int = 3) -> None:
+        """Capture ``_train_step_eager`` (launch-bound: ~1.5 k kernels of a few microseconds each) into a
+        CUDA graph.  Model / optimizer / BN state is snapshotted around the warm-up replays so enabling the
+        graph does not consume training steps.  Host-side scalars that change per step live on the device
+        (Adam's step counter / lr, BN counters), so replays stay exact."""
+        dev = self.device
+        keys_src = ("img", "K", "K_inv", "xyzs")
+        keys_tgt = ("img", "K", "K_inv", "xyzs", "G_src_tgt")
+        src, tgt = example_items
+        self._static = ({k: src[k].to(dev, dtype=torch.float32).clone() for k in keys_src},
+                        {k: tgt[k].to(dev, dtype=torch.float32).clone() for k in keys_tgt})
+        bufs = [self.arena.data, self.optimizer.exp_avg, self.optimizer.exp_avg_sq]
+        bufs += [b for m in (self.backbone, self.decoder) for b in m.buffers()]
+        self.optimizer.sync_hyper()
+        bufs += list(self.optimizer._hyper)
+        snap = [b.clone() for b in bufs]
+        step0, gstep0 = self.optimizer.step_count, self.global_step
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._train_step_eager(self._static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from .ops import cuda as _K
+        n0 = _K.LAUNCHES["count"]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._train_step_eager(self._static)
+        self.launches_per_step = _K.LAUNCHES["count"] - n0        # our kernels inside one replay
+        with torch.no_grad():
+            for b, s_ in zip(bufs, snap):
+                b.copy_(s_)
+        self.optimizer.step_count, self.global_step = step0, gstep0
+        self._graph, self._graph_out = graph, out
+
+    def _train_step_eager(self, items) -> Dict[str, torch.Tensor]:
         self.global_step += 1
         self.set_data(items)
         self.grad_sync.begin_step()

@@ -1,0 +1,89 @@
+"""Multi-process plumbing on CPU (gloo, world_size 2): cross-replica BN statistics + bucketed gradient
+averaging reproduce a single-process run on the concatenated batch ("DDP equivalence")."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = {"data.img_w": 128, "data.img_h": 96, "mpi.num_bins_coarse": 3, "data.visible_point_count": 32,
+       "model.imagenet_pretrained": False, "mpi.fix_disparity": True, "loss.smoothness_lambda_v2": 0.01,
+       "lr.backbone_lr": 0.0, "lr.decoder_lr": 0.0}      # lr 0: compare synchronised GRADIENTS (Adam would turn
+                                                          # fp noise on ~zero gradients into +-lr updates)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_task(batch, rank=0):
+    from mine_b200 import config as C
+    from mine_b200.task import SynthesisTask
+    cfg = C.config_for_dataset("llff", dict(CFG, **{"data.per_gpu_batch_size": batch}))
+    cfg["device"] = torch.device("cpu")
+    cfg["global_rank"] = rank
+    torch.manual_seed(0)
+    return SynthesisTask(cfg, None), cfg
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
+                       "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank)})
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mine_b200.data.synthetic import synthetic_batch
+    task, cfg = _make_task(1, rank)
+    assert task.comm.world_size == world and task.grad_sync.enabled
+    for step in range(2):
+        items = synthetic_batch(2, 96, 128, 32, seed=step)
+        mine = tuple({k: v[rank:rank + 1] for k, v in d.items()} for d in items)
+        task.train_step(mine)
+    torch.save({"params": task.arena.grad.clone(), "rm": task.decoder.blocks["upconv_2_1"].bn.running_mean.clone()},
+               os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_training_equals_single_process(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(tmp_path / "rank0.pt")
+    r1 = torch.load(tmp_path / "rank1.pt")
+    assert torch.equal(r0["params"], r1["params"]), "replicas diverged"
+    assert torch.equal(r0["rm"], r1["rm"])
+    from mine_b200.data.synthetic import synthetic_batch
+    task, _ = _make_task(2)
+    for step in range(2):
+        task.train_step(synthetic_batch(2, 96, 128, 32, seed=step))
+    ref = task.arena.grad
+    # fp32 + BatchNorm over 3x4 feature maps is badly conditioned: summation order alone moves individual
+    # tensors by ~1 %; semantics are checked through the direction and size of the whole gradient
+    cos = torch.nn.functional.cosine_similarity(r0["params"], ref, dim=0).item()
+    rel = (r0["params"] - ref).norm().item() / ref.norm().item()
+    assert cos > 0.999 and rel < 5e-2, (cos, rel)
+    assert torch.allclose(r0["rm"], task.decoder.blocks["upconv_2_1"].bn.running_mean, rtol=1e-3, atol=1e-5)
+
+
+def test_sharded_sampler_partitions_dataset():
+    from mine_b200.data.loader import ShardedSampler
+
+    class DS:
+        def __len__(self):
+            return 10
+    seen = []
+    for r in range(3):
+        s = ShardedSampler(DS(), 3, r, shuffle=True, seed=5)
+        s.set_epoch(2)
+        idx = list(s)
+        assert len(idx) == 4
+        seen += idx
+    assert set(seen) == set(range(10))
