@@ -49,7 +49,7 @@ def strip_module_prefix(sd: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tenso
 
 
 def backbone_to_reference(backbone, module_prefix: bool = True, include_fc: bool = True) -> Dict[str, torch.Tensor]:
-    sd = {k: v.detach().clone() for k, v in backbone.state_dict().items()}
+    sd = {k: v.detach().contiguous().clone() for k, v in backbone.state_dict().items()}
     if include_fc:
         for k, shape in FC_SHAPES.items():
             sd[k] = torch.zeros(shape)
@@ -61,7 +61,7 @@ def decoder_to_reference(decoder, module_prefix: bool = True) -> Dict[str, torch
     out = {}
     for k, v in decoder.state_dict().items():
         rk = _rename(k, table)
-        out["module." + rk if module_prefix else rk] = v.detach().clone()
+        out["module." + rk if module_prefix else rk] = v.detach().contiguous().clone()
     return out
 
 

@@ -183,12 +183,21 @@ def dgrad_up_raw(dy, w):
     return out
 
 
+def _wgrad_pixels(co: int, ci: int, h: int, w: int) -> int:
+    """Pixels per K step: aim at ~8 KB per TMA box (tiny boxes are issue-bound), keep the tile inside the map."""
+    kp = 8192 // (2 * min(64, max(co, ci)))
+    kp = max(32, min(256, kp))
+    while kp > 32 and kp > h * w:
+        kp //= 2
+    return kp
+
+
 def wgrad_same_raw(dy, xpad):
     """``dW [Co,Ci,3,3]`` (fp32) of :func:`conv_same_raw`."""
     n, h, w_, co = dy.shape
     ci = xpad.shape[3]
     dw = torch.zeros((9, co, ci), dtype=torch.float32, device=dy.device)
-    th, tw = pick_tile(h, w_, 32)
+    th, tw = pick_tile(h, w_, _wgrad_pixels(co, ci, h, w_))
     ext().wgrad_taps(dy, xpad, dw, h, w_, 1, 9, SAME_TAPS_Y, SAME_TAPS_X, 1, [0], [0], th, tw)
     _count(2)
     return dw.reshape(3, 3, co, ci).permute(2, 3, 0, 1)
@@ -200,7 +209,7 @@ def wgrad_up_raw(dy, xpad_lo):
     h, w_ = h2 // 2, w2 // 2
     ci = xpad_lo.shape[3]
     dwp = torch.zeros((16, co, ci), dtype=torch.float32, device=dy.device)
-    th, tw = pick_tile(h, w_, 32)
+    th, tw = pick_tile(h, w_, min(128, _wgrad_pixels(co, ci, h, w_)))      # strided dy box: 2*TW <= 256
     ext().wgrad_taps(dy, xpad_lo, dwp, h, w_, 4, 4, UP_TAPS_Y, UP_TAPS_X, 2, UP_OY, UP_OX, th, tw)
     _count(2)
     return unpack_up_grad(dwp.reshape(4, 4, co, ci))

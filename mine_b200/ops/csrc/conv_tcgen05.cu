@@ -154,17 +154,20 @@ constexpr int kMaxStages = 8;
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const ConvParams p) {
+  // Persistent: every CTA walks work items (group, image, tile) with a grid stride.  The smem ring runs
+  // across tile boundaries and the accumulator is double buffered in TMEM, so the TMA/MMA of tile i+1
+  // overlap the epilogue of tile i and the per-CTA setup (barriers, TMEM allocation) is paid once.
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t accum_full[2];
+  __shared__ __align__(8) uint64_t accum_empty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_stats[2][256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, n_img = blockIdx.y, g = blockIdx.z;
-  const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-  const int oy0 = tile_y * p.TH, ox0 = tile_x * p.TW;
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int total_work = tiles * p.N * p.G;
 
   const int row_bytes = p.KB * 2;                     // == swizzle span
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
@@ -175,7 +178,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&accum_full[s], 1); mbar_init(&accum_empty[s], 4); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_stats[0][0])[i] = 0.f;
@@ -188,16 +191,22 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int iters = p.T * p.kblocks;
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages, round = it / p.stages;
-        if (it >= p.stages) mbar_wait(&empty_bar[s], (round - 1) & 1);
-        const int t = it / p.kblocks, kb = it - t * p.kblocks;
-        uint8_t* a_dst = smem_aligned + (size_t)s * stage_bytes;
-        uint8_t* b_dst = a_dst + a_bytes;
-        mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
-        const int iy = oy0 * p.in_stride + p.tap_y[g][t], ix = ox0 * p.in_stride + p.tap_x[g][t];
-        tma_load_4d(&map_x, &full_bar[s], a_dst, kb * p.KB, ix, iy, n_img);
-        tma_load_3d(&map_w, &full_bar[s], b_dst, kb * p.KB, 0, g * p.T + t);
+      int it = 0;                                       // ring position, continues across tiles
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tile = w % tiles, n_img = (w / tiles) % p.N, g = w / (tiles * p.N);
+        const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+        const int oy0 = tile_y * p.TH, ox0 = tile_x * p.TW;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % p.stages, round = it / p.stages;
+          if (it >= p.stages) mbar_wait(&empty_bar[s], (round - 1) & 1);
+          const int t = i / p.kblocks, kb = i - t * p.kblocks;
+          uint8_t* a_dst = smem_aligned + (size_t)s * stage_bytes;
+          uint8_t* b_dst = a_dst + a_bytes;
+          mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+          const int iy = oy0 * p.in_stride + p.tap_y[g][t], ix = ox0 * p.in_stride + p.tap_x[g][t];
+          tma_load_4d(&map_x, &full_bar[s], a_dst, kb * p.KB, ix, iy, n_img);
+          tma_load_3d(&map_w, &full_bar[s], b_dst, kb * p.KB, 0, g * p.T + t);
+        }
       }
     }
   } else if (warp == 1) {
@@ -205,102 +214,121 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
       const uint32_t lt = layout_type_for(row_bytes);
       const uint32_t sbo = 8u * row_bytes;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages, round = it / p.stages;
-        mbar_wait(&full_bar[s], round & 1);
+      int it = 0, j = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
+        const int as = j & 1;
+        if (j >= 2) mbar_wait(&accum_empty[as], ((j >> 1) - 1) & 1);     // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        for (int k = 0; k < p.KB / 16; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, lt);
-          const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, lt);
-          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % p.stages, round = it / p.stages;
+          mbar_wait(&full_bar[s], round & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
+          const uint32_t b_addr = a_addr + a_bytes;
+          for (int k = 0; k < p.KB / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, lt);
+            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, lt);
+            umma_bf16(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
         }
-        umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
+        umma_commit(&accum_full[as]);           // accumulator of this tile complete
       }
-      umma_commit(&accum_bar);                // accumulator complete
     }
   } else {
     // ---------------- epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) ----------------
     const int q = warp & 3;
     const int r = q * 32 + lane;                       // row of the 128-pixel tile
     const int ty = r / p.TW, tx = r - ty * p.TW;
-    const int oy = oy0 + ty, ox = ox0 + tx;
-    const bool valid = (oy < p.Hg) && (ox < p.Wg);
-    const int out_y = oy * p.out_sy + p.out_oy[g], out_x = ox * p.out_sx + p.out_ox[g];
-    const size_t out_pix = ((size_t)n_img * p.Ho + out_y) * p.Wo + out_x;
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    const float* pbias = p.plane_bias ? p.plane_bias + (size_t)n_img * p.Co : nullptr;
-    const float* smap = nullptr;
-    if (p.shared_map && valid) smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (c0 >= p.Co) continue;
-      float f[16];
+    int j = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
+      const int tile = w % tiles, n_img = (w / tiles) % p.N, g = w / (tiles * p.N);
+      const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+      const int oy = tile_y * p.TH + ty, ox = tile_x * p.TW + tx;
+      const bool valid = (oy < p.Hg) && (ox < p.Wg);
+      const int out_y = oy * p.out_sy + p.out_oy[g], out_x = ox * p.out_sx + p.out_ox[g];
+      const size_t out_pix = ((size_t)n_img * p.Ho + out_y) * p.Wo + out_x;
+      const int as = j & 1;
+      mbar_wait(&accum_full[as], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (uint32_t)(as * p.BN) + ((uint32_t)(q * 32) << 16);
+      const float* pbias = p.plane_bias ? p.plane_bias + (size_t)n_img * p.Co : nullptr;
+      const float* smap = nullptr;
+      if (p.shared_map && valid)
+        smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_acc + (uint32_t)c0, v);
+        if (c0 >= p.Co) continue;
+        float f[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-      if (p.chan_bias) {
+        for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(v[jj]);
+        if (p.chan_bias) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) if (c0 + j < p.Co) f[j] += p.chan_bias[c0 + j];
-      }
-      if (pbias) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) if (c0 + j < p.Co) f[j] += pbias[c0 + j];
-      }
-      if (smap) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 m = *reinterpret_cast<const float4*>(smap + c0 + j);
-          f[j] += m.x; f[j + 1] += m.y; f[j + 2] += m.z; f[j + 3] += m.w;
+          for (int jj = 0; jj < 16; ++jj) if (c0 + jj < p.Co) f[jj] += p.chan_bias[c0 + jj];
         }
+        if (pbias) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) if (c0 + jj < p.Co) f[jj] += pbias[c0 + jj];
+        }
+        if (smap) {
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 4) {
+            const float4 m = *reinterpret_cast<const float4*>(smap + c0 + jj);
+            f[jj] += m.x; f[jj + 1] += m.y; f[jj + 2] += m.z; f[jj + 3] += m.w;
+          }
+        }
+        if (p.stats) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float x = valid ? f[jj] : 0.f;
+            const float s1 = warp_sum32(x), s2 = warp_sum32(x * x);
+            if (lane == 0) { atomicAdd(&s_stats[0][c0 + jj], s1); atomicAdd(&s_stats[1][c0 + jj], s2); }
+          }
+        }
+        if (valid) {
+          if (p.act == 1) {                     // MPI head: 4 real channels -> packed fp32 MPI (+ sign of sigma)
+            float4 o;
+            o.x = 1.f / (1.f + __expf(-f[0])); o.y = 1.f / (1.f + __expf(-f[1])); o.z = 1.f / (1.f + __expf(-f[2]));
+            o.w = p.head_alpha ? 1.f / (1.f + __expf(-f[3])) : fabsf(f[3]) + 1e-4f;
+            reinterpret_cast<float4*>(p.out)[out_pix] = o;
+            if (p.raw_out) reinterpret_cast<int8_t*>(p.raw_out)[out_pix] = f[3] >= 0.f ? (int8_t)1 : (int8_t)-1;
+          } else if (p.out_fp32) {
+            float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + c0;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) {
+              float4 o = make_float4(f[jj], f[jj + 1], f[jj + 2], f[jj + 3]);
+              if (p.accumulate) { const float4 e = *reinterpret_cast<float4*>(dst + jj); o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
+              *reinterpret_cast<float4*>(dst + jj) = o;
+            }
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + c0;
+            if (p.accumulate) {
+              const uint4 e0 = *reinterpret_cast<const uint4*>(dst), e1 = *reinterpret_cast<const uint4*>(dst + 8);
+              const __nv_bfloat16* eb0 = reinterpret_cast<const __nv_bfloat16*>(&e0);
+              const __nv_bfloat16* eb1 = reinterpret_cast<const __nv_bfloat16*>(&e1);
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) { f[jj] += __bfloat162float(eb0[jj]); f[8 + jj] += __bfloat162float(eb1[jj]); }
+            }
+            uint4 o0, o1;
+            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              h0[jj] = __floats2bfloat162_rn(f[2 * jj], f[2 * jj + 1]);
+              h1[jj] = __floats2bfloat162_rn(f[8 + 2 * jj], f[8 + 2 * jj + 1]);
+            }
+            *reinterpret_cast<uint4*>(dst) = o0;
+            *reinterpret_cast<uint4*>(dst + 8) = o1;
+          }
+        }
+        __syncwarp();
       }
-      if (p.stats) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float x = valid ? f[j] : 0.f;
-          const float s1 = warp_sum32(x), s2 = warp_sum32(x * x);
-          if (lane == 0) { atomicAdd(&s_stats[0][c0 + j], s1); atomicAdd(&s_stats[1][c0 + j], s2); }
-        }
-      }
-      if (valid) {
-      if (p.act == 1) {                       // MPI head: 4 real channels -> packed fp32 MPI (+ raw pre-activation)
-        float4 o;
-        o.x = 1.f / (1.f + __expf(-f[0])); o.y = 1.f / (1.f + __expf(-f[1])); o.z = 1.f / (1.f + __expf(-f[2]));
-        o.w = p.head_alpha ? 1.f / (1.f + __expf(-f[3])) : fabsf(f[3]) + 1e-4f;
-        reinterpret_cast<float4*>(p.out)[out_pix] = o;
-        if (p.raw_out) reinterpret_cast<int8_t*>(p.raw_out)[out_pix] = f[3] >= 0.f ? (int8_t)1 : (int8_t)-1;
-      } else if (p.out_fp32) {
-        float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + c0;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          if (p.accumulate) { const float4 e = *reinterpret_cast<float4*>(dst + j); o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
-          *reinterpret_cast<float4*>(dst + j) = o;
-        }
-      } else {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + c0;
-        if (p.accumulate) {
-          const uint4 e0 = *reinterpret_cast<const uint4*>(dst), e1 = *reinterpret_cast<const uint4*>(dst + 8);
-          const __nv_bfloat16* eb0 = reinterpret_cast<const __nv_bfloat16*>(&e0);
-          const __nv_bfloat16* eb1 = reinterpret_cast<const __nv_bfloat16*>(&e1);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { f[j] += __bfloat162float(eb0[j]); f[8 + j] += __bfloat162float(eb1[j]); }
-        }
-        uint4 o0, o1;
-        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          h0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          h1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-        }
-        *reinterpret_cast<uint4*>(dst) = o0;
-        *reinterpret_cast<uint4*>(dst + 8) = o1;
-      }
-    }   // valid
+      // this warp has finished reading the accumulator: hand it back to the MMA issuer
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(&accum_empty[as]);
     }
     if (p.stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");         // epilogue warps only
@@ -526,14 +554,22 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   p.kblocks = p.Ci / p.KB;
   p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
   p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
-  p.tmem_cols = next_pow2_cols(p.BN);
+  p.tmem_cols = next_pow2_cols(2 * p.BN);                  // double-buffered accumulator
   const uint32_t stage_bytes = ((128u * p.KB * 2 + (uint32_t)p.BN * p.KB * 2 + 1023u) / 1024u) * 1024u;
-  int stages = (int)(100u * 1024u / stage_bytes);
-  if (stages > 6) stages = 6;
-  if (stages < 2) stages = 2;
-  if (stages > p.T * p.kblocks) stages = p.T * p.kblocks;
+  int stages = (int)(64u * 1024u / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 3) stages = 3;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  size_t smem = (size_t)stages * stage_bytes + 1024;
+  // resident CTAs per SM: limited by TMEM columns (512) and shared memory; pad smem so exactly that many fit
+  int ctas_per_sm = 512 / p.tmem_cols;
+  const int by_smem = (int)((220u * 1024u) / (smem + 2048));
+  if (ctas_per_sm > by_smem) ctas_per_sm = by_smem;
+  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const size_t smem_floor = (220u * 1024u) / (ctas_per_sm + 1) + 1024;   // one more CTA must NOT fit
+  if (smem < smem_floor) smem = smem_floor;
+  if (smem > 200u * 1024u) smem = 200u * 1024u;
   CUtensorMap mx, mw;
   const char* e = nhwc_map(&mx, L.x, p.Ci, L.Wi, L.Hi, p.N, p.KB, p.TW, p.TH, p.in_stride);
   if (e) return e;
@@ -544,15 +580,19 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
     cudaFuncSetAttribute(conv_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  dim3 grid(p.tiles_x * p.tiles_y, p.N, p.G);
-  conv_taps_kernel<<<grid, kConvThreads, smem, stream>>>(mx, mw, p);
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int total_work = p.tiles_x * p.tiles_y * p.N * p.G;
+  int grid_x = num_sms * ctas_per_sm;
+  if (grid_x > total_work) grid_x = total_work;
+  conv_taps_kernel<<<grid_x, kConvThreads, smem, stream>>>(mx, mw, p);
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
 }
 
 const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
   WgradParams p = L.p;
-  if (p.TH * p.TW != p.KP || (p.KP != 32 && p.KP != 64)) return "wgrad pixel tile must be 32 or 64 pixels";
+  if (p.TH * p.TW != p.KP || p.KP % 16 || p.KP < 32 || p.KP > 256) return "wgrad pixel tile must be 32..256 pixels";
   // operand slabs: channel block = min(C, 64) with the matching swizzle
   p.a_cb = p.Co < 64 ? p.Co : 64;
   p.b_cb = p.Ci < 64 ? p.Ci : 64;
@@ -565,10 +605,10 @@ const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
   p.ci_blocks = p.Ci / p.NB;
   p.taps_per_chunk = 512 / p.NB;
   if (p.taps_per_chunk > p.T) p.taps_per_chunk = p.T;
-  // keep the stage under ~48 KB
+  // keep the stage under ~96 KB (>= 2 stages in flight)
   for (;;) {
     const uint32_t sb = (uint32_t)p.KP * p.a_cb * 2 * p.a_slabs + (uint32_t)p.KP * p.b_cb * 2 * p.b_slabs * p.taps_per_chunk;
-    if (sb <= 48 * 1024 || p.taps_per_chunk == 1) break;
+    if (sb <= 96 * 1024 || p.taps_per_chunk == 1) break;
     p.taps_per_chunk = (p.taps_per_chunk + 1) / 2;
   }
   p.tap_chunks = (p.T + p.taps_per_chunk - 1) / p.taps_per_chunk;

@@ -85,11 +85,10 @@ class ArenaAdam:
     def state_dict(self) -> Dict:
         state = {}
         if self.step_count > 0:
-            for i, (p, o) in enumerate(zip(self.arena.params, self.arena.offsets)):
-                n = p.numel()
+            for i in range(len(self.arena.params)):
                 state[i] = {"step": torch.tensor(float(self.step_count)),
-                            "exp_avg": self.exp_avg[o:o + n].view(p.shape).detach().cpu().clone(),
-                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).detach().cpu().clone()}
+                            "exp_avg": self.arena.view_of(self.exp_avg, i).detach().cpu().contiguous().clone(),
+                            "exp_avg_sq": self.arena.view_of(self.exp_avg_sq, i).detach().cpu().contiguous().clone()}
         groups = [{k: v for k, v in g.items() if not k.startswith("_")} for g in self.param_groups]
         return {"state": state, "param_groups": groups}
 
@@ -97,10 +96,9 @@ class ArenaAdam:
         steps = []
         for i, st in sd.get("state", {}).items():
             i = int(i)
-            p, o = self.arena.params[i], self.arena.offsets[i]
-            n = p.numel()
-            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
-            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            shape = self.arena.params[i].shape
+            self.arena.view_of(self.exp_avg, i).copy_(st["exp_avg"].reshape(shape))
+            self.arena.view_of(self.exp_avg_sq, i).copy_(st["exp_avg_sq"].reshape(shape))
             steps.append(int(float(st["step"])))
         self.step_count = max(steps) if steps else 0
         for g, saved in zip(self.param_groups, sd.get("param_groups", [])):

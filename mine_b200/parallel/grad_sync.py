@@ -26,7 +26,8 @@ from .comm import Communicator
 class FlatArena:
     """Re-homes the given parameters (and their ``.grad``) into contiguous fp32 buffers."""
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], align: int = 64, grad_alloc=None):
+    def __init__(self, params: Sequence[torch.nn.Parameter], align: int = 64, grad_alloc=None,
+                 channels_last: bool = True):
         self.params = [p for p in params]
         device = self.params[0].device
         self.offsets, off = [], 0
@@ -38,17 +39,29 @@ class FlatArena:
         # ``grad_alloc(numel)`` lets the communicator place the gradient arena on its symmetric heap so
         # the all-reduce runs in place over NVLink peer mappings
         self.grad = grad_alloc(off) if grad_alloc is not None else torch.zeros(off, dtype=torch.float32, device=device)
-        for p, o in zip(self.params, self.offsets):
-            n = p.numel()
-            self.data[o:o + n].copy_(p.data.reshape(-1).float())
-            p.data = self.data[o:o + n].view(p.shape)
-            p.grad = self.grad[o:o + n].view(p.shape)
+        # 4-D (convolution) weights are stored channels-last inside the arena: cuDNN then consumes them
+        # without per-step NCHW<->NHWC conversion kernels, and the tcgen05 packers read contiguous Ci.
+        self.channels_last = [bool(channels_last and p.dim() == 4 and p.is_cuda) for p in self.params]
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            view = self.view_of(self.data, i)
+            view.copy_(p.data.float())
+            p.data = view
+            p.grad = self.view_of(self.grad, i)
+
+    def view_of(self, flat: torch.Tensor, i: int) -> torch.Tensor:
+        """Logical-shape view of parameter ``i`` inside a flat buffer laid out like this arena."""
+        p, o = self.params[i], self.offsets[i]
+        chunk = flat[o:o + p.numel()]
+        if self.channels_last[i]:
+            co, ci, kh, kw = p.shape
+            return chunk.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+        return chunk.view(p.shape)
 
     def zero_grad(self) -> None:
         self.grad.zero_()
-        for p, o in zip(self.params, self.offsets):        # re-attach if something set grads to None
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):   # re-attach if something set grads to None
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
-                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                p.grad = self.view_of(self.grad, i)
 
     def slice_of(self, first: int, last: int):
         """Arena range covering params ``first..last`` inclusive."""

@@ -27,7 +27,21 @@ ref = dec(feats, disp)
 refs = [ref[("disp", k)].permute(0, 1, 3, 4, 2) for k in range(4)]
 for k in range(4): print('fwd', k, rel(outs[k], refs[k]))
 sum((o * g).sum() for o, g in zip(refs, gouts)).backward()
+ref_grads = {k: p.grad.clone() for k, p in dec.named_parameters() if p.grad is not None}
 for kname, p in dec.named_parameters():
     if kname in got: print('%-44s %.4f  |ref|=%.3e' % (kname, rel(got[kname], p.grad), p.grad.norm().item()))
 encs = [(k, rel(got['enc.' + k], p.grad)) for k, p in enc.named_parameters() if 'enc.' + k in got]
 print('encoder params: median rel', sorted(v for _, v in encs)[len(encs)//2], 'max', max(encs, key=lambda t: t[1]))
+# the same comparison for the library bf16 path (autocast) vs fp32: how much of the deviation is just bf16?
+for p in list(enc.parameters()) + list(dec.parameters()): p.grad = None
+with torch.autocast("cuda", dtype=torch.bfloat16):
+    feats_b = enc(img.contiguous(memory_format=torch.channels_last))
+    out_b = dec(feats_b, disp)
+outs_b = [out_b[("disp", k)].float().permute(0, 1, 3, 4, 2) for k in range(4)]
+for k in range(4): print('autocast fwd', k, rel(outs_b[k], refs[k]))
+ref_g = {k: p.grad for k, p in dec.named_parameters()}
+sum((o * g).sum() for o, g in zip(outs_b, gouts)).backward()
+print('autocast-bf16 vs fp32 (weights only):')
+for kname, p in dec.named_parameters():
+    if kname.endswith('conv.weight') or kname.endswith('0.weight'):
+        print('   %-40s %.4f' % (kname, rel(p.grad, ref_grads[kname])))
