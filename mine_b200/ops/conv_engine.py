@@ -101,6 +101,16 @@ def unpack_up_grad(dwp: torch.Tensor) -> torch.Tensor:
     return torch.einsum("pak,qbl,pqaboi->oikl", m, m, dwp.reshape(2, 2, 2, 2, co, ci))
 
 
+def pack(w: torch.Tensor, mode: int) -> torch.Tensor:
+    """bf16 GEMM operand pack of a [Co,Ci,3,3] fp32 weight (any strides) in ONE kernel launch.
+    mode 0/1: fprop same / upsample, 2/3: dgrad same / upsample (see csrc/conv_tcgen05.cu)."""
+    w = w.detach()
+    if w.dtype != torch.float32:
+        w = w.float()
+    _count()
+    return ext().pack_weights(w, mode)
+
+
 SAME_TAPS_Y = [ky for ky in range(3) for kx in range(3)]
 SAME_TAPS_X = [kx for ky in range(3) for kx in range(3)]
 UP_TAPS_Y = [py + a for py in range(2) for px in range(2) for a in range(2) for b in range(2)]
@@ -119,18 +129,18 @@ def conv_same_raw(xpad, w, out=None, chan_bias=None, plane_bias=None, shared_map
     n, hp, wp_, ci = xpad.shape
     h, w_ = hp - 2, wp_ - 2
     co = w.shape[0]
-    pack = _pad_co(pack_same(w.detach()))
+    pack_ = pack(w, 0)
     th, tw = pick_tile(h, w_)
     if head:
         out = torch.empty((n, h, w_, 4), dtype=torch.float32, device=xpad.device)
         sign = torch.empty((n, h, w_), dtype=torch.int8, device=xpad.device)
-        ext().conv_taps(xpad, pack, out, h, w_, 1, 9, SAME_TAPS_Y, SAME_TAPS_X, 1, co, 1, 1, [0], [0], False,
+        ext().conv_taps(xpad, pack_, out, h, w_, 1, 9, SAME_TAPS_Y, SAME_TAPS_X, 1, co, 1, 1, [0], [0], False,
                         chan_bias, None, None, 1, None, 1, head_alpha, sign, th, tw)
         _count()
         return out, sign
     if out is None:
         out = torch.empty((n, h, w_, co), dtype=torch.bfloat16, device=xpad.device)
-    ext().conv_taps(xpad, pack, out, h, w_, 1, 9, SAME_TAPS_Y, SAME_TAPS_X, 1, co, 1, 1, [0], [0], False,
+    ext().conv_taps(xpad, pack_, out, h, w_, 1, 9, SAME_TAPS_Y, SAME_TAPS_X, 1, co, 1, 1, [0], [0], False,
                     chan_bias, plane_bias, shared_map, planes, stats, 0, False, None, th, tw)
     _count()
     return out
@@ -142,10 +152,10 @@ def conv_up_raw(xpad_lo, w, chan_bias=None, plane_bias=None, shared_map=None, pl
     n, hp, wp_, ci = xpad_lo.shape
     h, w_ = hp - 2, wp_ - 2
     co = w.shape[0]
-    pack = _pad_co(pack_up(w.detach().float()).reshape(16, co, ci))
+    pack_ = pack(w, 1)
     out = torch.empty((n, 2 * h, 2 * w_, co), dtype=torch.bfloat16, device=xpad_lo.device)
     th, tw = pick_tile(h, w_)
-    ext().conv_taps(xpad_lo, pack, out, h, w_, 4, 4, UP_TAPS_Y, UP_TAPS_X, 1, co, 2, 2, UP_OY, UP_OX, False,
+    ext().conv_taps(xpad_lo, pack_, out, h, w_, 4, 4, UP_TAPS_Y, UP_TAPS_X, 1, co, 2, 2, UP_OY, UP_OX, False,
                     chan_bias, plane_bias, shared_map, planes, stats, 0, False, None, th, tw)
     _count()
     return out
@@ -155,10 +165,10 @@ def dgrad_same_raw(dy, w):
     """Gradient w.r.t. the PADDED input of :func:`conv_same_raw`: ``dy [N,H,W,Co]`` -> ``[N,H+2,W+2,Ci]``."""
     n, h, w_, co = dy.shape
     ci = w.shape[1]
-    pack = _pad_co(w.detach().permute(2, 3, 1, 0).reshape(9, ci, co))            # [tap][Ci][Co]
+    pack_ = pack(w, 2)                                                            # [tap][Ci][Co]
     out = torch.empty((n, h + 2, w_ + 2, ci), dtype=torch.bfloat16, device=dy.device)
     th, tw = pick_tile(h + 2, w_ + 2)
-    ext().conv_taps(dy, pack, out, h + 2, w_ + 2, 1, 9, [-k for k in SAME_TAPS_Y], [-k for k in SAME_TAPS_X], 1, ci,
+    ext().conv_taps(dy, pack_, out, h + 2, w_ + 2, 1, 9, [-k for k in SAME_TAPS_Y], [-k for k in SAME_TAPS_X], 1, ci,
                     1, 1, [0], [0], False, None, None, None, 1, None, 0, False, None, th, tw)
     _count()
     return out
@@ -170,14 +180,13 @@ def dgrad_up_raw(dy, w):
     n, h2, w2, co = dy.shape
     h, w_ = h2 // 2, w2 // 2
     ci = w.shape[1]
-    wp = pack_up(w.detach().float())                                              # [4,4,Co,Ci]
-    pack = _pad_co(wp.permute(0, 1, 3, 2).reshape(16, ci, co))                    # [g*4+t][Ci][Co]
+    pack_ = pack(w, 3)                                                            # [g*4+t][Ci][Co]
     # forward: out[2y+py] += xpad[y + (py+a)]  =>  dxpad[q] += dy[2(q - py - a) + py] = dy[2q - py - 2a]
     ty = [-py - 2 * a for py in range(2) for px in range(2) for a in range(2) for b in range(2)]
     tx = [-px - 2 * b for py in range(2) for px in range(2) for a in range(2) for b in range(2)]
     out = torch.empty((n, h + 2, w_ + 2, ci), dtype=torch.bfloat16, device=dy.device)
     th, tw = pick_tile(h + 2, w_ + 2)
-    ext().conv_taps(dy, pack, out, h + 2, w_ + 2, 1, 16, ty, tx, 2, ci, 1, 1, [0], [0], False, None, None, None, 1,
+    ext().conv_taps(dy, pack_, out, h + 2, w_ + 2, 1, 16, ty, tx, 2, ci, 1, 1, [0], [0], False, None, None, None, 1,
                     None, 0, False, None, th, tw)
     _count()
     return out

@@ -78,6 +78,19 @@ void conv_taps(const at::Tensor& x, const at::Tensor& wpack, at::Tensor out, int
   TORCH_CHECK(err == nullptr, "conv_taps: ", err ? err : "");
 }
 
+at::Tensor pack_weights(const at::Tensor& w, int64_t mode) {
+  TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.dim() == 4 && w.size(2) == 3 && w.size(3) == 3,
+              "pack_weights expects a CUDA fp32 [Co,Ci,3,3] tensor (any strides)");
+  c10::cuda::CUDAGuard guard(w.device());
+  const int Co = w.size(0), Ci = w.size(1);
+  const int rows = mode >= 2 ? Ci : Co, cols = mode >= 2 ? Co : Ci;
+  const int rows_pad = (rows + 15) / 16 * 16;
+  at::Tensor out = at::empty({(mode & 1) ? 16 : 9, rows_pad, cols}, w.options().dtype(at::kBFloat16));
+  mine::launch_pack_weights(w.data_ptr<float>(), w.stride(0), w.stride(1), w.stride(2), w.stride(3), Co, Ci, (int)mode,
+                            rows_pad, out.data_ptr(), cur_stream());
+  return out;
+}
+
 void wgrad_taps(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_t Hg, int64_t Wg, int64_t G, int64_t T,
                 std::vector<int64_t> tap_y, std::vector<int64_t> tap_x, int64_t dy_stride, std::vector<int64_t> dy_oy,
                 std::vector<int64_t> dy_ox, int64_t TH, int64_t TW) {
@@ -163,6 +176,7 @@ std::vector<at::Tensor> head_bwd(const at::Tensor& g_mpi, const at::Tensor& mpi,
 void register_conv(pybind11::module_& m) {
   m.def("conv_taps", &conv_taps);
   m.def("wgrad_taps", &wgrad_taps);
+  m.def("pack_weights", &pack_weights);
   m.def("bn_act_pad_fwd", &bn_act_pad_fwd);
   m.def("bn_act_bwd_reduce", &bn_act_bwd_reduce);
   m.def("bn_bwd_apply", &bn_bwd_apply);

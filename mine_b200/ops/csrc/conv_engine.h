@@ -26,7 +26,8 @@ struct ConvParams {
   int act, head_alpha;                   // act = 1: MPI head (packed fp32 [.,4] output)
   void* raw_out;                         // head: sign of the sigma pre-activation, int8 [N, Ho, Wo] or null
   // filled by the launcher
-  int stages, tmem_cols;
+  int stages, tmem_cols, ipb;
+  int dbg;                               // timing experiments only (MINE_CONV_DBG); 0 in production
 };
 
 struct ConvLaunch {
@@ -53,6 +54,8 @@ struct WgradLaunch {
 };
 
 const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream);
+void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co, int Ci, int mode,
+                         int rows_pad, void* out, cudaStream_t stream);
 const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream);
 
 }  // namespace mine

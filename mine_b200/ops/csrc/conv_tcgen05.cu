@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -164,14 +165,20 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __shared__ __align__(8) uint64_t accum_empty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_stats[2][256];
+  __shared__ int s_tap[4][16][2];                      // (dy, dx) of every (group, tap): smem, not param-space indexing
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 64) {
+    s_tap[threadIdx.x >> 4][threadIdx.x & 15][0] = p.tap_y[threadIdx.x >> 4][threadIdx.x & 15];
+    s_tap[threadIdx.x >> 4][threadIdx.x & 15][1] = p.tap_x[threadIdx.x >> 4][threadIdx.x & 15];
+  }
   const int tiles = p.tiles_x * p.tiles_y;
   const int total_work = tiles * p.N * p.G;
 
   const int row_bytes = p.KB * 2;                     // == swizzle span
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
-  const uint32_t stage_bytes = ((a_bytes + b_bytes + 1023u) / 1024u) * 1024u;
+  const uint32_t sub_bytes = a_bytes + ((b_bytes + 1023u) / 1024u) * 1024u;   // one (tap, k-block) operand pair
+  const uint32_t stage_bytes = sub_bytes * p.ipb;      // ipb iterations share one barrier round trip
   uint8_t* smem_aligned = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
 
   if (threadIdx.x == 0) {
@@ -191,21 +198,36 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int iters = p.T * p.kblocks;
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;                                       // ring position, continues across tiles
+      // Scalar bookkeeping is kept division-free inside the loops (one thread issues everything; integer
+      // divides and parameter-array indexing were the dominant cost for the 16/32-channel layers).
+      int s = 0;                                        // ring slot and its parity, carried across tiles
+      uint32_t par = 0;
+      bool ring_full = false;                           // becomes true once every slot has been used once
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int tile = w % tiles, n_img = (w / tiles) % p.N, g = w / (tiles * p.N);
+        const int tile = w % tiles, wi = w / tiles;
+        const int n_img = wi % p.N, g = wi / p.N;
         const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-        const int oy0 = tile_y * p.TH, ox0 = tile_x * p.TW;
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int s = it % p.stages, round = it / p.stages;
-          if (it >= p.stages) mbar_wait(&empty_bar[s], (round - 1) & 1);
-          const int t = i / p.kblocks, kb = i - t * p.kblocks;
-          uint8_t* a_dst = smem_aligned + (size_t)s * stage_bytes;
-          uint8_t* b_dst = a_dst + a_bytes;
-          mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
-          const int iy = oy0 * p.in_stride + p.tap_y[g][t], ix = ox0 * p.in_stride + p.tap_x[g][t];
-          tma_load_4d(&map_x, &full_bar[s], a_dst, kb * p.KB, ix, iy, n_img);
-          tma_load_3d(&map_w, &full_bar[s], b_dst, kb * p.KB, 0, g * p.T + t);
+        const int oy0 = tile_y * p.TH * p.in_stride, ox0 = tile_x * p.TW * p.in_stride;
+        const int wrow0 = g * p.T;
+        int u = 0, n_in = 0, remaining = iters;
+        uint8_t* slot = nullptr;
+        for (int t = 0; t < p.T; ++t) {
+          const int iy = oy0 + s_tap[g][t][0], ix = ox0 + s_tap[g][t][1];
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            if (u == 0) {                               // open the next pipeline stage
+              if (ring_full) mbar_wait(&empty_bar[s], par ^ 1u);
+              n_in = remaining < p.ipb ? remaining : p.ipb;
+              mbar_expect_tx(&full_bar[s], (uint32_t)n_in * (a_bytes + b_bytes));
+              slot = smem_aligned + (size_t)s * stage_bytes;
+            }
+            tma_load_4d(&map_x, &full_bar[s], slot, kb * p.KB, ix, iy, n_img);
+            tma_load_3d(&map_w, &full_bar[s], slot + a_bytes, kb * p.KB, 0, wrow0 + t);
+            slot += sub_bytes;
+            if (++u == n_in) {
+              u = 0; remaining -= n_in;
+              if (++s == p.stages) { s = 0; par ^= 1u; ring_full = true; }
+            }
+          }
         }
       }
     }
@@ -214,24 +236,31 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
       const uint32_t lt = layout_type_for(row_bytes);
       const uint32_t sbo = 8u * row_bytes;
-      int it = 0, j = 0;
+      const uint64_t desc0 = make_smem_desc(0, 16, sbo, lt);
+      const int ksteps = p.KB / 16;
+      int s = 0, j = 0;
+      uint32_t par = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
         const int as = j & 1;
         if (j >= 2) mbar_wait(&accum_empty[as], ((j >> 1) - 1) & 1);     // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int s = it % p.stages, round = it / p.stages;
-          mbar_wait(&full_bar[s], round & 1);
+        uint32_t first = 0;                              // 0 for the very first MMA of the tile (overwrite)
+        for (int remaining = iters; remaining > 0;) {
+          const int n_in = remaining < p.ipb ? remaining : p.ipb;
+          mbar_wait(&full_bar[s], par);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
-          const uint32_t b_addr = a_addr + a_bytes;
-          for (int k = 0; k < p.KB / 16; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, lt);
-            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, lt);
-            umma_bf16(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
+          for (int u = 0; u < n_in; ++u, a_addr += sub_bytes) {
+            const uint64_t da = desc0 + (uint64_t)(a_addr >> 4), db = desc0 + (uint64_t)((a_addr + a_bytes) >> 4);
+            for (int k = 0; k < ksteps; ++k) {
+              if (!(p.dbg & 4)) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
+              first = 1u;
+            }
           }
           umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
+          remaining -= n_in;
+          if (++s == p.stages) { s = 0; par ^= 1u; }
         }
         umma_commit(&accum_full[as]);           // accumulator of this tile complete
       }
@@ -241,6 +270,12 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int q = warp & 3;
     const int r = q * 32 + lane;                       // row of the 128-pixel tile
     const int ty = r / p.TW, tx = r - ty * p.TW;
+    // BN <= 32: BatchNorm partial sums stay in registers across ALL tiles of this CTA (one cross-lane
+    // reduction at the end) instead of 2 x 16 x 5 shuffles per tile
+    const bool reg_stats = p.stats && p.BN <= 32;
+    float ra1[16], ra2[16], rb1[16], rb2[16];
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) ra1[jj] = ra2[jj] = rb1[jj] = rb2[jj] = 0.f;
     int j = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
       const int tile = w % tiles, n_img = (w / tiles) % p.N, g = w / (tiles * p.N);
@@ -258,6 +293,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (p.shared_map && valid)
         smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        if (p.dbg & 8) break;
         uint32_t v[16];
         tmem_ld16(t_acc + (uint32_t)c0, v);
         if (c0 >= p.Co) continue;
@@ -279,7 +315,15 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             f[jj] += m.x; f[jj + 1] += m.y; f[jj + 2] += m.z; f[jj + 3] += m.w;
           }
         }
-        if (p.stats) {
+        if (reg_stats) {
+          if (c0 == 0) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) { const float x = valid ? f[jj] : 0.f; ra1[jj] += x; ra2[jj] += x * x; }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) { const float x = valid ? f[jj] : 0.f; rb1[jj] += x; rb2[jj] += x * x; }
+          }
+        } else if (p.stats) {
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             const float x = valid ? f[jj] : 0.f;
@@ -329,6 +373,17 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&accum_empty[as]);
+    }
+    if (reg_stats) {
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const float a1 = warp_sum32(ra1[jj]), a2 = warp_sum32(ra2[jj]);
+        const float b1 = warp_sum32(rb1[jj]), b2 = warp_sum32(rb2[jj]);
+        if (lane == 0) {
+          atomicAdd(&s_stats[0][jj], a1); atomicAdd(&s_stats[1][jj], a2);
+          if (p.BN > 16) { atomicAdd(&s_stats[0][16 + jj], b1); atomicAdd(&s_stats[1][16 + jj], b2); }
+        }
+      }
     }
     if (p.stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");         // epilogue warps only
@@ -415,23 +470,30 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.NB, 1, 1);
       const uint32_t lta = layout_type_for(a_row), ltb = layout_type_for(b_row);
       // A: when Co < 128 the missing MN blocks alias block 0 (LBO = 0): rows >= Co are copies and never stored
       const uint32_t a_lbo = (p.a_slabs > 1) ? a_slab : 0u;
-      const uint32_t b_lbo = (p.b_slabs > 1) ? b_slab : 0u;
+      // B: the tap tiles of a stage are consecutive [KP][b_cb] slabs, b_slab apart == the MN-block stride of the
+      // MN-major descriptor, so ONE instruction spans several taps: N = nblk * b_cb (<= 256).  A single thread
+      // issues every MMA, so few wide instructions instead of many 16-column ones is what keeps the tensor
+      // pipe busy for the 16/32-channel layers.
+      const int total_blocks = ntaps * p.b_slabs;
+      const int blk_per_mma = 256 / p.b_cb;
+      const uint64_t da0 = make_smem_desc(0, a_lbo, 8u * a_row, lta);
+      const uint64_t db0 = make_smem_desc(0, b_slab, 8u * b_row, ltb);
       for (int i = 0; i < my_tiles; ++i) {
         const int s = i % p.stages, round = i / p.stages;
         mbar_wait(&full_bar[s], round & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
-        for (int t = 0; t < ntaps; ++t) {
-          const uint32_t b_addr = a_addr + a_bytes + t * b_tap_bytes;
-          for (int k = 0; k < p.KP / 16; ++k) {
-            // 16 K rows (pixels) per instruction = two 8-row groups, SBO apart
-            const uint64_t da = make_smem_desc(a_addr + k * 16 * a_row, a_lbo, 8u * a_row, lta);
-            const uint64_t db = make_smem_desc(b_addr + k * 16 * b_row, b_lbo, 8u * b_row, ltb);
-            umma_bf16(tmem_base + t * p.NB, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int k = 0; k < p.KP / 16; ++k) {
+          // 16 K rows (pixels) per instruction = two 8-row groups, SBO apart
+          const uint64_t da = da0 + (uint64_t)((a_addr + k * 16 * a_row) >> 4);
+          for (int b0 = 0; b0 < total_blocks; b0 += blk_per_mma) {
+            const int nblk = min(blk_per_mma, total_blocks - b0);
+            const uint64_t db = db0 + (uint64_t)((b_addr + b0 * b_slab + k * 16 * b_row) >> 4);
+            umma_bf16(tmem_base + b0 * p.b_cb, da, db, make_idesc(128, nblk * p.b_cb, 1, 1), (i > 0 || k > 0) ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[s]);
@@ -544,6 +606,49 @@ static const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop
 
 static int next_pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 
+// ---- weight packing: fp32 [Co,Ci,3,3] (any strides) -> bf16 GEMM operand packs, one launch --------------
+// mode 0: fprop 3x3        out[ky*3+kx][co][ci]
+// mode 1: fprop upsample   out[(py*2+px)*4 + a*2+b][co][ci] = sum over the 3x3 taps that collapse onto (a,b)
+// mode 2: dgrad 3x3        out[ky*3+kx][ci][co]
+// mode 3: dgrad upsample   out[(py*2+px)*4 + a*2+b][ci][co]
+// rows (the GEMM N dimension) are zero-padded to `rows_pad` (multiple of 16).
+__device__ __forceinline__ bool phase_has(int p, int a, int k) {      // does 3-tap index k fold onto 2-tap index a?
+  return p == 0 ? (a == 0 ? k == 0 : k >= 1) : (a == 0 ? k <= 1 : k == 2);
+}
+__global__ void pack_weights_kernel(const float* __restrict__ w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co,
+                                    int Ci, int mode, int rows_pad, __nv_bfloat16* __restrict__ out, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const bool dgrad = mode >= 2, up = (mode & 1) != 0;
+  const int cols = dgrad ? Co : Ci;
+  const int col = idx % cols;
+  const int row = (idx / cols) % rows_pad;
+  const int gt = idx / (cols * rows_pad);
+  const int co = dgrad ? col : row, ci = dgrad ? row : col;
+  float v = 0.f;
+  if (co < Co && ci < Ci) {
+    const float* base = w + co * so + ci * si;
+    if (!up) {
+      v = base[(gt / 3) * sy + (gt % 3) * sx];
+    } else {
+      const int g = gt >> 2, t = gt & 3, py = g >> 1, px = g & 1, a = t >> 1, b = t & 1;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          if (phase_has(py, a, ky) && phase_has(px, b, kx)) v += base[ky * sy + kx * sx];
+    }
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co, int Ci, int mode,
+                         int rows_pad, void* out, cudaStream_t stream) {
+  const int gt = (mode & 1) ? 16 : 9;
+  const int cols = mode >= 2 ? Co : Ci;
+  const int total = gt * rows_pad * cols;
+  pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, so, si, sy, sx, Co, Ci, mode, rows_pad,
+                                                               (__nv_bfloat16*)out, total);
+}
+
 const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   ConvParams p = L.p;
   if (p.TH * p.TW != 128) return "tile must cover 128 pixels";
@@ -555,17 +660,29 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
   p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
   p.tmem_cols = next_pow2_cols(2 * p.BN);                  // double-buffered accumulator
-  const uint32_t stage_bytes = ((128u * p.KB * 2 + (uint32_t)p.BN * p.KB * 2 + 1023u) / 1024u) * 1024u;
-  int stages = (int)(64u * 1024u / stage_bytes);
+  const uint32_t sub_bytes = 128u * p.KB * 2 + (((uint32_t)p.BN * p.KB * 2 + 1023u) / 1024u) * 1024u;
+  int ipb = (int)(24u * 1024u / sub_bytes);                // (tap, k-block) iterations per barrier round trip
+  if (ipb > p.T * p.kblocks) ipb = p.T * p.kblocks;
+  if (ipb > 12) ipb = 12;
+  if (ipb < 1) ipb = 1;
+  static const int env_ipb = getenv("MINE_CONV_IPB") ? atoi(getenv("MINE_CONV_IPB")) : 0;
+  static const int env_stages = getenv("MINE_CONV_STAGES") ? atoi(getenv("MINE_CONV_STAGES")) : 0;
+  static const int env_dbg = getenv("MINE_CONV_DBG") ? atoi(getenv("MINE_CONV_DBG")) : 0;
+  if (env_ipb > 0) { ipb = env_ipb; if (ipb > p.T * p.kblocks) ipb = p.T * p.kblocks; }
+  p.ipb = ipb;
+  p.dbg = env_dbg;
+  const uint32_t stage_bytes = sub_bytes * ipb;
+  int stages = (int)(96u * 1024u / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 3) stages = 3;
+  if (stages < 2) stages = 2;
+  if (env_stages > 0) stages = env_stages;
   p.stages = stages;
   size_t smem = (size_t)stages * stage_bytes + 1024;
   // resident CTAs per SM: limited by TMEM columns (512) and shared memory; pad smem so exactly that many fit
   int ctas_per_sm = 512 / p.tmem_cols;
   const int by_smem = (int)((220u * 1024u) / (smem + 2048));
   if (ctas_per_sm > by_smem) ctas_per_sm = by_smem;
-  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  if (ctas_per_sm > 2) ctas_per_sm = 2;                      // ~126 registers x 192 threads: two CTAs per SM
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const size_t smem_floor = (220u * 1024u) / (ctas_per_sm + 1) + 1024;   // one more CTA must NOT fit
   if (smem < smem_floor) smem = smem_floor;

