@@ -193,7 +193,8 @@ def run_ours(args):
     device = ctx.device
     extra = {"data.img_w": shape["w"], "data.img_h": shape["h"], "mpi.num_bins_coarse": shape["planes"],
              "data.per_gpu_batch_size": shape["batch"], "model.imagenet_pretrained": False,
-             "training.eval_interval": 10 ** 9, "engine.cuda_graph": not args.no_graph}
+             "training.eval_interval": 10 ** 9, "engine.cuda_graph": not args.no_graph,
+             "engine.comm": os.environ.get("MINE_B200_COMM", "p2p")}
     config = cfglib.config_for_dataset(shape["dataset"], extra)
     config.update({"global_rank": ctx.rank, "local_rank": ctx.local_rank, "world_size": ctx.world_size, "device": device})
     torch.manual_seed(1234 + rank)

@@ -59,67 +59,114 @@ __device__ __forceinline__ void peer_barrier(const PeerTable& flags, int rank, i
   __syncthreads();
 }
 
+// Epochs live in DEVICE memory and are advanced by the kernels themselves, so a captured CUDA graph can be
+// replayed: every replay sees the next epoch without any host-side argument changing.
+//
 // ---- small one-shot SUM (BN statistics) -------------------------------------------------------------
-// data: [2 slots][cap] floats per rank (symmetric); slot = epoch & 1
-__global__ void __launch_bounds__(256) allreduce_small_oneshot_kernel(float* __restrict__ inout, int n, PeerTable data,
-                                                                      PeerTable flags, int rank, int world, int cap,
-                                                                      uint32_t epoch, int channel) {
+// data: [2 slots][cap] floats per rank (symmetric); slot = epoch & 1.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) allreduce_small_oneshot_kernel(float* __restrict__ inout, int n, PeerTable data,
+                                                                       PeerTable flags, int rank, int world, int cap,
+                                                                       uint32_t* __restrict__ epoch_ptr) {
+  const uint32_t epoch = *epoch_ptr + 1;
   float* my_slot = reinterpret_cast<float*>(data.ptr[rank]) + (size_t)(epoch & 1) * cap;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) my_slot[i] = inout[i];
-  peer_barrier(flags, rank, world, channel, epoch);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float acc = 0.f;
-    for (int p = 0; p < world; ++p) {
-      const float* src = reinterpret_cast<const float*>(data.ptr[p]) + (size_t)(epoch & 1) * cap;
-      float v;
-      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(src + i) : "memory");
-      acc += v;
-    }
-    inout[i] = acc;
+  const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(inout) & 15) == 0);
+  if (vec) {
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x)
+      reinterpret_cast<float4*>(my_slot)[i] = reinterpret_cast<const float4*>(inout)[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) my_slot[i] = inout[i];
   }
+  peer_barrier(flags, rank, world, 0, epoch);
+  if (vec) {
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < world; ++p) {                 // rank order: identical bits everywhere
+        const float4 v = ld_peer_v4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(data.ptr[p]) + (size_t)(epoch & 1) * cap) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      reinterpret_cast<float4*>(inout)[i] = acc;
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float acc = 0.f;
+      for (int p = 0; p < world; ++p) {
+        const float* src = reinterpret_cast<const float*>(data.ptr[p]) + (size_t)(epoch & 1) * cap;
+        float v;
+        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(src + i) : "memory");
+        acc += v;
+      }
+      inout[i] = acc;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch_ptr = epoch;
 }
 
 // ---- two-shot mean, in place on the symmetric arena ---------------------------------------------------
 // Elements [lo, hi) of every rank's arena (float offsets, multiples of 4).  Rank r reduces its 1/world slice.
+// Four independent 16-byte peer loads per thread are in flight before the first add (NVLink latency ~2 us).
+constexpr int kUnroll = 4;
 __global__ void __launch_bounds__(512) allreduce_mean_twoshot_kernel(PeerTable arena, PeerTable flags, float* mc_arena,
                                                                      int64_t lo, int64_t hi, int rank, int world,
-                                                                     float scale, uint32_t epoch, int use_multimem) {
+                                                                     float scale, uint32_t* __restrict__ epochs,
+                                                                     int use_multimem) {
   const int channel = blockIdx.x + 1;                       // channel 0 belongs to the small one-shot kernel
+  const uint32_t epoch = epochs[blockIdx.x] + 1;
   peer_barrier(flags, rank, world, channel, epoch);         // every rank's gradients for [lo, hi) are final
   const int64_t n4 = (hi - lo) / 4;
   const int64_t per = (n4 + world - 1) / world;
   const int64_t s4 = rank * per, e4 = (s4 + per < n4) ? s4 + per : n4;
   const int64_t base4 = lo / 4;
-  for (int64_t i = s4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 acc;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = s4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < e4; i0 += stride * kUnroll) {
+    float4 acc[kUnroll];
     if (use_multimem) {
-      acc = multimem_ld_reduce_v4(reinterpret_cast<const float4*>(mc_arena) + base4 + i);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < e4) acc[u] = multimem_ld_reduce_v4(reinterpret_cast<const float4*>(mc_arena) + base4 + i);
+      }
     } else {
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int p = 0; p < world; ++p) {                   // fixed order: identical bits on every rank
-        const float4 v = ld_peer_v4(reinterpret_cast<const float4*>(arena.ptr[p]) + base4 + i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int64_t i = i0 + u * stride;
+          v[u] = (i < e4) ? ld_peer_v4(reinterpret_cast<const float4*>(arena.ptr[p]) + base4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
       }
     }
-    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
-    if (use_multimem) {
-      multimem_st_v4(reinterpret_cast<float4*>(mc_arena) + base4 + i, acc);
-    } else {
-      for (int p = 0; p < world; ++p) st_peer_v4(reinterpret_cast<float4*>(arena.ptr[p]) + base4 + i, acc);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= e4) continue;
+      float4 r = acc[u];
+      r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+      if (use_multimem) {
+        multimem_st_v4(reinterpret_cast<float4*>(mc_arena) + base4 + i, r);
+      } else {
+        for (int p = 0; p < world; ++p) st_peer_v4(reinterpret_cast<float4*>(arena.ptr[p]) + base4 + i, r);
+      }
     }
   }
   peer_barrier(flags, rank, world, channel, epoch + 1);     // all slices have landed everywhere
+  if (threadIdx.x == 0) epochs[blockIdx.x] = epoch + 1;
 }
 
 void launch_allreduce_small(float* inout, int n, const PeerTable& data, const PeerTable& flags, int rank, int world,
-                            int cap, uint32_t epoch, cudaStream_t stream) {
-  allreduce_small_oneshot_kernel<<<1, 256, 0, stream>>>(inout, n, data, flags, rank, world, cap, epoch, 0);
+                            int cap, uint32_t* epoch_ptr, cudaStream_t stream) {
+  int threads = n >= 4096 ? 1024 : (n >= 1024 ? 512 : 256);
+  allreduce_small_oneshot_kernel<<<1, threads, 0, stream>>>(inout, n, data, flags, rank, world, cap, epoch_ptr);
 }
 
 void launch_allreduce_mean(const PeerTable& arena, const PeerTable& flags, float* mc_arena, int64_t lo, int64_t hi,
-                           int rank, int world, uint32_t epoch, int blocks, cudaStream_t stream) {
+                           int rank, int world, uint32_t* epochs, int blocks, cudaStream_t stream) {
   allreduce_mean_twoshot_kernel<<<blocks, 512, 0, stream>>>(arena, flags, mc_arena, lo, hi, rank, world, 1.0f / world,
-                                                            epoch, mc_arena != nullptr ? 1 : 0);
+                                                            epochs, mc_arena != nullptr ? 1 : 0);
 }
 
 }  // namespace mine

@@ -16,20 +16,23 @@ mine::PeerTable table_from(const std::vector<int64_t>& ptrs) {
 }
 
 void allreduce_small(at::Tensor inout, std::vector<int64_t> data_ptrs, std::vector<int64_t> flag_ptrs, int64_t rank,
-                     int64_t cap, int64_t epoch) {
+                     int64_t cap, at::Tensor epoch) {
+  TORCH_CHECK(epoch.is_cuda() && epoch.scalar_type() == at::kInt && epoch.numel() >= 1, "epoch must be a CUDA int32 tensor");
   TORCH_CHECK(inout.is_cuda() && inout.scalar_type() == at::kFloat && inout.is_contiguous(), "inout must be contiguous fp32");
   TORCH_CHECK(inout.numel() <= cap, "vector larger than the one-shot slot");
   c10::cuda::CUDAGuard guard(inout.device());
   mine::launch_allreduce_small(inout.data_ptr<float>(), (int)inout.numel(), table_from(data_ptrs), table_from(flag_ptrs),
-                               (int)rank, (int)data_ptrs.size(), (int)cap, (uint32_t)epoch,
+                               (int)rank, (int)data_ptrs.size(), (int)cap, reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
                                at::cuda::getCurrentCUDAStream().stream());
 }
 
 void allreduce_mean(std::vector<int64_t> arena_ptrs, std::vector<int64_t> flag_ptrs, int64_t mc_ptr, int64_t lo, int64_t hi,
-                    int64_t rank, int64_t epoch, int64_t blocks) {
+                    int64_t rank, at::Tensor epochs, int64_t blocks) {
   TORCH_CHECK(lo % 4 == 0 && hi % 4 == 0, "bucket bounds must be multiples of 4 floats");
+  TORCH_CHECK(epochs.is_cuda() && epochs.scalar_type() == at::kInt && epochs.numel() >= blocks, "epochs: CUDA int32 [blocks]");
+  c10::cuda::CUDAGuard guard(epochs.device());
   mine::launch_allreduce_mean(table_from(arena_ptrs), table_from(flag_ptrs), reinterpret_cast<float*>(mc_ptr), lo, hi,
-                              (int)rank, (int)arena_ptrs.size(), (uint32_t)epoch, (int)blocks,
+                              (int)rank, (int)arena_ptrs.size(), reinterpret_cast<uint32_t*>(epochs.data_ptr<int>()), (int)blocks,
                               at::cuda::getCurrentCUDAStream().stream());
 }
 

@@ -60,8 +60,9 @@ void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, v
 namespace mine {
 // ---- comm.cu (NVLink peer memory) -----------------------------------------------------------------
 struct PeerTable { void* ptr[16]; };
+// epoch counters are device-resident (advanced by the kernels): CUDA-graph replay safe
 void launch_allreduce_small(float* inout, int n, const PeerTable& data, const PeerTable& flags, int rank, int world,
-                            int cap, uint32_t epoch, cudaStream_t stream);
+                            int cap, uint32_t* epoch_ptr, cudaStream_t stream);
 void launch_allreduce_mean(const PeerTable& arena, const PeerTable& flags, float* mc_arena, int64_t lo, int64_t hi,
-                           int rank, int world, uint32_t epoch, int blocks, cudaStream_t stream);
+                           int rank, int world, uint32_t* epochs, int blocks, cudaStream_t stream);
 }  // namespace mine

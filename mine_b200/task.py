@@ -325,7 +325,8 @@ class SynthesisTask:
     def train_step(self, items) -> Dict[str, torch.Tensor]:
         """One optimisation step on a batch in the reference format (no host sync).  With
         ``engine.cuda_graph`` the whole step (forward, losses, backward, Adam) is ONE graph replay."""
-        if self._graph is None and self._want_graph and self.comm.world_size == 1 and self.device.type == "cuda":
+        graph_ok = self.comm.world_size == 1 or getattr(self.comm, "graph_safe", False)
+        if self._graph is None and self._want_graph and graph_ok and self.device.type == "cuda":
             self.enable_cuda_graph(items)
         if self._graph is not None:
             self._load_static(items)
