@@ -71,7 +71,7 @@ def rotmat2qvec(r) -> np.ndarray:
         [r[0, 0] - r[1, 1] - r[2, 2], 0, 0, 0],
         [r[1, 0] + r[0, 1], r[1, 1] - r[0, 0] - r[2, 2], 0, 0],
         [r[2, 0] + r[0, 2], r[2, 1] + r[1, 2], r[2, 2] - r[0, 0] - r[1, 1], 0],
-        [r[1, 2] - r[2, 1], r[2, 0] - r[0, 2], r[0, 1] - r[1, 0], r[0, 0] + r[1, 1] + r[2, 2]]]) / 3.0
+        [r[2, 1] - r[1, 2], r[0, 2] - r[2, 0], r[1, 0] - r[0, 1], r[0, 0] + r[1, 1] + r[2, 2]]]) / 3.0
     vals, vecs = np.linalg.eigh(k)
     q = vecs[[3, 0, 1, 2], np.argmax(vals)]
     return -q if q[0] < 0 else q
@@ -318,3 +318,25 @@ class COLMAPDatabase(sqlite3.Connection):
         row = self.execute("SELECT rows, cols, data FROM matches WHERE pair_id=?",
                            (image_ids_to_pair_id(image_id1, image_id2),)).fetchone()
         return np.frombuffer(row[2], np.uint32).reshape(row[0], row[1])
+
+
+def main(argv=None):
+    """Round-trip CLI: ``python -m mine_b200.data.colmap --input_model DIR --input_format .bin
+    --output_model DIR --output_format .txt`` (reference ``colmap_utils.py:481-503``)."""
+    import argparse
+    ap = argparse.ArgumentParser(description="Read and write COLMAP binary and text models")
+    ap.add_argument("--input_model", required=True)
+    ap.add_argument("--input_format", choices=[".bin", ".txt"], default=".bin")
+    ap.add_argument("--output_model")
+    ap.add_argument("--output_format", choices=[".bin", ".txt"], default=".txt")
+    a = ap.parse_args(argv)
+    cams, imgs, pts = read_model(a.input_model, a.input_format)
+    print("num_cameras:", len(cams))
+    print("num_images:", len(imgs))
+    print("num_points3D:", len(pts))
+    if a.output_model:
+        write_model(cams, imgs, pts, a.output_model, a.output_format)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,3 +27,7 @@ class ConvBlock(nn.Module):
 
 def upsample(x):
     return F.interpolate(x, scale_factor=2, mode="nearest")
+
+from mine_b200.models.geometry_layers import (BackprojectDepth, Project3D, SSIM3x3 as SSIM, compute_depth_errors,  # noqa: E402,F401
+                                              disp_to_depth, get_smooth_loss, get_translation_matrix,
+                                              rot_from_axisangle, transformation_from_parameters)

@@ -1,0 +1,230 @@
+"""Public API surface, config system, data pipeline, checkpoint/resume (CPU)."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mine_b200 import config as C
+from mine_b200.data import colmap
+from mine_b200.data.synthetic import config_batch, synthetic_batch
+
+SMALL = {"data.img_w": 128, "data.img_h": 96, "mpi.num_bins_coarse": 4, "data.visible_point_count": 32,
+         "model.imagenet_pretrained": False}
+
+
+def _task(extra=None, is_val=False):
+    from synthesis_task import SynthesisTask            # upstream-named entry point
+    cfg = C.config_for_dataset("llff", dict(SMALL, **(extra or {})))
+    cfg["device"] = torch.device("cpu")
+    torch.manual_seed(0)
+    return SynthesisTask(cfg, None, is_val=is_val), cfg
+
+
+# ---- config ---------------------------------------------------------------------------------
+def test_config_merge_and_unknown_keys(tmp_path):
+    cfg = C.config_for_dataset("kitti_raw", {"mpi.num_bins_coarse": 64})
+    assert cfg["data.img_w"] == 384 and cfg["data.img_h"] == 128 and cfg["mpi.num_bins_coarse"] == 64
+    assert cfg["mpi.disparity_start"] == 0.2 and cfg["lr.decay_steps"] == [40, 80, 100]
+    with pytest.raises(C.ConfigError):
+        C.config_for_dataset("llff", {"mpi.no_such_key": 1})
+    dtu = C.config_for_dataset("dtu")                       # crashes upstream (model.decoder_type not in defaults)
+    assert dtu["training.gpus"] == [1, 2, 3, 4, 5, 6, 7] and dtu["mpi.is_bg_depth_inf"] is True
+    assert C.get({"mpi.is_bg_depth_inf": True}, "mpi.render_tgt_rgb_depth") is True     # legacy alias
+    p = tmp_path / "params.yaml"
+    C.dump_config(cfg, str(p))
+    back = C.load_dumped_config(str(p), '{"data.per_gpu_batch_size": 1}')
+    assert back["lr.decay_steps"] == [40, 80, 100] and back["data.per_gpu_batch_size"] == 1
+    with pytest.raises(C.ConfigError):
+        C.validate_resolution({"data.img_h": 100, "data.img_w": 128})
+
+
+def test_upstream_yaml_files_load():
+    ref = "/root/reference/configs"
+    if not os.path.isdir(ref):
+        pytest.skip("reference not mounted")
+    for name in ("params_llff", "params_realestate", "params_kitti_raw", "params_flowers", "params_dtu"):
+        cfg = C.build_config(os.path.join(ref, name + ".yaml"), default_path=os.path.join(ref, "params_default.yaml"))
+        ours = C.build_config(os.path.join(C.DEFAULT_CONFIG_DIR, name + ".yaml"))
+        for k in C.SCHEMA:
+            if not k.startswith(("engine.", "training.seed", "training.checkpoint", "training.log_", "training.all_rank",
+                                 "training.max_steps", "data.training_set_path", "data.val_set_path")):
+                assert cfg[k] == ours[k], (name, k, cfg[k], ours[k])
+
+
+# ---- task API -------------------------------------------------------------------------------
+def test_task_public_surface_and_shapes():
+    task, cfg = _task()
+    for attr in ("backbone", "decoder", "global_step", "logger", "homography_sampler_list", "set_data",
+                 "network_forward", "mpi_predictor", "loss_fcn", "loss_fcn_per_scale", "render_novel_view", "train",
+                 "train_epoch", "run_eval", "log_training", "log_val", "compute_scale_factor", "init_data"):
+        assert hasattr(task, attr), attr
+    assert tuple(task.homography_sampler_list[1].meshgrid.shape) == (3, 48, 64)
+    items = config_batch(cfg)
+    task.set_data(items)
+    out = task.network_forward()
+    b, s = 2, 4
+    assert tuple(out["disparity_all_src"].shape) == (b, s)
+    assert torch.all(out["disparity_all_src"][:, :-1] > out["disparity_all_src"][:, 1:])      # near -> far
+    for k, m in enumerate(out["mpi_all_src_list"]):
+        assert tuple(m.shape) == (b, s, 4, 96 // 2 ** k, 128 // 2 ** k)
+        assert m[:, :, :3].min() >= 0 and m[:, :, :3].max() <= 1 and m[:, :, 3].min() >= 1e-4
+    m0 = out["mpi_all_src_list"][0]
+    res = task.render_novel_view(m0[:, :, :3], m0[:, :, 3:], out["disparity_all_src"], task.G_tgt_src, task.K_src_inv,
+                                 task.K_tgt, scale=0, scale_factor=torch.ones(b))
+    assert set(res) == {"tgt_imgs_syn", "tgt_disparity_syn", "tgt_mask_syn"}
+    assert tuple(res["tgt_imgs_syn"].shape) == (b, 3, 96, 128) and tuple(res["tgt_mask_syn"].shape) == (b, 1, 96, 128)
+    loss_dict, vis = task.loss_fcn(is_val=False)
+    for k in ("loss", "loss_rgb_src", "loss_ssim_src", "loss_disp_pt3dsrc", "loss_smooth_src", "loss_smooth_tgt",
+              "loss_smooth_src_v2", "loss_smooth_tgt_v2", "loss_rgb_tgt", "loss_ssim_tgt", "lpips_tgt", "psnr_tgt",
+              "loss_disp_pt3dtgt"):
+        assert k in loss_dict and torch.isfinite(loss_dict[k]).all(), k
+    assert set(vis) == {"src_disparity_syn", "tgt_disparity_syn", "tgt_imgs_syn", "tgt_mask_syn", "src_imgs_syn"}
+
+
+@pytest.mark.parametrize("extra", [{"mpi.num_bins_fine": 2}, {"mpi.use_alpha": True}, {"mpi.is_bg_depth_inf": True},
+                                   {"mpi.fix_disparity": True, "training.src_rgb_blending": False},
+                                   {"loss.smoothness_lambda_v1": 0.5, "loss.smoothness_lambda_v2": 0.01}])
+def test_task_variants_train_one_step(extra):
+    task, cfg = _task(extra)
+    ld = task.train_step(config_batch(cfg))
+    assert torch.isfinite(ld["loss"])
+    assert task.arena.grad.abs().sum() > 0
+    if extra.get("mpi.num_bins_fine"):
+        task.set_data(config_batch(cfg))
+        assert task.network_forward()["disparity_all_src"].shape[1] == 6
+
+
+def test_identity_pose_reproduces_source_view():
+    task, cfg = _task({"mpi.fix_disparity": True})
+    items = config_batch(cfg)
+    task.set_data(items)
+    out = task.network_forward()
+    m0 = out["mpi_all_src_list"][0]
+    eye = torch.eye(4)[None].repeat(2, 1, 1)
+    res = task.render_novel_view(m0[:, :, :3], m0[:, :, 3:], out["disparity_all_src"], eye, task.K_src_inv, task.K_src)
+    from mine_b200.spec import render as R
+    src = R.render_src(m0[:, :, :3], m0[:, :, 3:], out["disparity_all_src"], task.K_src_inv, blend=False)
+    assert (res["tgt_imgs_syn"] - src["rgb"]).abs().max() < 1e-4
+    assert torch.all(res["tgt_mask_syn"] == 4)
+
+
+def test_checkpoint_resume_is_exact(tmp_path):
+    task, cfg = _task({"lr.decay_steps": "1,2"})
+    cfg["local_workspace"] = str(tmp_path)
+    items = config_batch(cfg)
+    task.train_step(items)
+    task.current_epoch = 2
+    task.lr_scheduler.step()
+    path = task.save_checkpoint("checkpoint_latest.pth", with_optimizer=True)
+    raw = torch.load(path, weights_only=False)
+    assert set(raw) >= {"backbone", "decoder", "optimizer", "meta"}
+    assert all(k.startswith("module.") for k in raw["backbone"])
+    task2, cfg2 = _task({"lr.decay_steps": "1,2", "training.pretrained_checkpoint_path": path})
+    assert task2.global_step == 1 and task2.current_epoch == 2
+    assert task2.optimizer.step_count == 1
+    assert task2.optimizer.param_groups[0]["lr"] == pytest.approx(task.optimizer.param_groups[0]["lr"])
+    assert torch.equal(task2.arena.data, task.arena.data)
+    assert torch.equal(task2.optimizer.exp_avg, task.optimizer.exp_avg)
+    rng = torch.get_rng_state()            # both tasks share this process' generator: replay the same stream
+    a = task.train_step(items)["loss"].item()
+    torch.set_rng_state(rng)
+    b = task2.train_step(items)["loss"].item()
+    assert a == pytest.approx(b, rel=1e-5)
+
+
+# ---- data -----------------------------------------------------------------------------------
+def _write_scene(root, n_views=4, n_pts=80, w=160, h=120):
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    os.makedirs(os.path.join(root, "scene0", "images"), exist_ok=True)
+    cams = {1: colmap.Camera(1, "SIMPLE_RADIAL", w, h, np.array([140.0, w / 2, h / 2, 0.01]))}
+    pts_xyz = np.stack([rng.uniform(-1, 1, n_pts), rng.uniform(-1, 1, n_pts), rng.uniform(3, 6, n_pts)], 1)
+    imgs, pts = {}, {}
+    for i in range(1, n_views + 1):
+        Image.fromarray((rng.random((h, w, 3)) * 255).astype(np.uint8)).save(os.path.join(root, "scene0", "images", f"v{i}.png"))
+        q = np.array([1.0, 0.01 * i, -0.02 * i, 0.005 * i]); q /= np.linalg.norm(q)
+        t = np.array([0.05 * i, -0.03 * i, 0.02 * i])
+        imgs[i] = colmap.Image(i, q, t, 1, f"v{i}.png", rng.uniform(0, 100, (n_pts, 2)), np.arange(1, n_pts + 1))
+    for j in range(n_pts):
+        pts[j + 1] = colmap.Point3D(j + 1, pts_xyz[j], np.array([1, 2, 3]), 0.5, np.arange(1, n_views + 1), np.full(n_views, j))
+    colmap.write_model(cams, imgs, pts, os.path.join(root, "scene0", "sparse", "0"), ".bin")
+    return cams, imgs, pts
+
+
+def test_colmap_roundtrip_and_database(tmp_path):
+    cams, imgs, pts = _write_scene(str(tmp_path))
+    c2, i2, p2 = colmap.read_model(str(tmp_path / "scene0" / "sparse" / "0"), ".bin")
+    assert c2[1].model == "SIMPLE_RADIAL" and np.allclose(c2[1].params, cams[1].params)
+    assert i2[3].name == "v3.png" and np.allclose(i2[3].qvec, imgs[3].qvec) and np.array_equal(i2[3].point3D_ids, imgs[3].point3D_ids)
+    assert np.allclose(p2[7].xyz, pts[7].xyz) and np.array_equal(p2[7].image_ids, pts[7].image_ids)
+    txt = tmp_path / "txt"
+    colmap.write_model(c2, i2, p2, str(txt), ".txt")
+    c3, i3, p3 = colmap.read_model(str(txt), ".txt")
+    assert np.allclose(i3[2].tvec, imgs[2].tvec) and np.allclose(i3[2].xys, imgs[2].xys) and np.allclose(p3[5].xyz, pts[5].xyz)
+    r = colmap.qvec2rotmat(imgs[2].qvec)
+    assert np.allclose(r @ r.T, np.eye(3), atol=1e-9) and np.allclose(colmap.rotmat2qvec(r), imgs[2].qvec, atol=1e-9)
+    colmap.main(["--input_model", str(tmp_path / "scene0" / "sparse" / "0"), "--output_model", str(tmp_path / "cli"), "--output_format", ".txt"])
+    assert os.path.exists(tmp_path / "cli" / "images.txt")
+    db = colmap.COLMAPDatabase.connect(str(tmp_path / "database.db"))
+    db.create_tables()
+    cid = db.add_camera(2, 160, 120, [140.0, 80, 60, 0.01])
+    a, b = db.add_image("a.png", cid), db.add_image("b.png", cid)
+    db.add_keypoints(a, np.random.rand(5, 2)), db.add_matches(a, b, np.array([[0, 1], [2, 3]]))
+    assert db.read_keypoints(a).shape == (5, 2) and np.array_equal(db.read_matches(a, b), [[0, 1], [2, 3]])
+    assert colmap.pair_id_to_image_ids(colmap.image_ids_to_pair_id(3, 9)) == (3, 9)
+
+
+def test_llff_dataset_batches_match_reference_format(tmp_path):
+    from torch.utils.data import DataLoader
+    from input_pipelines.llff.nerf_dataset import NeRFDataset          # upstream-named path
+    _write_scene(str(tmp_path))
+    ds = NeRFDataset({}, None, root=str(tmp_path), is_validation=False, img_size=(128, 96), supervision_count=1,
+                     visible_points_count=16, img_pre_downsample_ratio=None)
+    assert len(ds) == 4
+    src, tgt = next(iter(DataLoader(ds, batch_size=2, collate_fn=ds.collate_fn)))
+    assert tuple(src["img"].shape) == (2, 3, 96, 128) and tuple(src["K"].shape) == (2, 3, 3) and tuple(src["xyzs"].shape) == (2, 3, 16)
+    assert "G_cam_world" not in src
+    assert tuple(tgt["img"].shape) == (2, 1, 3, 96, 128) and tuple(tgt["G_src_tgt"].shape) == (2, 1, 4, 4)
+    assert tuple(tgt["xyzs"].shape) == (2, 1, 3, 16)
+    assert torch.allclose(src["K"] @ src["K_inv"], torch.eye(3).expand(2, 3, 3), atol=1e-4)
+    assert src["K"][0, 0, 0].item() == pytest.approx(140.0 * 128 / 160, rel=1e-5)     # focal rescaled to the working size
+    assert (src["xyzs"][:, 2] > 0).all()
+    # the batch drives a training step unchanged
+    task, cfg = _task({"data.visible_point_count": 16})
+    assert torch.isfinite(task.train_step((src, tgt))["loss"])
+
+
+def test_synthetic_batch_geometry():
+    s, t = synthetic_batch(2, 96, 128, 32, seed=1)
+    for xyz, k in ((s["xyzs"], s["K"]), (t["xyzs"][:, 0], t["K"][:, 0])):
+        p = k @ xyz
+        u, v = p[:, 0] / p[:, 2], p[:, 1] / p[:, 2]
+        assert (xyz[:, 2] > 0).all() and (u > 0).all() and (u < 127).all() and (v > 0).all() and (v < 95).all()
+
+
+def test_static_assets():
+    from mine_b200.data import assets as A
+    val = A.realestate10k_pairs("validation")
+    assert len(val) == 250 and len(A.realestate10k_pairs("test")) == 3335
+    assert val[0]["src"]["pose"].shape == (3, 4) and A.intrinsics_matrix(val[0]["src"]["intrinsics"], 384, 256).shape == (3, 3)
+    f = A.flowers_lightfield()
+    assert len(f["view_id"]) == 64 and len(f["train"]) == 3243 and len(f["test"]) == 100
+
+
+def test_video_generator_cpu(tmp_path):
+    import cv2
+    from visualizations.image_to_video import VideoGenerator, path_planning
+    xs, ys, zs = path_planning(90, -0.16, 0.0, -0.3, "double-straight-line")
+    assert len(xs) == 90 and xs[0] == pytest.approx(0.3 * -0.16)
+    xs, ys, zs = path_planning(90, -0.16, 0.0, -0.2, "circle")
+    assert len(xs) == 90
+    task, cfg = _task({"data.per_gpu_batch_size": 1}, is_val=True)
+    cfg["data.name"] = "realestate10k"
+    img = (np.random.rand(100, 140, 3) * 255).astype(np.uint8)
+    gen = VideoGenerator(task, cfg, task.logger, img, str(tmp_path))
+    gen.traj_config["num_frames"] = 4
+    frames = list(gen.render_frames(gen.tgts_poses[0][:3]))
+    assert len(frames) == 3 and frames[0][0].shape == (96, 128, 3) and frames[0][1].shape == (96, 128)
