@@ -15,24 +15,14 @@ import torch
 
 
 def inv3x3(m: torch.Tensor) -> torch.Tensor:
-    """Adjugate inverse of ``[...,3,3]`` matrices."""
-    a, b, c = m[..., 0, 0], m[..., 0, 1], m[..., 0, 2]
-    d, e, f = m[..., 1, 0], m[..., 1, 1], m[..., 1, 2]
-    g, h, i = m[..., 2, 0], m[..., 2, 1], m[..., 2, 2]
-    c00 = e * i - f * h
-    c01 = c * h - b * i
-    c02 = b * f - c * e
-    c10 = f * g - d * i
-    c11 = a * i - c * g
-    c12 = c * d - a * f
-    c20 = d * h - e * g
-    c21 = b * g - a * h
-    c22 = a * e - b * d
-    det = a * c00 + b * c10 + c * c20
-    adj = torch.stack([torch.stack([c00, c01, c02], -1),
-                       torch.stack([c10, c11, c12], -1),
-                       torch.stack([c20, c21, c22], -1)], -2)
-    return adj / det[..., None, None]
+    """Adjugate inverse of ``[...,3,3]`` matrices: the columns of adj(M) are the cross products of its rows
+    (6 small kernels on the GPU instead of a cuSOLVER call with a host sync)."""
+    r0, r1, r2 = m[..., 0, :], m[..., 1, :], m[..., 2, :]
+    c0 = torch.linalg.cross(r1, r2, dim=-1)
+    c1 = torch.linalg.cross(r2, r0, dim=-1)
+    c2 = torch.linalg.cross(r0, r1, dim=-1)
+    det = (r0 * c0).sum(dim=-1)
+    return torch.stack([c0, c1, c2], dim=-1) / det[..., None, None]
 
 
 def inv_rigid(g: torch.Tensor) -> torch.Tensor:
@@ -66,6 +56,19 @@ def scale_intrinsics(k: torch.Tensor, scale: int) -> torch.Tensor:
     deliberately *no* half-pixel correction - checkpoints were trained with this)."""
     ks = k / float(2 ** scale)
     ks = ks.clone()
+    ks[..., 2, 2] = 1.0
+    return ks
+
+
+_PYR_SCALES = {}
+
+
+def intrinsics_pyramid(k: torch.Tensor, levels: int = 4) -> torch.Tensor:
+    """``[levels,B,3,3]``: ``K / 2**s`` with ``K[2,2] = 1`` for every pyramid level, in two kernels."""
+    key = (str(k.device), k.dtype, levels)
+    if key not in _PYR_SCALES:      # cached per device: a host->device copy is illegal inside CUDA-graph capture
+        _PYR_SCALES[key] = torch.tensor([1.0 / 2 ** s for s in range(levels)], dtype=k.dtype).to(k.device)
+    ks = k[None] * _PYR_SCALES[key][:, None, None, None]
     ks[..., 2, 2] = 1.0
     return ks
 

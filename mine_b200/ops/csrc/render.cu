@@ -343,6 +343,23 @@ __device__ __forceinline__ Taps make_taps(float xc, float yc, int W, int H) {
   return t;
 }
 
+struct TapVals {
+  float4 a, b, c, d;
+};
+__device__ __forceinline__ TapVals load_taps(const float4* __restrict__ plane, const Taps& t) {
+  TapVals v;
+  v.a = ldg4(plane + t.i00); v.b = ldg4(plane + t.i01); v.c = ldg4(plane + t.i10); v.d = ldg4(plane + t.i11);
+  return v;
+}
+__device__ __forceinline__ float4 combine_taps(const TapVals& v, const Taps& t) {
+  float4 r;
+  r.x = v.a.x * t.w00 + v.b.x * t.w01 + v.c.x * t.w10 + v.d.x * t.w11;
+  r.y = v.a.y * t.w00 + v.b.y * t.w01 + v.c.y * t.w10 + v.d.y * t.w11;
+  r.z = v.a.z * t.w00 + v.b.z * t.w01 + v.c.z * t.w10 + v.d.z * t.w11;
+  r.w = v.a.w * t.w00 + v.b.w * t.w01 + v.c.w * t.w10 + v.d.w * t.w11;
+  return r;
+}
+
 __device__ __forceinline__ float4 bilerp(const float4* __restrict__ plane, const Taps& t) {
   const float4 a = ldg4(plane + t.i00), b = ldg4(plane + t.i01), c = ldg4(plane + t.i10), d = ldg4(plane + t.i11);
   float4 r;
@@ -374,12 +391,20 @@ __global__ void __launch_bounds__(256) render_tgt_fwd_kernel(
   const float4* base = mpi + (size_t)b * S * HW;
 
   float A = 1.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_z = 0.f, acc_w = 0.f, mask = 0.f;
+  // software pipeline: the four gathers of plane s+1 are in flight while plane s is composited
   Sample cur = plane_sample(s_geom[0], blk, s_depth[0], x, y, W, H);
+  Taps tp = make_taps(cur.xc, cur.yc, W, H);
+  TapVals tv = load_taps(base, tp);
   for (int s = 0; s < S; ++s) {
     Sample nxt = cur;
-    if (s + 1 < S) nxt = plane_sample(s_geom[s + 1], blk, s_depth[s + 1], x, y, W, H);
-    const Taps tp = make_taps(cur.xc, cur.yc, W, H);
-    const float4 v = bilerp(base + (size_t)s * HW, tp);
+    Taps tpn = tp;
+    TapVals tvn = tv;
+    if (s + 1 < S) {
+      nxt = plane_sample(s_geom[s + 1], blk, s_depth[s + 1], x, y, W, H);
+      tpn = make_taps(nxt.xc, nxt.yc, W, H);
+      tvn = load_taps(base + (size_t)(s + 1) * HW, tpn);
+    }
+    const float4 v = combine_taps(tv, tp);
     const float sig = (cur.pz >= 0.0f) ? v.w : 0.0f;
     float w, a_next;
     if (kAlpha) {
@@ -397,7 +422,7 @@ __global__ void __launch_bounds__(256) render_tgt_fwd_kernel(
     acc_z += w * cur.pz; acc_w += w;
     mask += (float)cur.valid;
     A = a_next;
-    cur = nxt;
+    cur = nxt; tp = tpn; tv = tvn;
   }
   rgb_out[(b * 3 + 0) * HW + pix] = acc_r;
   rgb_out[(b * 3 + 1) * HW + pix] = acc_g;
@@ -453,11 +478,18 @@ __global__ void __launch_bounds__(256) render_tgt_bwd_kernel(
 
   float A = 1.f, prefix = 0.f;
   Sample cur = plane_sample(s_geom[0], blk, s_depth[0], x, y, W, H);
+  Taps tp = make_taps(cur.xc, cur.yc, W, H);
+  TapVals tv = load_taps(base, tp);
   for (int s = 0; s < S; ++s) {
     Sample nxt = cur;
-    if (s + 1 < S) nxt = plane_sample(s_geom[s + 1], blk, s_depth[s + 1], x, y, W, H);
-    const Taps tp = make_taps(cur.xc, cur.yc, W, H);
-    const float4 v = bilerp(base + (size_t)s * HW, tp);
+    Taps tpn = tp;
+    TapVals tvn = tv;
+    if (s + 1 < S) {
+      nxt = plane_sample(s_geom[s + 1], blk, s_depth[s + 1], x, y, W, H);
+      tpn = make_taps(nxt.xc, nxt.yc, W, H);
+      tvn = load_taps(base + (size_t)(s + 1) * HW, tpn);
+    }
+    const float4 v = combine_taps(tv, tp);
     const bool front = cur.pz >= 0.0f;
     const float sig = front ? v.w : 0.0f;
     float w, a_next, T = 0.f, delta = kLastDelta;
@@ -484,7 +516,7 @@ __global__ void __launch_bounds__(256) render_tgt_bwd_kernel(
     if (tp.w10 != 0.f) red_add_v4(gp + tp.i10, make_float4(gv.x * tp.w10, gv.y * tp.w10, gv.z * tp.w10, gv.w * tp.w10));
     if (tp.w11 != 0.f) red_add_v4(gp + tp.i11, make_float4(gv.x * tp.w11, gv.y * tp.w11, gv.z * tp.w11, gv.w * tp.w11));
     A = a_next;
-    cur = nxt;
+    cur = nxt; tp = tpn; tv = tvn;
   }
 }
 

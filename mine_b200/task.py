@@ -177,6 +177,12 @@ class SynthesisTask:
         self.tgt_imgs, self.G_src_tgt = tgt_imgs[:, 0], g_src_tgt[:, 0]
         self.K_tgt, self.K_tgt_inv, self.pt3d_tgt = mv(tgt["K"])[:, 0], mv(tgt["K_inv"])[:, 0], mv(tgt["xyzs"])[:, 0]
         self.G_tgt_src = geo.inv_affine4x4(self.G_src_tgt)
+        # per-level intrinsics / image pyramids once per batch (not once per scale inside the loss)
+        self._K_src_lv = geo.intrinsics_pyramid(self.K_src)
+        self._K_tgt_lv = geo.intrinsics_pyramid(self.K_tgt)
+        self._K_src_inv_lv = geo.inv3x3(self._K_src_lv)
+        self._src_pyr = [L.nearest_downsample(self.src_imgs, s) for s in range(4)]
+        self._tgt_pyr = [L.nearest_downsample(self.tgt_imgs, s) for s in range(4)]
 
     # ------------------------------------------------------------------------------------------
     # model
@@ -226,12 +232,9 @@ class SynthesisTask:
     # ------------------------------------------------------------------------------------------
     def loss_fcn_per_scale(self, scale, mpi_all_src, disparity_all_src, scale_factor=None, is_val=False):
         c = self.config
-        src_img = L.nearest_downsample(self.src_imgs, scale)
-        tgt_img = L.nearest_downsample(self.tgt_imgs, scale)
+        src_img, tgt_img = self._src_pyr[scale], self._tgt_pyr[scale]
         B = src_img.shape[0]
-        K_src = geo.scale_intrinsics(self.K_src, scale)
-        K_tgt = geo.scale_intrinsics(self.K_tgt, scale)
-        K_src_inv = geo.inv3x3(K_src)
+        K_src, K_tgt, K_src_inv = self._K_src_lv[scale], self._K_tgt_lv[scale], self._K_src_inv_lv[scale]
         use_alpha = bool(c.get("mpi.use_alpha", False))
         if tuple(mpi_all_src.shape[-2:]) != tuple(src_img.shape[-2:]):
             raise ValueError("MPI resolution must equal the image resolution of its pyramid level")
