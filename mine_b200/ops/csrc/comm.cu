@@ -102,6 +102,48 @@ __global__ void __launch_bounds__(1024) allreduce_small_oneshot_kernel(float* __
   if (threadIdx.x == 0) *epoch_ptr = epoch;
 }
 
+// ---- small SUM, low-latency variant ------------------------------------------------------------------
+// Every value travels as one 8-byte word {fp32 bits, epoch}: the sender PUSHES its vector into every peer's
+// receive buffer, the receiver polls its own memory until the word carries the current epoch.  Data and flag
+// arrive together (64-bit stores are single-copy atomic), so one NVLink traversal replaces the
+// publish / flag / pull round trips of the kernel above.  ll: [2 parities][world sources][cap] uint2 per rank.
+__global__ void __launch_bounds__(1024) allreduce_small_ll_kernel(float* __restrict__ inout, int n, PeerTable ll, int rank,
+                                                                  int world, int cap, uint32_t* __restrict__ epoch_ptr) {
+  __shared__ uint2* s_dst[16];
+  const uint32_t epoch = *epoch_ptr + 1;
+  const size_t par_off = (size_t)(epoch & 1) * world * cap;
+  if ((int)threadIdx.x < world)
+    s_dst[threadIdx.x] = reinterpret_cast<uint2*>(ll.ptr[threadIdx.x]) + par_off + (size_t)rank * cap;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t bits = __float_as_uint(inout[i]);
+    for (int p = 0; p < world; ++p) {
+      if (p == rank) continue;
+      asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(s_dst[p] + i), "r"(bits), "r"(epoch) : "memory");
+    }
+  }
+  const uint2* mine = reinterpret_cast<const uint2*>(ll.ptr[rank]) + par_off;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float own = inout[i];
+    float acc = 0.f;
+    for (int r = 0; r < world; ++r) {                     // rank order: identical bits on every rank
+      float x = own;
+      if (r != rank) {
+        uint32_t lo, hi;
+        const uint2* src = mine + (size_t)r * cap + i;
+        do {
+          asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(src) : "memory");
+        } while (hi != epoch);
+        x = __uint_as_float(lo);
+      }
+      acc += x;
+    }
+    inout[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch_ptr = epoch;
+}
+
 // ---- two-shot mean, in place on the symmetric arena ---------------------------------------------------
 // Elements [lo, hi) of every rank's arena (float offsets, multiples of 4).  Rank r reduces its 1/world slice.
 // Four independent 16-byte peer loads per thread are in flight before the first add (NVLink latency ~2 us).
@@ -161,6 +203,12 @@ void launch_allreduce_small(float* inout, int n, const PeerTable& data, const Pe
                             int cap, uint32_t* epoch_ptr, cudaStream_t stream) {
   int threads = n >= 4096 ? 1024 : (n >= 1024 ? 512 : 256);
   allreduce_small_oneshot_kernel<<<1, threads, 0, stream>>>(inout, n, data, flags, rank, world, cap, epoch_ptr);
+}
+
+void launch_allreduce_small_ll(float* inout, int n, const PeerTable& ll, int rank, int world, int cap,
+                               uint32_t* epoch_ptr, cudaStream_t stream) {
+  int threads = n >= 2048 ? 1024 : (n >= 512 ? 512 : 256);
+  allreduce_small_ll_kernel<<<1, threads, 0, stream>>>(inout, n, ll, rank, world, cap, epoch_ptr);
 }
 
 void launch_allreduce_mean(const PeerTable& arena, const PeerTable& flags, float* mc_arena, int64_t lo, int64_t hi,

@@ -26,6 +26,16 @@ void allreduce_small(at::Tensor inout, std::vector<int64_t> data_ptrs, std::vect
                                at::cuda::getCurrentCUDAStream().stream());
 }
 
+void allreduce_small_ll(at::Tensor inout, std::vector<int64_t> ll_ptrs, int64_t rank, int64_t cap, at::Tensor epoch) {
+  TORCH_CHECK(inout.is_cuda() && inout.scalar_type() == at::kFloat && inout.is_contiguous(), "inout must be contiguous fp32");
+  TORCH_CHECK(inout.numel() <= cap, "vector larger than the LL slot");
+  TORCH_CHECK(epoch.is_cuda() && epoch.scalar_type() == at::kInt, "epoch must be a CUDA int32 tensor");
+  c10::cuda::CUDAGuard guard(inout.device());
+  mine::launch_allreduce_small_ll(inout.data_ptr<float>(), (int)inout.numel(), table_from(ll_ptrs), (int)rank,
+                                  (int)ll_ptrs.size(), (int)cap, reinterpret_cast<uint32_t*>(epoch.data_ptr<int>()),
+                                  at::cuda::getCurrentCUDAStream().stream());
+}
+
 void allreduce_mean(std::vector<int64_t> arena_ptrs, std::vector<int64_t> flag_ptrs, int64_t mc_ptr, int64_t lo, int64_t hi,
                     int64_t rank, at::Tensor epochs, int64_t blocks) {
   TORCH_CHECK(lo % 4 == 0 && hi % 4 == 0, "bucket bounds must be multiples of 4 floats");
@@ -40,5 +50,6 @@ void allreduce_mean(std::vector<int64_t> arena_ptrs, std::vector<int64_t> flag_p
 
 void register_comm(pybind11::module_& m) {
   m.def("allreduce_small", &allreduce_small);
+  m.def("allreduce_small_ll", &allreduce_small_ll);
   m.def("allreduce_mean", &allreduce_mean);
 }

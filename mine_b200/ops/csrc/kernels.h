@@ -63,6 +63,8 @@ struct PeerTable { void* ptr[16]; };
 // epoch counters are device-resident (advanced by the kernels): CUDA-graph replay safe
 void launch_allreduce_small(float* inout, int n, const PeerTable& data, const PeerTable& flags, int rank, int world,
                             int cap, uint32_t* epoch_ptr, cudaStream_t stream);
+void launch_allreduce_small_ll(float* inout, int n, const PeerTable& ll, int rank, int world, int cap,
+                               uint32_t* epoch_ptr, cudaStream_t stream);
 void launch_allreduce_mean(const PeerTable& arena, const PeerTable& flags, float* mc_arena, int64_t lo, int64_t hi,
                            int rank, int world, uint32_t* epochs, int blocks, cudaStream_t stream);
 }  // namespace mine

@@ -478,18 +478,11 @@ __global__ void __launch_bounds__(256) render_tgt_bwd_kernel(
 
   float A = 1.f, prefix = 0.f;
   Sample cur = plane_sample(s_geom[0], blk, s_depth[0], x, y, W, H);
-  Taps tp = make_taps(cur.xc, cur.yc, W, H);
-  TapVals tv = load_taps(base, tp);
   for (int s = 0; s < S; ++s) {
     Sample nxt = cur;
-    Taps tpn = tp;
-    TapVals tvn = tv;
-    if (s + 1 < S) {
-      nxt = plane_sample(s_geom[s + 1], blk, s_depth[s + 1], x, y, W, H);
-      tpn = make_taps(nxt.xc, nxt.yc, W, H);
-      tvn = load_taps(base + (size_t)(s + 1) * HW, tpn);
-    }
-    const float4 v = combine_taps(tv, tp);
+    if (s + 1 < S) nxt = plane_sample(s_geom[s + 1], blk, s_depth[s + 1], x, y, W, H);
+    const Taps tp = make_taps(cur.xc, cur.yc, W, H);
+    const float4 v = bilerp(base + (size_t)s * HW, tp);
     const bool front = cur.pz >= 0.0f;
     const float sig = front ? v.w : 0.0f;
     float w, a_next, T = 0.f, delta = kLastDelta;
@@ -516,7 +509,7 @@ __global__ void __launch_bounds__(256) render_tgt_bwd_kernel(
     if (tp.w10 != 0.f) red_add_v4(gp + tp.i10, make_float4(gv.x * tp.w10, gv.y * tp.w10, gv.z * tp.w10, gv.w * tp.w10));
     if (tp.w11 != 0.f) red_add_v4(gp + tp.i11, make_float4(gv.x * tp.w11, gv.y * tp.w11, gv.z * tp.w11, gv.w * tp.w11));
     A = a_next;
-    cur = nxt; tp = tpn; tv = tvn;
+    cur = nxt;
   }
 }
 

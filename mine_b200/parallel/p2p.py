@@ -16,6 +16,7 @@ import torch.distributed as dist
 from .comm import Communicator
 
 SMALL_CAP = 64 * 1024            # floats per one-shot slot
+LL_CAP = 8 * 1024                # floats per source in the low-latency (data+flag words) receive buffer
 FLAG_CHANNELS = 72               # channel 0: one-shot; 1..: CTAs of the two-shot kernel
 TWO_SHOT_BLOCKS = 64             # CTAs of the gradient kernel (leaves SMs for the overlapped backward)
 
@@ -37,6 +38,10 @@ class P2PComm(Communicator):
         mm = os.environ.get("MINE_B200_MULTIMEM", "auto")
         self.use_multimem = (dist.get_world_size(self.group) >= 4) if mm == "auto" else (mm == "1")
         self._small = self._alloc(2 * SMALL_CAP, torch.float32)
+        self.use_ll = os.environ.get("MINE_B200_LL", "1") == "1"
+        self._ll = self._alloc(2 * self.world_size * LL_CAP * 2, torch.int32)      # uint2 words
+        self._ll["tensor"].zero_()
+        self._epoch_ll = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._flags = self._alloc(FLAG_CHANNELS * 16, torch.int32)
         self._flags["tensor"].zero_()
         self._small["tensor"].zero_()
@@ -68,7 +73,10 @@ class P2PComm(Communicator):
         if t.numel() > SMALL_CAP or t.dtype != torch.float32:
             dist.all_reduce(t, group=self.group)                  # cold path (never hit by BN statistics)
             return t
-        self._ext.allreduce_small(t, self._small["ptrs"], self._flags["ptrs"], self.rank, SMALL_CAP, self._epoch_small)
+        if self.use_ll and t.numel() <= LL_CAP:
+            self._ext.allreduce_small_ll(t, self._ll["ptrs"], self.rank, LL_CAP, self._epoch_ll)
+        else:
+            self._ext.allreduce_small(t, self._small["ptrs"], self._flags["ptrs"], self.rank, SMALL_CAP, self._epoch_small)
         from ..ops import cuda as C
         C.LAUNCHES["count"] += 1
         return t

@@ -20,7 +20,7 @@ def main():
     res["multicast"] = bool(comm._small["mc"])
     # 1. small one-shot SUM, repeated (flag reuse / epoch bugs), odd sizes
     ok = True
-    for it, n in enumerate([1, 7, 513, 4097, 2 * 2048 + 1, 65536, 33, 33, 33]):
+    for it, n in enumerate([1, 7, 128, 513, 4097, 2 * 2048 + 1, 8192, 65536, 33, 33, 33, 256, 256]):
         g = torch.Generator(device="cpu").manual_seed(100 * it + rank)
         x = torch.randn(n, generator=g).to(dev)
         ref = x.clone()
@@ -77,9 +77,14 @@ def main():
         comm2.use_multimem = True
         res["ms_152MB_multimem"] = timeit(lambda: comm2.allreduce_mean_(a2))
     res["ms_152MB_nccl"] = timeit(lambda: (dist.all_reduce(nccl_buf), nccl_buf.mul_(1.0 / world)))
-    small = torch.zeros(4097, device=dev)
-    res["us_small_p2p"] = 1e3 * timeit(lambda: comm2.allreduce_sum_(small), 50)
-    res["us_small_nccl"] = 1e3 * timeit(lambda: dist.all_reduce(small), 50)
+    for n_small in (256, 4097):
+        small = torch.zeros(n_small, device=dev)
+        comm2.use_ll = True
+        res["us_small%d_ll" % n_small] = 1e3 * timeit(lambda: comm2.allreduce_sum_(small), 50)
+        comm2.use_ll = False
+        res["us_small%d_oneshot" % n_small] = 1e3 * timeit(lambda: comm2.allreduce_sum_(small), 50)
+        comm2.use_ll = True
+        res["us_small%d_nccl" % n_small] = 1e3 * timeit(lambda: dist.all_reduce(small), 50)
     # 4. two-rank training step: own comm == NCCL comm (same weights, same data)
     from mine_b200 import config as C
     from mine_b200.data.synthetic import synthetic_batch

