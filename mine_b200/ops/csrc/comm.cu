@@ -45,6 +45,15 @@ __device__ __forceinline__ void multimem_st_v4(float4* mc, float4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Spin guard: a peer that never arrives (crashed rank, mismatched call sequence) must not hang the GPU forever:
+// after ~10 s of polling the kernel traps, which surfaces as a CUDA error on the host.
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr uint64_t kSpinLimitNs = 10ull * 1000ull * 1000ull * 1000ull;
+
 // Flag barrier between the same-numbered CTA of every rank.  flags: [channels][world] uint32 per rank
 // (symmetric).  Thread p < world signals peer p and waits for peer p's signal; values only grow.
 __device__ __forceinline__ void peer_barrier(const PeerTable& flags, int rank, int world, int channel, uint32_t epoch) {
@@ -54,7 +63,11 @@ __device__ __forceinline__ void peer_barrier(const PeerTable& flags, int rank, i
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(flags.ptr[p]) + channel * world + rank, epoch);
     const uint32_t* mine_flag = reinterpret_cast<const uint32_t*>(flags.ptr[rank]) + channel * world + p;
-    while ((int32_t)(ld_acquire_sys(mine_flag) - epoch) < 0) { }
+    const uint64_t t0 = global_ns();
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(mine_flag) - epoch) < 0) {
+      if ((++spins & 0xFFFF) == 0 && global_ns() - t0 > kSpinLimitNs) __trap();
+    }
   }
   __syncthreads();
 }
@@ -131,8 +144,14 @@ __global__ void __launch_bounds__(1024) allreduce_small_ll_kernel(float* __restr
       if (r != rank) {
         uint32_t lo, hi;
         const uint2* src = mine + (size_t)r * cap + i;
+        uint32_t spins = 0;
+        uint64_t t0 = 0;
         do {
           asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(src) : "memory");
+          if (hi != epoch && (++spins & 0xFFFF) == 0) {
+            if (t0 == 0) t0 = global_ns();
+            else if (global_ns() - t0 > kSpinLimitNs) __trap();
+          }
         } while (hi != epoch);
         x = __uint_as_float(lo);
       }

@@ -89,7 +89,8 @@ def main():
     from mine_b200 import config as C
     from mine_b200.data.synthetic import synthetic_batch
     from mine_b200.task import SynthesisTask
-    base = {"data.img_w": 128, "data.img_h": 128, "mpi.num_bins_coarse": 4, "data.visible_point_count": 32,
+    # 256x256: the receptive-field block then normalises over >= 16 values per channel also at 8 ranks
+    base = {"data.img_w": 256, "data.img_h": 256, "mpi.num_bins_coarse": 4, "data.visible_point_count": 32,
             "model.imagenet_pretrained": False, "mpi.fix_disparity": True, "data.per_gpu_batch_size": 1,
             "lr.backbone_lr": 0.0, "lr.decoder_lr": 0.0}
     grads = {}
@@ -98,7 +99,7 @@ def main():
         cfg.update({"device": dev, "global_rank": rank})
         torch.manual_seed(0)
         task = SynthesisTask(cfg, None)
-        items = synthetic_batch(world, 128, 128, 32, seed=0)
+        items = synthetic_batch(world, 256, 256, 32, seed=0)
         mine = tuple({k: v[rank:rank + 1] for k, v in d.items()} for d in items)
         task.train_step(mine)
         torch.cuda.synchronize()
