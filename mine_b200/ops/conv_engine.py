@@ -18,8 +18,7 @@ Reference semantics: ``network/monodepth2/depth_decoder.py:124-146`` + ``layers.
 """
 from __future__ import annotations
 
-import os
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -60,15 +59,6 @@ def pick_tile(h: int, w: int, pixels: int = 128) -> Tuple[int, int]:
     return best
 
 
-def _pad_co(w_pack: torch.Tensor) -> torch.Tensor:
-    """[GT, Co, Ci] -> [GT, BN, Ci] with BN = Co rounded up to a multiple of 16."""
-    co = w_pack.shape[1]
-    bn = (co + 15) // 16 * 16
-    if bn != co:
-        w_pack = F.pad(w_pack, (0, 0, 0, bn - co))
-    return w_pack.to(torch.bfloat16).contiguous()
-
-
 _PHASE = torch.tensor([[[1.0, 0.0, 0.0], [0.0, 1.0, 1.0]],      # phase 0: taps {k0}, {k1 + k2}
                        [[1.0, 1.0, 0.0], [0.0, 0.0, 1.0]]])     # phase 1: taps {k0 + k1}, {k2}
 _PHASE_CACHE: Dict = {}
@@ -82,13 +72,9 @@ def _phase(device, dtype) -> torch.Tensor:
     return _PHASE_CACHE[key]
 
 
-def pack_same(w: torch.Tensor) -> torch.Tensor:
-    """[Co, Ci, 3, 3] -> fprop pack [9, Co, Ci] (tap = ky*3 + kx)."""
-    return w.permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1])
-
-
 def pack_up(w: torch.Tensor) -> torch.Tensor:
-    """[Co, Ci, 3, 3] -> phase pack [4 (py*2+px), 4 (a*2+b), Co, Ci] of the 2x2 sub-pixel kernels."""
+    """[Co, Ci, 3, 3] -> phase pack [4 (py*2+px), 4 (a*2+b), Co, Ci] of the 2x2 sub-pixel kernels (torch form of
+    ``pack(w, 1)``; used by tests and as the definition the CUDA packer is checked against)."""
     m = _phase(w.device, w.dtype)
     wp = torch.einsum("pak,qbl,oikl->pqaboi", m, m, w)
     return wp.reshape(4, 4, w.shape[0], w.shape[1])

@@ -27,7 +27,6 @@ struct ConvParams {
   void* raw_out;                         // head: sign of the sigma pre-activation, int8 [N, Ho, Wo] or null
   // filled by the launcher
   int stages, tmem_cols, ipb;
-  int dbg;                               // timing experiments only (MINE_CONV_DBG); 0 in production
 };
 
 struct ConvLaunch {

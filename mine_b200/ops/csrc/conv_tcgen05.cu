@@ -254,7 +254,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int u = 0; u < n_in; ++u, a_addr += sub_bytes) {
             const uint64_t da = desc0 + (uint64_t)(a_addr >> 4), db = desc0 + (uint64_t)((a_addr + a_bytes) >> 4);
             for (int k = 0; k < ksteps; ++k) {
-              if (!(p.dbg & 4)) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
               first = 1u;
             }
           }
@@ -293,7 +293,6 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (p.shared_map && valid)
         smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        if (p.dbg & 8) break;
         uint32_t v[16];
         tmem_ld16(t_acc + (uint32_t)c0, v);
         if (c0 >= p.Co) continue;
@@ -665,12 +664,11 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   if (ipb > p.T * p.kblocks) ipb = p.T * p.kblocks;
   if (ipb > 12) ipb = 12;
   if (ipb < 1) ipb = 1;
+  // tuning overrides for experiments (pipeline depth / iterations per barrier)
   static const int env_ipb = getenv("MINE_CONV_IPB") ? atoi(getenv("MINE_CONV_IPB")) : 0;
   static const int env_stages = getenv("MINE_CONV_STAGES") ? atoi(getenv("MINE_CONV_STAGES")) : 0;
-  static const int env_dbg = getenv("MINE_CONV_DBG") ? atoi(getenv("MINE_CONV_DBG")) : 0;
   if (env_ipb > 0) { ipb = env_ipb; if (ipb > p.T * p.kblocks) ipb = p.T * p.kblocks; }
   p.ipb = ipb;
-  p.dbg = env_dbg;
   const uint32_t stage_bytes = sub_bytes * ipb;
   int stages = (int)(96u * 1024u / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
