@@ -135,6 +135,57 @@ void fused_adam(at::Tensor p, const at::Tensor& g, at::Tensor m, at::Tensor v, c
                           cur_stream());
 }
 
+std::vector<at::Tensor> smooth_v2_fwd(const at::Tensor& img, const at::Tensor& disp, bool need_grad) {
+  check_f32(img, "img"); check_f32(disp, "disp");
+  TORCH_CHECK(img.dim() == 4 && img.size(1) == 3 && disp.dim() == 4 && disp.size(1) == 1, "img Bx3xHxW, disp Bx1xHxW");
+  const int B = disp.size(0), H = disp.size(2), W = disp.size(3);
+  c10::cuda::CUDAGuard guard(disp.device());
+  auto o = disp.options();
+  at::Tensor out = at::zeros({}, o), sums = at::zeros({B}, o), gd = at::zeros({B}, o);
+  at::Tensor g = need_grad ? at::empty({B, 1, H, W}, o) : at::Tensor();
+  mine::launch_smooth_v2_fwd(img.data_ptr<float>(), disp.data_ptr<float>(), sums.data_ptr<float>(), out.data_ptr<float>(),
+                             need_grad ? g.data_ptr<float>() : nullptr, need_grad ? gd.data_ptr<float>() : nullptr, B, H, W,
+                             cur_stream());
+  return {out, sums, g, gd};
+}
+
+at::Tensor smooth_v2_bwd(const at::Tensor& g, const at::Tensor& sums, const at::Tensor& gd, const at::Tensor& gout) {
+  check_f32(g, "g"); check_f32(gout, "gout");
+  c10::cuda::CUDAGuard guard(g.device());
+  at::Tensor grad = at::empty_like(g);
+  const int B = g.size(0), HW = g.size(2) * g.size(3);
+  mine::launch_smooth_v2_bwd(g.data_ptr<float>(), sums.data_ptr<float>(), gd.data_ptr<float>(), gout.data_ptr<float>(),
+                             grad.data_ptr<float>(), B, HW, cur_stream());
+  return grad;
+}
+
+std::vector<at::Tensor> smooth_v1_fwd(const at::Tensor& img, const at::Tensor& disp, double gmin, double ratio,
+                                      bool need_grad) {
+  check_f32(img, "img"); check_f32(disp, "disp");
+  TORCH_CHECK(img.dim() == 4 && img.size(1) == 3 && disp.dim() == 4 && disp.size(1) == 1, "img Bx3xHxW, disp Bx1xHxW");
+  const int B = disp.size(0), H = disp.size(2), W = disp.size(3);
+  c10::cuda::CUDAGuard guard(disp.device());
+  auto o = disp.options();
+  at::Tensor out = at::zeros({}, o), stats = at::zeros({B, 6}, o), hs = at::zeros({B, 4}, o);
+  at::Tensor sob = at::empty({B, 2, H, W}, o);
+  at::Tensor hmap = need_grad ? at::empty({B, 2, H, W}, o) : at::Tensor();
+  mine::launch_smooth_v1_fwd(img.data_ptr<float>(), disp.data_ptr<float>(), stats.data_ptr<float>(), sob.data_ptr<float>(),
+                             out.data_ptr<float>(), need_grad ? hmap.data_ptr<float>() : nullptr, hs.data_ptr<float>(),
+                             (float)gmin, (float)ratio, B, H, W, cur_stream());
+  return {out, stats, sob, hmap, hs};
+}
+
+at::Tensor smooth_v1_bwd(const at::Tensor& sob, const at::Tensor& stats, const at::Tensor& hmap, const at::Tensor& hs,
+                         const at::Tensor& gout) {
+  check_f32(sob, "sob"); check_f32(hmap, "hmap"); check_f32(gout, "gout");
+  c10::cuda::CUDAGuard guard(sob.device());
+  const int B = sob.size(0), H = sob.size(2), W = sob.size(3);
+  at::Tensor grad = at::zeros({B, 1, H, W}, sob.options());
+  mine::launch_smooth_v1_bwd(sob.data_ptr<float>(), stats.data_ptr<float>(), hmap.data_ptr<float>(), hs.data_ptr<float>(),
+                             gout.data_ptr<float>(), grad.data_ptr<float>(), B, H, W, cur_stream());
+  return grad;
+}
+
 }  // namespace
 
 void register_conv(pybind11::module_& m);     // conv_bindings.cpp
@@ -149,6 +200,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ssim_bwd", &ssim_bwd);
   m.def("masked_l1_fwd", &masked_l1_fwd);
   m.def("fused_adam", &fused_adam);
+  m.def("smooth_v2_fwd", &smooth_v2_fwd);
+  m.def("smooth_v2_bwd", &smooth_v2_bwd);
+  m.def("smooth_v1_fwd", &smooth_v1_fwd);
+  m.def("smooth_v1_bwd", &smooth_v1_bwd);
   register_conv(m);
   register_comm(m);
 }

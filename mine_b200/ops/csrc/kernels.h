@@ -68,3 +68,15 @@ void launch_allreduce_small_ll(float* inout, int n, const PeerTable& ll, int ran
 void launch_allreduce_mean(const PeerTable& arena, const PeerTable& flags, float* mc_arena, int64_t lo, int64_t hi,
                            int rank, int world, uint32_t* epochs, int blocks, cudaStream_t stream);
 }  // namespace mine
+
+namespace mine {
+// ---- smooth.cu (edge-aware smoothness v1 / v2; buffers sums/stats/out/gd/hs/grad must be zeroed by the caller) ----
+void launch_smooth_v2_fwd(const float* img, const float* disp, float* sums, float* out, float* g, float* gd, int B, int H,
+                          int W, cudaStream_t stream);
+void launch_smooth_v2_bwd(const float* g, const float* sums, const float* gd, const float* gout, float* grad, int B, int HW,
+                          cudaStream_t stream);
+void launch_smooth_v1_fwd(const float* img, const float* disp, float* stats, float* sob, float* out, float* hmap, float* hs,
+                          float gmin, float ratio, int B, int H, int W, cudaStream_t stream);
+void launch_smooth_v1_bwd(const float* sob, const float* stats, const float* hmap, const float* hs, const float* gout,
+                          float* grad, int B, int H, int W, cudaStream_t stream);
+}  // namespace mine

@@ -147,15 +147,50 @@ def masked_l1(syn, gt, mask_count, threshold: float) -> torch.Tensor:
     return _MaskedL1.apply(syn, gt, mask_count, threshold)
 
 
+class _SmoothV1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, disp, gmin, ratio):
+        need = disp.requires_grad
+        out, stats, sob, hmap, hs = _ext.smooth_v1_fwd(_f32c(img), _f32c(disp), float(gmin), float(ratio), need)
+        _count(2)
+        if need:
+            ctx.save_for_backward(sob, stats, hmap, hs)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sob, stats, hmap, hs = ctx.saved_tensors
+        grad = _ext.smooth_v1_bwd(sob, stats, hmap, hs, _f32c(g).reshape(1))
+        _count()
+        return None, grad, None, None
+
+
+class _SmoothV2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, disp):
+        need = disp.requires_grad
+        out, sums, g, gd = _ext.smooth_v2_fwd(_f32c(img), _f32c(disp), need)
+        _count(2)
+        if need:
+            ctx.save_for_backward(g, sums, gd)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        g, sums, gd = ctx.saved_tensors
+        grad = _ext.smooth_v2_bwd(g, sums, gd, _f32c(gout).reshape(1))
+        _count()
+        return None, grad
+
+
 def edge_aware_loss(img, disp, gmin: float, grad_ratio: float) -> torch.Tensor:
-    # composed from ATen ops for now (cold for LLFF: lambda_v1 = 0 -> logging only)
-    from ..spec import losses as L
-    return L.edge_aware_loss(img, disp, gmin, grad_ratio)
+    """Smoothness v1 (Sobel edge mask x hinge on instance-normalised |Sobel(disp)|): 2 launches (+1 backward)."""
+    return _SmoothV1.apply(img, disp, gmin, grad_ratio)
 
 
 def edge_aware_loss_v2(img, disp) -> torch.Tensor:
-    from ..spec import losses as L
-    return L.edge_aware_loss_v2(img, disp)
+    """Smoothness v2 (mean-normalised first differences x exp(-|dI|)): 2 launches (+1 backward)."""
+    return _SmoothV2.apply(img, disp)
 
 
 # ---- optimizer -----------------------------------------------------------------------------------

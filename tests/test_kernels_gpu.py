@@ -138,6 +138,28 @@ def test_masked_l1_matches_spec():
     assert torch.allclose(a.grad, a2.grad, atol=1e-9)
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 48), (1, 256, 384), (3, 50, 70)])
+def test_smoothness_losses_match_spec(shape):
+    from mine_b200.ops import cuda as C
+    b, h, w = shape
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(b, 3, h, w, generator=g).to(dev)
+    disp0 = (torch.rand(b, 1, h, w, generator=g) * 0.9 + 0.1).to(dev)
+    for kernel, spec in ((lambda d: C.edge_aware_loss_v2(img, d), lambda d: L.edge_aware_loss_v2(img.double(), d)),
+                         (lambda d: C.edge_aware_loss(img, d, 0.8, 0.2), lambda d: L.edge_aware_loss(img.double(), d, 0.8, 0.2))):
+        d1 = disp0.clone().requires_grad_(True)
+        d2 = disp0.double().clone().requires_grad_(True)
+        v1, v2 = kernel(d1), spec(d2)
+        assert abs(v1.item() - v2.item()) <= 2e-4 * abs(v2.item()) + 1e-7, (v1.item(), v2.item())
+        (3.0 * v1).backward(), (3.0 * v2).backward()
+        ref = d2.grad.float()
+        rel = (d1.grad - ref).norm().item() / (ref.norm().item() + 1e-12)
+        assert rel < 1e-2, rel                      # hinge / sign decisions can flip between fp32 and fp64 on a few pixels
+        with torch.no_grad():                       # no-grad path (logging metric)
+            assert abs(kernel(disp0).item() - v2.item()) <= 2e-4 * abs(v2.item()) + 1e-7
+
+
 def test_fused_adam_matches_torch():
     from mine_b200.ops import cuda as C
     dev = torch.device("cuda")
