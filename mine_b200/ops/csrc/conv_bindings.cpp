@@ -120,6 +120,8 @@ at::Tensor bn_act_pad_fwd(const at::Tensor& y, const at::Tensor& stats, const at
   check_bf16_nhwc(y, "y");
   c10::cuda::CUDAGuard guard(y.device());
   const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
+  TORCH_CHECK((C & (C - 1)) == 0 && C >= 16, "channels must be a power of two >= 16");
+  TORCH_CHECK((int64_t)N * (H + 2) * (W + 2) * (C / 8) < (1ll << 31), "tensor too large for 32-bit indexing");
   at::Tensor out = at::empty({N, H + 2, W + 2, C}, y.options());
   mine::launch_bn_act_pad_fwd(y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(),
                               out.data_ptr(), N, H, W, C, (int)pad_mode, (float)(1.0 / count), (float)eps, cur_stream());
@@ -133,6 +135,8 @@ std::vector<at::Tensor> bn_act_bwd_reduce(const at::Tensor& dapad, const at::Ten
   c10::cuda::CUDAGuard guard(y.device());
   const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
   TORCH_CHECK(dapad.size(1) == H + 2 && dapad.size(2) == W + 2 && dapad.size(3) == C, "dapad shape");
+  TORCH_CHECK((C & (C - 1)) == 0 && C >= 16, "channels must be a power of two >= 16");
+  TORCH_CHECK((int64_t)N * (H + 2) * (W + 2) * (C / 8) < (1ll << 31), "tensor too large for 32-bit indexing");
   at::Tensor g = at::empty_like(y);
   at::Tensor sums = at::zeros({2, C}, stats.options());
   mine::launch_bn_act_bwd_reduce(dapad.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(),

@@ -73,17 +73,21 @@ __global__ void __launch_bounds__(256) bn_act_pad_fwd_kernel(
     const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C, int pad_mode,
     float inv_count, float eps) {
-  const int cg = C >> 3;
+  const int cg = C >> 3;                         // power of two (C in {16,...,256})
+  const int cg_shift = 31 - __clz(cg);
   const int Hp = H + 2, Wp = W + 2;
-  const size_t total = (size_t)N * Hp * Wp * cg;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cg) * 8;
-    size_t pix = i / cg;
-    const int px = (int)(pix % Wp); pix /= Wp;
-    const int py = (int)(pix % Hp);
-    const int n = (int)(pix / Hp);
+  const unsigned total = (unsigned)N * Hp * Wp * cg;          // < 2^31 for every decoder tensor (checked on the host)
+  const unsigned stride = ((gridDim.x * blockDim.x) >> cg_shift) << cg_shift;   // keeps the channel group per thread
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= stride) return;
+  const int c0 = (int)(i0 & (cg - 1)) * 8;
+  const BnCoef k = bn_coef(stats, gamma, beta, C, c0, inv_count, eps);
+  for (unsigned i = i0; i < total; i += stride) {
+    unsigned pix = i >> cg_shift;
+    const int px = (int)(pix % (unsigned)Wp); pix /= (unsigned)Wp;
+    const int py = (int)(pix % (unsigned)Hp);
+    const int n = (int)(pix / (unsigned)Hp);
     const int sy = pad_src(py, H, pad_mode), sx = pad_src(px, W, pad_mode);
-    const BnCoef k = bn_coef(stats, gamma, beta, C, c0, inv_count, eps);
     V8 v = load_bf16x8(y + (((size_t)n * H + sy) * W + sx) * C + c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -102,23 +106,24 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
   extern __shared__ float s_sum[];     // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
   __syncthreads();
-  const int cg = C >> 3;
+  const int cg = C >> 3;                         // power of two
+  const int cg_shift = 31 - __clz(cg);
   const int Hp = H + 2, Wp = W + 2;
-  const size_t total = (size_t)N * H * W * cg;
+  const unsigned total = (unsigned)N * H * W * cg;            // < 2^31 (checked on the host)
   // a thread keeps its channel group for the whole grid-stride loop when the stride is a multiple of cg
-  const size_t stride = ((size_t)gridDim.x * blockDim.x / cg) * cg;
+  const unsigned stride = ((gridDim.x * blockDim.x) >> cg_shift) << cg_shift;
   float acc1[8], acc2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc1[j] = acc2[j] = 0.f;
-  size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const int c0 = (int)(i0 % cg) * 8;
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 & (cg - 1)) * 8;
   const BnCoef k = bn_coef(stats, gamma, beta, C, c0, inv_count, eps);
   if (i0 < stride) {
-    for (size_t i = i0; i < total; i += stride) {
-      size_t pix = i / cg;
-      const int x = (int)(pix % W); pix /= W;
-      const int yy = (int)(pix % H);
-      const int n = (int)(pix / H);
+    for (unsigned i = i0; i < total; i += stride) {
+      unsigned pix = i >> cg_shift;
+      const int x = (int)(pix % (unsigned)W); pix /= (unsigned)W;
+      const int yy = (int)(pix % (unsigned)H);
+      const int n = (int)(pix / (unsigned)H);
       // rows / cols of the padded gradient that map onto this pixel
       int ry[3], rx[3], ny = 1, nx = 1;
       ry[0] = yy + 1; rx[0] = x + 1;
