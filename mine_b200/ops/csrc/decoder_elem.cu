@@ -99,12 +99,26 @@ __global__ void __launch_bounds__(256) bn_act_pad_fwd_kernel(
 }
 
 // g = fold(dapad) * ELU'(bn(y)); sums[0][c] += g, sums[1][c] += g * xhat
+// BN coefficients live in shared memory (4 x C floats) instead of 32 registers per thread; interior pixels
+// (no pad adjoint) take a branch-free fast path.
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dapad, const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ g_out,
     float* __restrict__ sums, int N, int H, int W, int C, int pad_mode, float inv_count, float eps) {
-  extern __shared__ float s_sum[];     // [2][C]
+  extern __shared__ float s_mem[];     // [2][C] sums, then a[C], b[C], mean[C], invstd[C]
+  float* s_sum = s_mem;
+  float* s_a = s_mem + 2 * C;
+  float* s_b = s_a + C;
+  float* s_mean = s_b + C;
+  float* s_is = s_mean + C;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float m = stats[c] * inv_count;
+    float var = stats[C + c] * inv_count - m * m;
+    var = var < 0.f ? 0.f : var;
+    const float is = rsqrtf(var + eps);
+    s_mean[c] = m; s_is[c] = is; s_a[c] = gamma[c] * is; s_b[c] = beta[c] - m * gamma[c] * is;
+  }
   __syncthreads();
   const int cg = C >> 3;                         // power of two
   const int cg_shift = 31 - __clz(cg);
@@ -117,45 +131,40 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
   for (int j = 0; j < 8; ++j) acc1[j] = acc2[j] = 0.f;
   const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(i0 & (cg - 1)) * 8;
-  const BnCoef k = bn_coef(stats, gamma, beta, C, c0, inv_count, eps);
+  const int lo = pad_mode == 0 ? 1 : 0;          // reflection folds the border onto row/col 1 and n-2, replication onto 0 and n-1
   if (i0 < stride) {
     for (unsigned i = i0; i < total; i += stride) {
       unsigned pix = i >> cg_shift;
       const int x = (int)(pix % (unsigned)W); pix /= (unsigned)W;
       const int yy = (int)(pix % (unsigned)H);
       const int n = (int)(pix / (unsigned)H);
-      // rows / cols of the padded gradient that map onto this pixel
-      int ry[3], rx[3], ny = 1, nx = 1;
-      ry[0] = yy + 1; rx[0] = x + 1;
-      if (pad_mode == 0) {
-        if (yy == 1) ry[ny++] = 0;
-        if (yy == H - 2) ry[ny++] = H + 1;
-        if (x == 1) rx[nx++] = 0;
-        if (x == W - 2) rx[nx++] = W + 1;
-      } else {
-        if (yy == 0) ry[ny++] = 0;
-        if (yy == H - 1) ry[ny++] = H + 1;
-        if (x == 0) rx[nx++] = 0;
-        if (x == W - 1) rx[nx++] = W + 1;
+      const __nv_bfloat16* base = dapad + ((size_t)n * Hp * Wp) * C + c0;
+      V8 d = load_bf16x8(base + ((size_t)(yy + 1) * Wp + (x + 1)) * C);
+      const bool top = (yy == lo), bot = (yy == H - 1 - lo), lef = (x == lo), rig = (x == W - 1 - lo);
+      if (top | bot | lef | rig) {               // border pixels also receive the gradient of their pad copies
+        int ry[3], rx[3], ny = 1, nx = 1;
+        ry[0] = yy + 1; rx[0] = x + 1;
+        if (top) ry[ny++] = 0;
+        if (bot) ry[ny++] = H + 1;
+        if (lef) rx[nx++] = 0;
+        if (rig) rx[nx++] = W + 1;
+        for (int a = 0; a < ny; ++a)
+          for (int b = 0; b < nx; ++b) {
+            if (a == 0 && b == 0) continue;
+            const V8 t = load_bf16x8(base + ((size_t)ry[a] * Wp + rx[b]) * C);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d.f[j] += t.f[j];
+          }
       }
-      V8 d;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d.f[j] = 0.f;
-      for (int a = 0; a < ny; ++a)
-        for (int b = 0; b < nx; ++b) {
-          const V8 t = load_bf16x8(dapad + (((size_t)n * Hp + ry[a]) * Wp + rx[b]) * C + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d.f[j] += t.f[j];
-        }
       const size_t o = (((size_t)n * H + yy) * W + x) * C + c0;
       const V8 yv = load_bf16x8(y + o);
       V8 g;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float u = yv.f[j] * k.a[j] + k.b[j];
+        const float u = yv.f[j] * s_a[c0 + j] + s_b[c0 + j];
         const float de = u > 0.f ? 1.f : __expf(u);
         g.f[j] = d.f[j] * de;
-        const float xhat = (yv.f[j] - k.mean[j]) * k.invstd[j];
+        const float xhat = (yv.f[j] - s_mean[c0 + j]) * s_is[c0 + j];
         acc1[j] += g.f[j];
         acc2[j] += g.f[j] * xhat;
       }
@@ -291,7 +300,7 @@ void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* sta
   const size_t total = (size_t)N * H * W * (C / 8);
   int blocks = grid_for(total, 148 * 8);
   // the grid-stride must be a multiple of the channel-group count so every thread keeps its channels
-  bn_act_bwd_reduce_kernel<<<blocks, 256, 2 * C * sizeof(float), stream>>>(
+  bn_act_bwd_reduce_kernel<<<blocks, 256, 6 * C * sizeof(float), stream>>>(
       (const __nv_bfloat16*)dapad, (const __nv_bfloat16*)y, stats, gamma, beta, (__nv_bfloat16*)g_out, sums, N, H, W, C,
       pad_mode, inv_count, eps);
 }
