@@ -4,7 +4,7 @@ Reference: ``torch.optim.Adam(params=[backbone group, decoder group], weight_dec
 ``MultiStepLR`` stepped once per epoch (``synthesis_task.py:83-87,116-118,666``).  In torch 1.8
 that is a per-tensor Python loop (221 tensors x ~8 launches).  Here all parameters, gradients and
 both moment buffers are contiguous fp32 arenas, so one step is ONE fused multi-tensor kernel
-(``mine_b200/ops/csrc/adam_fused.cu``) per learning-rate group - or a handful of flat torch ops on
+(``mine_b200/ops/csrc/adam.cu``) per learning-rate group - or a handful of flat torch ops on
 CPU.  ``state_dict()`` / ``load_state_dict()`` speak ``torch.optim.Adam``'s format (per-parameter
 ``step / exp_avg / exp_avg_sq``) so optimizer state is interchangeable with reference checkpoints.
 """
