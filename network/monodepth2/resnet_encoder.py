@@ -1,1 +1,2 @@
-from mine_b200.models.encoder import ResnetEncoder  # noqa: F401
+from mine_b200.models.encoder import (ResnetEncoder, ResNetMultiImageInput,  # noqa: F401
+                                      resnet_multiimage_input)

@@ -228,3 +228,37 @@ def test_video_generator_cpu(tmp_path):
     gen.traj_config["num_frames"] = 4
     frames = list(gen.render_frames(gen.tgts_poses[0][:3]))
     assert len(frames) == 3 and frames[0][0].shape == (96, 128, 3) and frames[0][1].shape == (96, 128)
+
+
+# ---- encoder family (reference network/monodepth2/resnet_encoder.py:18-108) ----------------------------------------
+def test_resnet_encoder_family_and_multi_image_stem():
+    import torchvision
+    from network.monodepth2.resnet_encoder import ResnetEncoder, ResNetMultiImageInput, resnet_multiimage_input
+    from mine_b200.models.encoder import adapt_stem_to_multi_image
+    x = torch.rand(1, 3, 64, 96)
+    for n in (18, 50):
+        enc = ResnetEncoder(n, False).eval()
+        tv = getattr(torchvision.models, "resnet%d" % n)().eval()
+        enc.encoder.load_state_dict({k: v for k, v in tv.state_dict().items() if not k.startswith("fc.")}, strict=True)
+        xn = (x - enc.img_mean) / enc.img_std
+        want = tv.layer4(tv.layer3(tv.layer2(tv.layer1(tv.maxpool(tv.relu(tv.bn1(tv.conv1(xn))))))))
+        outs = enc(x)
+        assert [o.shape[1] for o in outs] == list(enc.num_ch_enc)
+        assert torch.allclose(outs[-1], want, atol=1e-5)
+    with pytest.raises(ValueError):
+        ResnetEncoder(20, False)
+    # two stacked identical frames through the tiled/halved stem == one frame through the original stem
+    single = ResnetEncoder(18, False).eval()
+    multi = resnet_multiimage_input(18, False, num_input_images=2).eval()
+    assert isinstance(multi, ResNetMultiImageInput) and multi.conv1.weight.shape[1] == 6
+    multi.load_state_dict(adapt_stem_to_multi_image(single.encoder.state_dict(), 2), strict=True)
+    xn = (x - single.img_mean) / single.img_std
+    assert torch.allclose(multi.conv1(torch.cat([xn, xn], 1)), single.encoder.conv1(xn), atol=1e-5)
+    assert ResnetEncoder(18, False, num_input_images=2)(torch.rand(1, 6, 64, 96))[-1].shape == (1, 512, 2, 3)
+
+
+def test_rendering_demo_checks():
+    from operations import test_rendering as demo
+    demo.test_mpi_composition()
+    demo.rotation_test()
+    demo.test_homography_sample()
