@@ -22,11 +22,16 @@ class ShardedSampler(data.Sampler):
                  drop_last: bool = False):
         self.n, self.world_size, self.rank, self.shuffle, self.seed, self.drop_last = len(dataset), world_size, rank, shuffle, seed, drop_last
         self.epoch = 0
+        self.start = 0                      # one-shot offset into this rank's shard (mid-epoch resume)
         self.num_samples = self.n // world_size if drop_last else math.ceil(self.n / world_size)
         self.total = self.num_samples * world_size
 
     def set_epoch(self, epoch: int):
         self.epoch = epoch
+
+    def set_start(self, consumed: int):
+        """Skip the first ``consumed`` samples of this rank's shard in the NEXT iteration only."""
+        self.start = max(0, int(consumed))
 
     def __len__(self):
         return self.num_samples
@@ -41,7 +46,9 @@ class ShardedSampler(data.Sampler):
             idx = idx[:self.total]
         else:
             idx = (idx * math.ceil(self.total / max(len(idx), 1)))[:self.total]
-        return iter(idx[self.rank:self.total:self.world_size])
+        shard = idx[self.rank:self.total:self.world_size]
+        start, self.start = self.start, 0
+        return iter(shard[start:])
 
 
 def _pin(tree):

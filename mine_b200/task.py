@@ -17,6 +17,7 @@ and checkpoint formats - on a different execution stack:
 from __future__ import annotations
 
 import glob
+import itertools
 import os
 from typing import Dict, List, Mapping, Optional, Tuple
 
@@ -142,6 +143,7 @@ class SynthesisTask:
         self.train_losses = {k: AverageMeter("train_" + k) for k in _LOSS_KEYS_TRAIN}
         self.val_losses = {k: AverageMeter("val_" + k) for k in _LOSS_KEYS_VAL}
         self.current_epoch = 0
+        self.epoch_step = 0                     # batches of the current epoch already consumed (mid-epoch resume)
         self.global_step = 0
         self.profiler = PhaseProfiler(enabled=False)
         self._gen = None
@@ -412,8 +414,20 @@ class SynthesisTask:
         log_every = int(cfg_get(c, "training.log_interval", 10))
         ckpt_every = int(cfg_get(c, "training.checkpoint_interval", 5000))
         max_steps = int(cfg_get(c, "training.max_steps", 0))
-        for step, items in enumerate(train_data_loader, start=1):
+        # resuming inside an epoch: this rank's shard continues after the batches it had consumed
+        skip = self.epoch_step if self.epoch_step < len(train_data_loader) else 0
+        if skip:
+            if hasattr(sampler, "set_start"):
+                sampler.set_start(skip * int(c["data.per_gpu_batch_size"]))
+                batches = train_data_loader
+            else:
+                batches = itertools.islice(iter(train_data_loader), skip, None)
+        else:
+            batches = train_data_loader
+        self.epoch_step = skip
+        for step, items in enumerate(batches, start=skip + 1):
             loss_dict = self.train_step(items)
+            self.epoch_step = step
             if step % log_every == 0 and self._is_main():
                 self.log_training(epoch, step, self.global_step, len(train_data_loader), loss_dict)
             if step % ckpt_every == 0 and self._is_main():
@@ -422,7 +436,8 @@ class SynthesisTask:
                                          or self.global_step % int(c["training.eval_interval"]) == 0):
                 self._eval_and_checkpoint(val_data_loader)
             if max_steps and self.global_step >= max_steps:
-                return
+                return self.epoch_step >= len(train_data_loader)
+        return True
 
     def _eval_and_checkpoint(self, val_data_loader):
         """All ranks arrive here at the same step.  Rank 0 evaluates (BN in eval mode does not
@@ -443,7 +458,7 @@ class SynthesisTask:
         if not ws:
             return None
         path = os.path.join(ws, name)
-        meta = {"global_step": self.global_step, "epoch": self.current_epoch,
+        meta = {"global_step": self.global_step, "epoch": self.current_epoch, "epoch_step": self.epoch_step,
                 "lr_scheduler": self.lr_scheduler.state_dict() if self.lr_scheduler else None,
                 "rng": rng_state() if with_optimizer else None}
         ckpt.save_checkpoint(path, self.backbone, self.decoder, self.optimizer if with_optimizer else None, meta)
@@ -457,6 +472,7 @@ class SynthesisTask:
     def _apply_resume(self, meta: Mapping) -> None:
         self.global_step = int(meta.get("global_step", 0))
         self.current_epoch = int(meta.get("epoch", 0))
+        self.epoch_step = int(meta.get("epoch_step", 0))
         if self.lr_scheduler is not None and meta.get("lr_scheduler"):
             self.lr_scheduler.load_state_dict(meta["lr_scheduler"])
         if meta.get("rng") is not None:
@@ -464,18 +480,23 @@ class SynthesisTask:
                 set_rng_state(meta["rng"])
             except Exception:      # RNG layouts differ across devices/torch versions: not fatal
                 pass
-        self.logger.info("Resumed at epoch %d, global_step %d" % (self.current_epoch, self.global_step))
+        self.logger.info("Resumed at epoch %d (batch %d), global_step %d" % (self.current_epoch, self.epoch_step,
+                                                                              self.global_step))
 
     def train(self, train_data_loader, val_data_loader):
         max_steps = int(cfg_get(self.config, "training.max_steps", 0))
         start_epoch = max(self.current_epoch, 1) if self.resume_meta else 1
         for epoch in range(start_epoch, int(self.config["training.epochs"]) + 1):
-            self.train_epoch(train_data_loader, val_data_loader, epoch)
-            self.lr_scheduler.step()
+            finished = self.train_epoch(train_data_loader, val_data_loader, epoch)
+            if finished:
+                self.lr_scheduler.step()
+                self.current_epoch, self.epoch_step = epoch + 1, 0        # a restart begins the next epoch
             if self._is_main():
-                self.logger.info("Epoch finished, average losses: ")
+                self.logger.info("Epoch finished, average losses: " if finished else "Stopped at training.max_steps: ")
                 for v in self.train_losses.values():
                     self.logger.info("    {}".format(v))
+                # the state a restart continues from (upstream only writes it every checkpoint interval)
+                self.save_checkpoint("checkpoint_latest.pth", with_optimizer=True)
             if max_steps and self.global_step >= max_steps:
                 break
 

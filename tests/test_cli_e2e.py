@@ -1,0 +1,64 @@
+"""Command-line surface end to end on CPU: launcher -> 2-rank training (gloo) -> checkpoint -> resume -> video.
+
+Mirrors the reference's only documented workflows (``README.md`` of the reference: ``sh start_training.sh ...`` and
+``python3 visualizations/image_to_video.py ...``)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+EXTRA = {"data.training_set_path": "synthetic:8", "data.img_w": 64, "data.img_h": 64, "data.per_gpu_batch_size": 1,
+         "mpi.num_bins_coarse": 4, "training.epochs": 2, "training.checkpoint_interval": 2, "training.log_interval": 1,
+         "data.visible_point_count": 16}
+
+
+def _launch(ws, port, max_steps):
+    extra = dict(EXTRA, **{"training.max_steps": max_steps})
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    cmd = ["sh", os.path.join(REPO, "start_training.sh"), "MASTER_ADDR=127.0.0.1", "MASTER_PORT=%d" % port,
+           "GPUS_PER_NODE=2", "WORKSPACE=%s" % ws, "DATASET=llff", "VERSION=v0", "EXTRA_CONFIG=%s" % json.dumps(extra)]
+    return subprocess.run(cmd, env=env, cwd=REPO, capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.timeout(1500)
+def test_launcher_train_resume_and_video(tmp_path):
+    ws = str(tmp_path / "ws")
+    r = _launch(ws, 29621, 3)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = os.path.join(ws, "v0")
+    names = os.listdir(out)
+    assert {"params.yaml", "training.log", "checkpoint_latest.pth"} <= set(names)
+    assert any(n.startswith("events.out.tfevents") for n in names)
+    ck = torch.load(os.path.join(out, "checkpoint_latest.pth"), map_location="cpu", weights_only=False)
+    assert {"backbone", "decoder", "optimizer"} <= set(ck)                       # upstream checkpoint layout
+    assert any(k.startswith("module.encoder.layer1.0.conv1") for k in ck["backbone"])      # DDP-style upstream names
+    step0 = int(ck["meta"]["global_step"])
+    assert step0 == 3
+
+    # same command again: picks up checkpoint_latest.pth and continues from step 3
+    r = _launch(ws, 29622, 5)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    log = open(os.path.join(out, "training.log")).read()
+    assert "Resumed at epoch 1 (batch 3), global_step 3" in log          # 4 batches per rank and epoch: mid-epoch restart
+    ck = torch.load(os.path.join(out, "checkpoint_latest.pth"), map_location="cpu", weights_only=False)
+    assert int(ck["meta"]["global_step"]) == 5 and int(ck["meta"]["epoch"]) == 2 and int(ck["meta"]["epoch_step"]) == 1
+
+    # inference CLI on the trained checkpoint
+    import cv2
+    rng = np.random.default_rng(0)
+    img_path = str(tmp_path / "photo.png")
+    cv2.imwrite(img_path, (rng.random((80, 96, 3)) * 255).astype(np.uint8))
+    vid_dir = str(tmp_path / "video")
+    r = subprocess.run([sys.executable, os.path.join(REPO, "visualizations", "image_to_video.py"), "--checkpoint_path",
+                        os.path.join(out, "checkpoint_latest.pth"), "--data_path", img_path, "--output_dir", vid_dir,
+                        "--gpus", "cpu"], cwd=REPO, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    produced = os.listdir(vid_dir)
+    assert any(n.endswith((".mp4", ".avi")) or os.path.isdir(os.path.join(vid_dir, n)) for n in produced), produced

@@ -87,3 +87,9 @@ def test_sharded_sampler_partitions_dataset():
         assert len(idx) == 4
         seen += idx
     assert set(seen) == set(range(10))
+    # mid-epoch resume: the offset applies to the next pass only and continues the same permutation
+    s = ShardedSampler(DS(), 3, 1, shuffle=True, seed=5)
+    s.set_epoch(2)
+    full = list(s)
+    s.set_start(3)
+    assert list(s) == full[3:] and list(s) == full
