@@ -50,6 +50,7 @@ class NeRFDataset(data.Dataset):
         if is_validation:
             folder += "_val"
         ratio = 1.0 if (ratio is None or ratio <= 1) else float(ratio)
+        self.image_folder = folder
 
         self.items: List[Dict] = []
         self.scene_of: List[str] = []
@@ -137,23 +138,31 @@ class NeRFDataset(data.Dataset):
         return src, dict(tgt)
 
 
-def resize_llff_images(root: str, ratio: float) -> int:
+def resize_llff_images(root: str, ratio: float, val_every: int = 0) -> int:
     """Offline helper: write ``images_<ratio>/`` downsampled copies for every scene
-    (reference ``input_pipelines/llff/misc/resize_nerf_llff_images.py``)."""
+    (reference ``input_pipelines/llff/misc/resize_nerf_llff_images.py``).
+
+    ``val_every = n > 0`` additionally creates the held-out split the dataset class looks for
+    (``images_<ratio>_val/``, reference ``nerf_dataset.py:52-53``): every n-th image of a scene (the usual LLFF
+    convention is 8) goes there instead of the training folder.  Upstream leaves that split to the user."""
     import cv2
     n = 0
     for scene in sorted(os.listdir(root)):
         src_dir = os.path.join(root, scene, "images")
         if not os.path.isdir(src_dir):
             continue
-        dst_dir = os.path.join(root, scene, "images_" + str(ratio))
-        os.makedirs(dst_dir, exist_ok=True)
-        for name in sorted(os.listdir(src_dir)):
+        train_dir = os.path.join(root, scene, "images_" + str(ratio))
+        val_dir = train_dir + "_val"
+        os.makedirs(train_dir, exist_ok=True)
+        if val_every > 0:
+            os.makedirs(val_dir, exist_ok=True)
+        for i, name in enumerate(sorted(os.listdir(src_dir))):
             img = cv2.imread(os.path.join(src_dir, name), cv2.IMREAD_COLOR)
             if img is None:
                 continue
             h, w = img.shape[:2]
             out = cv2.resize(img, (int(round(w / ratio)), int(round(h / ratio))), interpolation=cv2.INTER_AREA)
-            cv2.imwrite(os.path.join(dst_dir, name), out)
+            held_out = val_every > 0 and i % val_every == 0
+            cv2.imwrite(os.path.join(val_dir if held_out else train_dir, name), out)
             n += 1
     return n

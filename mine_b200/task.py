@@ -443,7 +443,7 @@ class SynthesisTask:
         """All ranks arrive here at the same step.  Rank 0 evaluates (BN in eval mode does not
         communicate); the others wait at a barrier - no rank runs ahead into a collective
         (the reference relies on accidental pairing, SURVEY 2.4 'rank-asymmetric control flow')."""
-        if self._is_main() and val_data_loader is not None:
+        if self._is_main() and val_data_loader is not None and len(val_data_loader) > 0:
             self.run_eval(val_data_loader)
             path = self.save_checkpoint("checkpoint_%012d.pth" % self.global_step, with_optimizer=False)
             if "hdfs_workspace" in self.config and path:

@@ -62,3 +62,33 @@ def test_launcher_train_resume_and_video(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     produced = os.listdir(vid_dir)
     assert any(n.endswith((".mp4", ".avi")) or os.path.isdir(os.path.join(vid_dir, n)) for n in produced), produced
+
+
+@pytest.mark.timeout(900)
+def test_train_cli_on_llff_layout_with_heldout_split(tmp_path):
+    """COLMAP scene on disk -> resize helper (train / ``_val`` folders) -> ``train.py`` with periodic evaluation."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from test_api_and_data import _write_scene
+    from mine_b200.data.llff import resize_llff_images
+    root = str(tmp_path / "llff")
+    _write_scene(root, n_views=8)
+    assert resize_llff_images(root, 2.0, val_every=4) == 8
+    assert sorted(os.listdir(os.path.join(root, "scene0", "images_2.0_val"))) == ["v1.png", "v5.png"]
+    extra = {"data.training_set_path": root, "data.img_pre_downsample_ratio": 2.0, "data.img_w": 64, "data.img_h": 64,
+             "data.per_gpu_batch_size": 2, "mpi.num_bins_coarse": 4, "training.epochs": 1, "training.eval_interval": 2,
+             "training.log_interval": 1, "data.visible_point_count": 16}
+    cmd = [sys.executable, os.path.join(REPO, "train.py"), "--config_path", os.path.join(REPO, "configs/params_llff.yaml"),
+           "--workspace", str(tmp_path / "ws"), "--version", "v0"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", MASTER_ADDR="127.0.0.1", MASTER_PORT="29631")
+    r = subprocess.run(cmd + ["--extra_config", json.dumps(extra)], cwd=REPO, env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = str(tmp_path / "ws" / "v0")
+    assert os.path.exists(os.path.join(out, "checkpoint_000000000002.pth"))       # written after the evaluation pass
+    log = open(os.path.join(out, "training.log")).read()
+    assert "number of images: 6" in log and "number of images: 2" in log and "val_psnr_tgt" in log
+    # the default ratio points at folders that do not exist here: fail loudly instead of training on nothing
+    extra["data.img_pre_downsample_ratio"] = 7.875
+    r = subprocess.run(cmd + ["--extra_config", json.dumps(extra)], cwd=REPO, env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode != 0 and "no training images under" in (r.stdout + r.stderr)

@@ -58,6 +58,13 @@ def get_dataset(config, logger, ctx):
                   img_pre_downsample_ratio=config["data.img_pre_downsample_ratio"])
         train_ds = NeRFDataset(config, logger, is_validation=False, seed=int(config.get("training.seed", 0)) + ctx.rank, **kw)
         val_ds = NeRFDataset(config, logger, is_validation=True, **kw)
+        if len(train_ds) == 0:
+            raise FileNotFoundError(
+                "no training images under %s/<scene>/%s (COLMAP model in <scene>/sparse/0): create the folder with "
+                "input_pipelines/llff/misc/resize_nerf_llff_images.py or set data.img_pre_downsample_ratio to null"
+                % (root, train_ds.image_folder))
+        if len(val_ds) == 0 and logger:
+            logger.info("no validation images under <scene>/%s: evaluation will be skipped" % val_ds.image_folder)
     else:
         raise NotImplementedError(
             f"no loader for {name!r} was ever released upstream; use data.training_set_path=synthetic "
