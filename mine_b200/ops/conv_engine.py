@@ -23,14 +23,30 @@ from typing import Dict, List, Tuple
 import torch
 import torch.nn.functional as F
 
+from .counters import LAUNCHES
+
 AVAILABLE = True
 BN_EPS = 1e-5
+ACT_DTYPE = torch.bfloat16      # activation / operand storage type (fp32 only under the emulator, for tight tests)
 
 _ext = None
+_emulated = False
+
+
+def use_emulator(flag: bool, dtype: torch.dtype = torch.bfloat16) -> None:
+    """Route the engine's kernel calls to the PyTorch specification in ``emu.py`` (any device, tests only)."""
+    global _emulated, ACT_DTYPE
+    from . import emu
+    _emulated = bool(flag)
+    ACT_DTYPE = dtype if flag else torch.bfloat16
+    emu.ACT_DTYPE = ACT_DTYPE
 
 
 def ext():
     global _ext
+    if _emulated:
+        from . import emu
+        return emu
     if _ext is None:
         from . import cuda as C
         _ext = C._ext
@@ -38,8 +54,7 @@ def ext():
 
 
 def _count(n=1):
-    from . import cuda as C
-    C.LAUNCHES["count"] += n
+    LAUNCHES["count"] += n
 
 
 # ---------------------------------------------------------------------------------------------
@@ -125,7 +140,7 @@ def conv_same_raw(xpad, w, out=None, chan_bias=None, plane_bias=None, shared_map
         _count()
         return out, sign
     if out is None:
-        out = torch.empty((n, h, w_, co), dtype=torch.bfloat16, device=xpad.device)
+        out = torch.empty((n, h, w_, co), dtype=ACT_DTYPE, device=xpad.device)
     ext().conv_taps(xpad, pack_, out, h, w_, 1, 9, SAME_TAPS_Y, SAME_TAPS_X, 1, co, 1, 1, [0], [0], False,
                     chan_bias, plane_bias, shared_map, planes, stats, 0, False, None, th, tw)
     _count()
@@ -139,7 +154,7 @@ def conv_up_raw(xpad_lo, w, chan_bias=None, plane_bias=None, shared_map=None, pl
     h, w_ = hp - 2, wp_ - 2
     co = w.shape[0]
     pack_ = pack(w, 1)
-    out = torch.empty((n, 2 * h, 2 * w_, co), dtype=torch.bfloat16, device=xpad_lo.device)
+    out = torch.empty((n, 2 * h, 2 * w_, co), dtype=ACT_DTYPE, device=xpad_lo.device)
     th, tw = pick_tile(h, w_)
     ext().conv_taps(xpad_lo, pack_, out, h, w_, 4, 4, UP_TAPS_Y, UP_TAPS_X, 1, co, 2, 2, UP_OY, UP_OX, False,
                     chan_bias, plane_bias, shared_map, planes, stats, 0, False, None, th, tw)
@@ -152,7 +167,7 @@ def dgrad_same_raw(dy, w):
     n, h, w_, co = dy.shape
     ci = w.shape[1]
     pack_ = pack(w, 2)                                                            # [tap][Ci][Co]
-    out = torch.empty((n, h + 2, w_ + 2, ci), dtype=torch.bfloat16, device=dy.device)
+    out = torch.empty((n, h + 2, w_ + 2, ci), dtype=ACT_DTYPE, device=dy.device)
     th, tw = pick_tile(h + 2, w_ + 2)
     ext().conv_taps(dy, pack_, out, h + 2, w_ + 2, 1, 9, [-k for k in SAME_TAPS_Y], [-k for k in SAME_TAPS_X], 1, ci,
                     1, 1, [0], [0], False, None, None, None, 1, None, 0, False, None, th, tw)
@@ -170,7 +185,7 @@ def dgrad_up_raw(dy, w):
     # forward: out[2y+py] += xpad[y + (py+a)]  =>  dxpad[q] += dy[2(q - py - a) + py] = dy[2q - py - 2a]
     ty = [-py - 2 * a for py in range(2) for px in range(2) for a in range(2) for b in range(2)]
     tx = [-px - 2 * b for py in range(2) for px in range(2) for a in range(2) for b in range(2)]
-    out = torch.empty((n, h + 2, w_ + 2, ci), dtype=torch.bfloat16, device=dy.device)
+    out = torch.empty((n, h + 2, w_ + 2, ci), dtype=ACT_DTYPE, device=dy.device)
     th, tw = pick_tile(h + 2, w_ + 2)
     ext().conv_taps(dy, pack_, out, h + 2, w_ + 2, 1, 16, ty, tx, 2, ci, 1, 1, [0], [0], False, None, None, None, 1,
                     None, 0, False, None, th, tw)
@@ -331,7 +346,9 @@ class ConvEngine:
         dec = self.decoder
         b, s = disparity.shape
         n = b * s
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        amp = dict(device_type=src_imgs.device.type, dtype=torch.bfloat16,
+                   enabled=src_imgs.is_cuda and ACT_DTYPE == torch.bfloat16)
+        with torch.autocast(**amp):
             feats = self.backbone(src_imgs.contiguous(memory_format=torch.channels_last))
             top = dec.receptive_field_extension(feats[-1])
         emb = dec.embed(disparity).float()                                       # [N, E]
@@ -343,7 +360,7 @@ class ConvEngine:
             bias = blk.conv.conv.bias
             smap = None
             if feat is not None:
-                with torch.autocast("cuda", dtype=torch.bfloat16):
+                with torch.autocast(**amp):
                     smap = F.conv2d(F.pad(feat, (1, 1, 1, 1), mode="reflect"), ws)
                 smap = smap.permute(0, 2, 3, 1).float().contiguous()            # [B,H,W,Co] fp32
             if blk.c_emb > 0:
@@ -357,7 +374,7 @@ class ConvEngine:
         y40 = smap[:, None] + pbias.reshape(b, s, 1, 1, -1)                        # [B,S,h,w,C]
         y40 = y40.reshape(n, *smap.shape[1:]).permute(0, 3, 1, 2)
         a = F.elu(blk.bn(y40)).permute(0, 2, 3, 1)                                 # NHWC fp32
-        xpad = pad_nhwc(a.to(torch.bfloat16), "replicate")                        # feeds the upsample conv
+        xpad = pad_nhwc(a.to(ACT_DTYPE), "replicate")                        # feeds the upsample conv
 
         outputs: Dict[int, torch.Tensor] = {}
         for i in range(4, -1, -1):

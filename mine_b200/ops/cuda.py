@@ -17,7 +17,7 @@ except Exception as e:  # pragma: no cover
     raise RuntimeError(
         "mine_b200 CUDA extension is not available (python -m mine_b200.ops.build): %r" % (e,)) from e
 
-LAUNCHES = {"count": 0}      # kernels launched by this package (bench.py reports it)
+from .counters import LAUNCHES  # noqa: E402  (kernels launched by this package; bench.py reports it)
 
 
 def _count(n: int = 1) -> None:

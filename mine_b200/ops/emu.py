@@ -1,0 +1,179 @@
+"""Executable specification of the conv-engine entry points (``csrc/conv_bindings.cpp``) in plain PyTorch.
+
+Every function here has the signature and the semantics of the sm_100a kernel of the same name - tap tables,
+sub-pixel groups, TMA out-of-bounds zero fill, strided gathers, epilogue fusions, BatchNorm partial sums - but runs
+anywhere (CPU included).  Two uses:
+
+* ``tests/test_engine_emulated.py`` drives the Python orchestration of the engine (``conv_engine.py``,
+  ``encoder_engine.py``: packing, tap tables, autograd wiring, BN algebra) against the ``nn.Module`` models on the
+  CPU test tier, where the kernels themselves cannot run;
+* it is the written-down contract the GPU tests hold the kernels to (``tests/test_conv_engine_gpu.py`` compares
+  kernel and emulator outputs for the same arguments).
+
+It is NOT a fallback: ``conv_engine.ext()`` only returns it when ``conv_engine.use_emulator(True)`` was called
+explicitly (tests) - on a GPU the real extension is used or an error is raised.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+ACT_DTYPE = torch.bfloat16          # ``conv_engine.use_emulator(True, torch.float32)`` switches to fp32 for tight tests
+
+
+def _gather(x: torch.Tensor, iy: torch.Tensor, ix: torch.Tensor) -> torch.Tensor:
+    """``x[:, iy, ix, :]`` with zero fill outside the tensor (what a TMA box returns)."""
+    hi, wi = x.shape[1], x.shape[2]
+    vy, vx = (iy >= 0) & (iy < hi), (ix >= 0) & (ix < wi)
+    patch = x[:, iy.clamp(0, hi - 1)][:, :, ix.clamp(0, wi - 1)]
+    return patch * (vy[:, None] & vx[None, :])[None, :, :, None].to(patch.dtype)
+
+
+def conv_taps(x, wpack, out, Hg, Wg, G, T, tap_y, tap_x, in_stride, Co, out_sy, out_sx, out_oy, out_ox, accumulate,
+              chan_bias, plane_bias, shared_map, planes_per_image, stats, act, head_alpha, raw_out, TH, TW) -> None:
+    """``out[n, oy*out_sy + out_oy[g], ox*out_sx + out_ox[g], :Co] = sum_t x[n, oy*in_stride + tap_y[g,t],
+    ox*in_stride + tap_x[g,t], :] @ wpack[g*T + t, :Co, :]^T`` (+ epilogue terms), for oy < Hg, ox < Wg."""
+    n = x.shape[0]
+    dev = x.device
+    xf, wf = x.float(), wpack.float()
+    oy, ox = torch.arange(Hg, device=dev), torch.arange(Wg, device=dev)
+    planes = max(int(planes_per_image), 1)
+    for g in range(G):
+        acc = torch.zeros((n, Hg, Wg, Co), dtype=torch.float32, device=dev)
+        for t in range(T):
+            patch = _gather(xf, oy * in_stride + tap_y[g * T + t], ox * in_stride + tap_x[g * T + t])
+            acc += patch @ wf[g * T + t, :Co].t()
+        yy, xx = oy * out_sy + out_oy[g], ox * out_sx + out_ox[g]
+        if chan_bias is not None:
+            acc += chan_bias.float()
+        if plane_bias is not None:
+            acc += plane_bias.float().reshape(n, 1, 1, Co)
+        if shared_map is not None:
+            sm = shared_map.float().reshape(n // planes, shared_map.shape[-3], shared_map.shape[-2], Co)
+            acc += sm[:, yy][:, :, xx].repeat_interleave(planes, dim=0)
+        if stats is not None:
+            stats[0] += acc.sum(dim=(0, 1, 2))
+            stats[1] += (acc * acc).sum(dim=(0, 1, 2))
+        if act == 1:
+            o4 = out.reshape(n, out.shape[-3], out.shape[-2], 4)
+            rgb = torch.sigmoid(acc[..., :3])
+            last = torch.sigmoid(acc[..., 3:4]) if head_alpha else acc[..., 3:4].abs() + 1e-4
+            o4[:, yy[:, None], xx[None, :]] = torch.cat([rgb, last], dim=-1)
+            if raw_out is not None:
+                sgn = torch.where(acc[..., 3] >= 0, 1, -1).to(raw_out.dtype)
+                raw_out.reshape(n, out.shape[-3], out.shape[-2])[:, yy[:, None], xx[None, :]] = sgn
+        else:
+            if accumulate:
+                acc = acc + out[:, yy[:, None], xx[None, :]].float()
+            out[:, yy[:, None], xx[None, :]] = acc.to(out.dtype)
+
+
+def wgrad_taps(dy, x, dw, Hg, Wg, G, T, tap_y, tap_x, dy_stride, dy_oy, dy_ox, TH, TW, x_stride: int = 1) -> None:
+    """``dw[g*T + t, co, ci] += sum_{n, oy < Hg, ox < Wg} dy[n, oy*dy_stride + dy_oy[g], ox*dy_stride + dy_ox[g], co] *
+    x[n, oy*x_stride + tap_y[g,t], ox*x_stride + tap_x[g,t], ci]`` (zero outside either tensor)."""
+    dev = x.device
+    dyf, xf = dy.float(), x.float()
+    oy, ox = torch.arange(Hg, device=dev), torch.arange(Wg, device=dev)
+    for g in range(G):
+        dyg = _gather(dyf, oy * dy_stride + dy_oy[g], ox * dy_stride + dy_ox[g])
+        for t in range(T):
+            xg = _gather(xf, oy * x_stride + tap_y[g * T + t], ox * x_stride + tap_x[g * T + t])
+            dw[g * T + t] += torch.einsum("nhwo,nhwi->oi", dyg, xg)
+
+
+def _phase_has(p: int, a: int, k: int) -> bool:
+    return (k == 0 if a == 0 else k >= 1) if p == 0 else (k <= 1 if a == 0 else k == 2)
+
+
+def pack_weights(w: torch.Tensor, mode: int) -> torch.Tensor:
+    """fp32 ``[Co,Ci,3,3]`` -> ``[9 | 16, rows_pad, cols]`` GEMM operand pack (modes: see ``conv_tcgen05.cu``)."""
+    co, ci = w.shape[:2]
+    dgrad, up = mode >= 2, bool(mode & 1)
+    if not up:
+        taps = [w[:, :, ky, kx] for ky in range(3) for kx in range(3)]
+    else:
+        taps = []
+        for py in range(2):
+            for px in range(2):
+                for a in range(2):
+                    for b in range(2):
+                        acc = torch.zeros_like(w[:, :, 0, 0])
+                        for ky in range(3):
+                            for kx in range(3):
+                                if _phase_has(py, a, ky) and _phase_has(px, b, kx):
+                                    acc = acc + w[:, :, ky, kx]
+                        taps.append(acc)
+    mats = [m.t() if dgrad else m for m in taps]                         # rows: Co (fprop) or Ci (dgrad)
+    rows = mats[0].shape[0]
+    rows_pad = (rows + 15) // 16 * 16
+    out = torch.zeros((len(mats), rows_pad, mats[0].shape[1]), dtype=ACT_DTYPE, device=w.device)
+    for i, m in enumerate(mats):
+        out[i, :rows] = m.to(ACT_DTYPE)
+    return out
+
+
+def _pad_src(n: int, mode: int, device) -> torch.Tensor:
+    s = torch.arange(-1, n + 1, device=device)
+    if mode == 0:
+        s = s.abs()
+        s = torch.where(s >= n, 2 * n - 2 - s, s)
+    else:
+        s = s.clamp(0, n - 1)
+    return s
+
+
+def _bn_coef(stats, gamma, beta, count, eps):
+    mean = stats[0] / count
+    var = (stats[1] / count - mean * mean).clamp_min(0)
+    invstd = torch.rsqrt(var + eps)
+    a = gamma * invstd
+    return mean, invstd, a, beta - mean * a
+
+
+def bn_act_pad_fwd(y, stats, gamma, beta, pad_mode, count, eps):
+    """``pad(ELU(BN(y)))``: reflection (0) or replication (1) border of one pixel, NHWC."""
+    _, _, a, b = _bn_coef(stats.float(), gamma.float(), beta.float(), count, eps)
+    u = F.elu(y.float() * a + b)
+    sy, sx = _pad_src(y.shape[1], pad_mode, y.device), _pad_src(y.shape[2], pad_mode, y.device)
+    return u[:, sy][:, :, sx].to(y.dtype).contiguous()
+
+
+def bn_act_bwd_reduce(dapad, y, stats, gamma, beta, pad_mode, count, eps):
+    """Adjoint of the pad, times ELU', plus the two BatchNorm backward sums ``[sum g, sum g*xhat]``."""
+    n, h, w, c = y.shape
+    mean, invstd, a, b = _bn_coef(stats.float(), gamma.float(), beta.float(), count, eps)
+    sy, sx = _pad_src(h, pad_mode, y.device), _pad_src(w, pad_mode, y.device)
+    d = torch.zeros((n, h, w, c), dtype=torch.float32, device=y.device)
+    d.index_put_((torch.arange(n, device=y.device)[:, None, None], sy[None, :, None], sx[None, None, :]),
+                 dapad.float(), accumulate=True)
+    yf = y.float()
+    u = yf * a + b
+    g = d * torch.where(u > 0, torch.ones_like(u), torch.exp(u))
+    xhat = (yf - mean) * invstd
+    sums = torch.stack([g.sum(dim=(0, 1, 2)), (g * xhat).sum(dim=(0, 1, 2))])
+    return [g.to(y.dtype), sums]
+
+
+def bn_bwd_apply(g, y, stats, gamma, sums, planes_per_image, want_shared, want_plane_bias, count, eps):
+    n, h, w, c = y.shape
+    s = max(int(planes_per_image), 1)
+    mean, invstd, _, _ = _bn_coef(stats.float(), gamma.float(), torch.zeros_like(gamma.float()), count, eps)
+    xhat = (y.float() - mean) * invstd
+    dy = gamma.float() * invstd * (g.float() - sums[0] / count - xhat * (sums[1] / count))
+    dshared = dy.reshape(n // s, s, h, w, c).sum(dim=1) if want_shared else None
+    dpb = dy.sum(dim=(1, 2)) if want_plane_bias else None
+    return [dy.to(y.dtype), dshared, dpb]
+
+
+def head_bwd(g_mpi, mpi, sign, use_alpha):
+    """Gradient of ``(sigmoid rgb, |x| + 1e-4 or sigmoid)`` as the 16-channel tensor the GEMMs consume."""
+    gm, o = g_mpi.reshape(-1, 4).float(), mpi.reshape(-1, 4).float()
+    d = gm * o * (1 - o)
+    if not use_alpha:
+        d = torch.cat([d[:, :3], gm[:, 3:] * sign.reshape(-1, 1).float()], dim=1)
+    dz = torch.zeros((*sign.shape, 16), dtype=ACT_DTYPE, device=mpi.device)
+    dz[..., :4] = d.reshape(*sign.shape, 4).to(ACT_DTYPE)
+    return [dz, d.sum(dim=0)]
+

@@ -207,3 +207,29 @@ def test_decoder_engine_matches_module():
         if r > 0.15:
             bad.append((kname, round(r, 3)))
     assert not bad, bad[:10]
+
+
+def test_kernels_match_emulator_contract():
+    """Same arguments through the sm_100a kernels and through the PyTorch specification (``ops/emu.py``) that the
+    CPU tier uses to test the engine's orchestration: fprop with every epilogue term, strided phase dgrad, wgrad."""
+    from mine_b200.ops import conv_engine as E
+    from mine_b200.ops import emu
+    n, h, w, ci, co = 4, 12, 20, 32, 64
+    xlo = _bf(_rand((n, h + 2, w + 2, ci), 0)).to(torch.bfloat16)
+    wt = _bf(_rand((co, ci, 3, 3), 1, 0.1))
+    pb, sm = _rand((n, co), 2), _rand((2, 2 * h, 2 * w, co), 3)
+    dy = _bf(_rand((n, 2 * h, 2 * w, co), 4)).to(torch.bfloat16)
+
+    def run():
+        stats = torch.zeros(2, co, device="cuda")
+        y = E.conv_up_raw(xlo, wt, plane_bias=pb, shared_map=sm, planes=2, stats=stats)
+        return y, stats, E.dgrad_up_raw(dy, wt), E.wgrad_up_raw(dy, xlo)
+    real = run()
+    E.use_emulator(True)
+    try:
+        spec = run()
+    finally:
+        E.use_emulator(False)
+    assert _rel(real[0], spec[0]) < 1e-2 and _rel(real[2], spec[2]) < 1e-2
+    assert torch.allclose(real[1], spec[1], rtol=2e-3, atol=1.0)
+    assert _rel2(real[3], spec[3]) < 2e-3

@@ -1,0 +1,147 @@
+"""Engine orchestration on the CPU tier: ``conv_engine.py`` driven through the PyTorch specification of the kernels
+(``mine_b200/ops/emu.py``) in fp32, compared with plain PyTorch modules / functional ops.
+
+What this pins down without a GPU: tap tables, sub-pixel phase packing and its adjoint, strided dgrad gathers, the
+padded-activation bookkeeping, BatchNorm forward/backward algebra, shared-skip / plane-bias factorisation, head
+activation gradients and the autograd wiring of the whole decoder.  The kernels themselves are held to the same
+specification by ``tests/test_conv_engine_gpu.py``."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mine_b200.ops import conv_engine as E
+
+
+@pytest.fixture(autouse=True)
+def _emulated_fp32():
+    E.use_emulator(True, torch.float32)
+    yield
+    E.use_emulator(False)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def _rand(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+SHAPES = [(2, 7, 10, 16, 32), (1, 12, 9, 32, 16), (2, 6, 6, 64, 64)]
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", SHAPES)
+def test_same_conv_all_directions(n, h, w, ci, co):
+    x = _rand((n, ci, h, w), 0).requires_grad_()
+    wt = _rand((co, ci, 3, 3), 1, 0.1).requires_grad_()
+    xp = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    xp.retain_grad()
+    ref = F.conv2d(xp, wt)
+    stats = torch.zeros(2, co)
+    pb, sm = _rand((n, co), 2), _rand((1, h, w, co), 3)
+    y = E.conv_same_raw(_nhwc(xp.detach()), wt.detach(), plane_bias=pb, shared_map=sm, planes=n, stats=stats)
+    full = ref + pb[:, :, None, None] + _nchw(sm)
+    assert torch.allclose(_nchw(y), full, atol=1e-4)
+    assert torch.allclose(stats[0], full.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(stats[1], (full * full).sum(dim=(0, 2, 3)), rtol=1e-4)
+    dy = _rand(ref.shape, 4)
+    ref.backward(dy)
+    assert torch.allclose(_nchw(E.dgrad_same_raw(_nhwc(dy), wt.detach())), xp.grad, atol=1e-4)
+    assert torch.allclose(E.wgrad_same_raw(_nhwc(dy), _nhwc(xp.detach())), wt.grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", SHAPES)
+def test_upsample_conv_all_directions(n, h, w, ci, co):
+    """conv3x3(reflect_pad(nearest_up2(x))) == 4 sub-pixel 2x2 convs on the replicate-padded low-res input."""
+    x = _rand((n, ci, h, w), 0)
+    wt = _rand((co, ci, 3, 3), 1, 0.1).requires_grad_()
+    xlo = F.pad(x, (1, 1, 1, 1), mode="replicate").requires_grad_()
+    inner = xlo[:, :, 1:-1, 1:-1]
+    ref = F.conv2d(F.pad(F.interpolate(inner, scale_factor=2, mode="nearest"), (1, 1, 1, 1), mode="reflect"), wt)
+    y = E.conv_up_raw(_nhwc(xlo.detach()), wt.detach())
+    assert torch.allclose(_nchw(y), ref, atol=1e-4)
+    # gradients w.r.t. the padded low-res tensor: the engine differentiates the phase form, in which the border
+    # samples come from the pad ring, so compare after folding the ring back (adjoint of replicate padding)
+    dy = _rand(ref.shape, 4)
+    ref.backward(dy)
+
+    def fold(g):                     # NCHW gradient of the padded tensor -> gradient of the unpadded tensor
+        g = g.clone()
+        g[:, :, 1] += g[:, :, 0]; g[:, :, -2] += g[:, :, -1]
+        g[:, :, :, 1] += g[:, :, :, 0]; g[:, :, :, -2] += g[:, :, :, -1]
+        return g[:, :, 1:-1, 1:-1]
+    got = _nchw(E.dgrad_up_raw(_nhwc(dy), wt.detach()))
+    assert torch.allclose(fold(got), fold(xlo.grad), atol=1e-4)
+    assert torch.allclose(E.wgrad_up_raw(_nhwc(dy), _nhwc(xlo.detach())), wt.grad, rtol=1e-4, atol=1e-3)
+    # CUDA packer definition == einsum definition
+    assert torch.allclose(E.pack(wt, 1)[:, :co].reshape(4, 4, co, ci), E.pack_up(wt.detach()), atol=1e-6)
+
+
+def test_fused_layer_autograd_matches_module_chain():
+    """PlaneConvBNAct (conv + shared skip + plane bias -> BN -> ELU -> pad) and HeadConv against torch autograd."""
+    b, s, h, w, ci, co = 2, 3, 6, 8, 32, 16
+    n = b * s
+    x = _rand((n, ci, h, w), 0)
+    wt = _rand((co, ci, 3, 3), 1, 0.1).requires_grad_()
+    sm = _rand((b, h, w, co), 2).requires_grad_()
+    pb = _rand((n, co), 3).requires_grad_()
+    gamma, beta = (torch.rand(co, generator=torch.Generator().manual_seed(4)) + 0.5).requires_grad_(), _rand((co,), 5).requires_grad_()
+    xin = x.clone().requires_grad_()
+    xp = F.pad(xin, (1, 1, 1, 1), mode="reflect")
+    yref = F.conv2d(xp, wt) + _nchw(sm).repeat_interleave(s, 0) + pb[:, :, None, None]
+    aref = F.pad(F.elu(F.batch_norm(yref, None, None, gamma, beta, True, 0.1, E.BN_EPS)), (1, 1, 1, 1), mode="reflect")
+    hw = _rand((4, co, 3, 3), 6, 0.2).requires_grad_()
+    hb = _rand((4,), 7).requires_grad_()
+    z = F.conv2d(aref, hw, hb)
+    mref = torch.cat([torch.sigmoid(z[:, :3]), z[:, 3:].abs() + 1e-4], 1)
+    gm = _rand(mref.shape, 8)
+    (mref * gm).sum().backward()
+    want = [t.grad.clone() for t in (xin, wt, sm, pb, gamma, beta, hw, hb)]
+    for t in (xin, wt, sm, pb, gamma, beta, hw, hb):
+        t.grad = None
+
+    xp2 = F.pad(xin, (1, 1, 1, 1), mode="reflect")
+    apad = E.PlaneConvBNAct.apply(_nhwc(xp2), wt, None, pb, sm, gamma, beta, False, s, 0, None, None)
+    mpi = E.HeadConv.apply(apad, hw, hb, False)
+    assert torch.allclose(_nchw(mpi), mref, atol=1e-4)
+    (mpi * _nhwc(gm)).sum().backward()
+    got = [t.grad for t in (xin, wt, sm, pb, gamma, beta, hw, hb)]
+    for name, g, r in zip("x w shared plane_bias gamma beta head_w head_b".split(), got, want):
+        assert torch.allclose(g, r, rtol=2e-3, atol=2e-4 * r.abs().max().item() + 1e-5), name
+
+
+def test_whole_decoder_on_emulated_engine_matches_modules():
+    from mine_b200.models.decoder import DepthDecoder
+    from mine_b200.models.encoder import ResnetEncoder
+    torch.manual_seed(0)
+    enc, dec = ResnetEncoder(18, False), DepthDecoder(num_ch_enc=[64, 64, 128, 256, 512])
+    b, s, h, w = 1, 2, 64, 64
+    img = torch.rand(b, 3, h, w)
+    disp = torch.rand(b, s) * 0.8 + 0.1
+    outs = E.ConvEngine(enc, dec, {}, torch.device("cpu")).predict(img, disp)
+    gouts = [torch.randn_like(o) for o in outs]
+    sum((o * g).sum() for o, g in zip(outs, gouts)).backward()
+    got = {k: p.grad.clone() for k, p in list(dec.named_parameters()) + [("enc." + k, p) for k, p in enc.named_parameters()]
+           if p.grad is not None}
+    for p in list(enc.parameters()) + list(dec.parameters()):
+        p.grad = None
+    ref = dec(enc(img), disp)
+    refs = [ref[("disp", k)].permute(0, 1, 3, 4, 2) for k in range(4)]
+    for k in range(4):
+        assert torch.allclose(outs[k], refs[k], atol=2e-4), k
+    sum((o * g).sum() for o, g in zip(refs, gouts)).backward()
+    checked = 0
+    for kname, p in list(dec.named_parameters()) + [("enc." + k, p) for k, p in enc.named_parameters()]:
+        if p.grad is None or kname.endswith("conv.conv.bias"):
+            continue        # conv biases in front of BatchNorm have an exactly-zero true gradient
+        assert kname in got, kname
+        # absolute floor: at this tiny resolution the receptive-field-extension maps are 1x1, so two of its
+        # BatchNorm shifts have an exactly-zero true gradient and both sides return ~1e-4 of rounding noise
+        diff = (got[kname] - p.grad).norm().item()
+        assert diff < 5e-3 * p.grad.norm().item() + 1e-3, (kname, diff, p.grad.norm().item())
+        checked += 1
+    assert checked > 80
