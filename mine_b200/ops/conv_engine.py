@@ -18,6 +18,7 @@ Reference semantics: ``network/monodepth2/depth_decoder.py:124-146`` + ``layers.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Tuple
 
 import torch
@@ -332,8 +333,16 @@ class ConvEngine:
     """Runs encoder (library convs, bf16 channels_last - 4 % of the FLOPs) and the factorised decoder
     with every per-plane convolution on the tcgen05 kernels."""
 
-    def __init__(self, backbone, decoder, config, device):
+    def __init__(self, backbone, decoder, config, device, encoder_mode: str | None = None):
         self.backbone, self.decoder, self.config, self.device = backbone, decoder, config, device
+        # encoder: "cudnn" (library convolutions under bf16 autocast) or "tcgen05" (encoder_engine.py)
+        self.encoder_mode = encoder_mode or os.environ.get("MINE_B200_ENCODER", "cudnn")
+        if self.encoder_mode not in ("cudnn", "tcgen05"):
+            raise ValueError("MINE_B200_ENCODER must be cudnn or tcgen05, got %r" % self.encoder_mode)
+        self.encoder_engine = None
+        if self.encoder_mode == "tcgen05":
+            from .encoder_engine import EncoderEngine
+            self.encoder_engine = EncoderEngine(backbone)
 
     def _reducer(self):
         from ..models.norm import BatchNorm
@@ -348,8 +357,12 @@ class ConvEngine:
         n = b * s
         amp = dict(device_type=src_imgs.device.type, dtype=torch.bfloat16,
                    enabled=src_imgs.is_cuda and ACT_DTYPE == torch.bfloat16)
+        if self.encoder_mode == "tcgen05":
+            feats = self.encoder_engine(src_imgs)
+        else:
+            with torch.autocast(**amp):
+                feats = self.backbone(src_imgs.contiguous(memory_format=torch.channels_last))
         with torch.autocast(**amp):
-            feats = self.backbone(src_imgs.contiguous(memory_format=torch.channels_last))
             top = dec.receptive_field_extension(feats[-1])
         emb = dec.embed(disparity).float()                                       # [N, E]
         reducer = self._reducer()

@@ -177,3 +177,32 @@ def head_bwd(g_mpi, mpi, sign, use_alpha):
     dz[..., :4] = d.reshape(*sign.shape, 4).to(ACT_DTYPE)
     return [dz, d.sum(dim=0)]
 
+
+
+# ---- encoder companions (csrc/encoder_elem.cu) ------------------------------------------------------------------
+def bn_res_act_fwd(y, stats, gamma, beta, residual, relu, count, eps):
+    """``[relu](BN(y) [+ residual])`` on an unpadded NHWC tensor."""
+    _, _, a, b = _bn_coef(stats.float(), gamma.float(), beta.float(), count, eps)
+    u = y.float() * a + b
+    if residual is not None:
+        u = u + residual.float()
+    if relu:
+        u = torch.relu(u)
+    return u.to(y.dtype)
+
+
+def bn_res_act_bwd_reduce(dout, out, y, stats, gamma, beta, relu, count, eps):
+    """``g = dout * [out > 0]`` (also the gradient of the residual branch) and ``[sum g, sum g*xhat]``."""
+    mean, invstd, _, _ = _bn_coef(stats.float(), gamma.float(), beta.float(), count, eps)
+    g = dout.float()
+    if relu:
+        g = g * (out.float() > 0).to(g.dtype)
+    xhat = (y.float() - mean) * invstd
+    sums = torch.stack([g.sum(dim=(0, 1, 2)), (g * xhat).sum(dim=(0, 1, 2))])
+    return [g.to(y.dtype), sums]
+
+
+def channel_stats(y):
+    """``[sum, sum of squares]`` per channel of an NHWC tensor (for convolutions that ran outside the engine)."""
+    yf = y.float()
+    return torch.stack([yf.sum(dim=(0, 1, 2)), (yf * yf).sum(dim=(0, 1, 2))])

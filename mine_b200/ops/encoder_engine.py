@@ -1,0 +1,265 @@
+"""ResNet encoder on the tcgen05 conv engine (Python orchestration).
+
+Same kernels as the decoder (``csrc/conv_tcgen05.cu``): every 1x1 and 3x3 convolution of the trunk - stride 1 or 2,
+forward, data gradient and weight gradient - is a tap table for ``conv_taps`` / ``wgrad_taps``:
+
+    fprop 3x3 /s : 9 taps (ky-1, kx-1), TMA element stride s, zero padding = TMA out-of-bounds fill
+    fprop 1x1 /s : 1 tap, element stride s
+    dgrad  /1    : mirrored taps, transposed weight pack
+    dgrad 3x3 /2 : 4 output-parity phases x (1|2)x(1|2) taps (zero-weight taps pad every phase to 4), strided store
+    dgrad 1x1 /2 : 1 tap, strided store into a zeroed tensor
+    wgrad        : taps as fprop, x gathered with element stride s
+
+BatchNorm statistics come out of the conv epilogue (per-channel sum / sum of squares); normalise + residual add +
+ReLU is one elementwise kernel, its backward two (reduce, apply) with the cross-GPU reduction of the 2C sums in
+between - the same structure as the decoder layers.  Only the 7x7 stem convolution (3 input channels, 0.6 % of the
+encoder FLOPs) and the max-pool stay on library kernels.
+
+Reference semantics: ``network/monodepth2/resnet_encoder.py:88-108`` (torchvision ResNet trunk, five outputs).
+Status: validated against the ``nn.Module`` encoder through the kernel specification (``ops/emu.py``,
+``tests/test_engine_emulated.py``); selected with ``MINE_B200_ENCODER=tcgen05`` (default: library convolutions).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import conv_engine as E
+from .conv_engine import BN_EPS, _count, ctx_world, ext, pick_tile
+
+
+def _taps(k: int) -> Tuple[List[int], List[int]]:
+    p = k // 2
+    return [ky - p for ky in range(k) for kx in range(k)], [kx - p for ky in range(k) for kx in range(k)]
+
+
+def _out_size(n: int, k: int, stride: int) -> int:
+    return (n + 2 * (k // 2) - k) // stride + 1
+
+
+def _pack_fprop(w: torch.Tensor) -> torch.Tensor:
+    """[Co,Ci,k,k] -> [k*k, Co, Ci] in the operand dtype."""
+    co, ci, k, _ = w.shape
+    return w.detach().permute(2, 3, 0, 1).reshape(k * k, co, ci).to(E.ACT_DTYPE).contiguous()
+
+
+def _pack_dgrad(w: torch.Tensor) -> torch.Tensor:
+    """[Co,Ci,k,k] -> [k*k, Ci, Co]."""
+    co, ci, k, _ = w.shape
+    return w.detach().permute(2, 3, 1, 0).reshape(k * k, ci, co).to(E.ACT_DTYPE).contiguous()
+
+
+# per-axis decomposition of the stride-2 3x3 data gradient: dx[2q + p] = sum_a dy[q + OFF[p][a]] * W[K[p][a]]
+_S2_OFF = ((0, 0), (1, 0))
+_S2_K = ((1, -1), (0, 2))            # -1: zero-weight filler tap (keeps T uniform across the four phases)
+_S2_INDEX_CACHE = {}
+
+
+def _pack_dgrad_s2(w: torch.Tensor) -> torch.Tensor:
+    """[Co,Ci,3,3] -> [16 (phase*4 + tap), Ci, Co] for the four output-parity phases."""
+    co, ci = w.shape[:2]
+    key = str(w.device)
+    if key not in _S2_INDEX_CACHE:
+        idx = []
+        for py in range(2):
+            for px in range(2):
+                for a in range(2):
+                    for b in range(2):
+                        ky, kx = _S2_K[py][a], _S2_K[px][b]
+                        idx.append(9 if (ky < 0 or kx < 0) else ky * 3 + kx)
+        _S2_INDEX_CACHE[key] = torch.tensor(idx, dtype=torch.long).to(w.device)
+    taps = torch.cat([_pack_dgrad(w), torch.zeros((1, ci, co), dtype=E.ACT_DTYPE, device=w.device)], dim=0)
+    return taps.index_select(0, _S2_INDEX_CACHE[key]).contiguous()
+
+
+_S2_TY = [_S2_OFF[py][a] for py in range(2) for px in range(2) for a in range(2) for b in range(2)]
+_S2_TX = [_S2_OFF[px][b] for py in range(2) for px in range(2) for a in range(2) for b in range(2)]
+_S2_OY = [py for py in range(2) for px in range(2)]
+_S2_OX = [px for py in range(2) for px in range(2)]
+
+
+# ---------------------------------------------------------------------------------------------
+# raw wrappers
+# ---------------------------------------------------------------------------------------------
+def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int, stats: Optional[torch.Tensor]) -> torch.Tensor:
+    """``x [N,H,W,Ci]`` -> ``conv(x, w, stride, padding=k//2) [N,Ho,Wo,Co]``; ``stats [2,Co]`` accumulates BN sums."""
+    n, h, w_, ci = x.shape
+    co, _, k, _ = w.shape
+    ho, wo = _out_size(h, k, stride), _out_size(w_, k, stride)
+    ty, tx = _taps(k)
+    out = torch.empty((n, ho, wo, co), dtype=E.ACT_DTYPE, device=x.device)
+    th, tw = pick_tile(ho, wo)
+    ext().conv_taps(x, _pack_fprop(w), out, ho, wo, 1, k * k, ty, tx, stride, co, 1, 1, [0], [0], False,
+                    None, None, None, 1, stats, 0, False, None, th, tw)
+    _count(2)
+    return out
+
+
+def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, h: int, w_: int) -> torch.Tensor:
+    """Gradient w.r.t. the ``[N,h,w_,Ci]`` input of :func:`conv_fprop`."""
+    n, ho, wo, co = dy.shape
+    ci, k = w.shape[1], w.shape[2]
+    if stride == 1:
+        ty, tx = _taps(k)
+        out = torch.empty((n, h, w_, ci), dtype=E.ACT_DTYPE, device=dy.device)
+        th, tw = pick_tile(h, w_)
+        ext().conv_taps(dy, _pack_dgrad(w), out, h, w_, 1, k * k, [-t for t in ty], [-t for t in tx], 1, ci, 1, 1,
+                        [0], [0], False, None, None, None, 1, None, 0, False, None, th, tw)
+        _count(2)
+        return out
+    if stride != 2:
+        raise ValueError("stride must be 1 or 2")
+    if k == 1:
+        out = torch.zeros((n, h, w_, ci), dtype=E.ACT_DTYPE, device=dy.device)        # odd rows / columns stay zero
+        th, tw = pick_tile(ho, wo)
+        ext().conv_taps(dy, _pack_dgrad(w), out, ho, wo, 1, 1, [0], [0], 1, ci, 2, 2, [0], [0], False,
+                        None, None, None, 1, None, 0, False, None, th, tw)
+        _count(3)
+        return out
+    if k != 3 or h % 2 or w_ % 2:
+        raise ValueError("stride-2 data gradient needs a 3x3 kernel and even input size")
+    out = torch.empty((n, h, w_, ci), dtype=E.ACT_DTYPE, device=dy.device)
+    th, tw = pick_tile(h // 2, w_ // 2)
+    ext().conv_taps(dy, _pack_dgrad_s2(w), out, h // 2, w_ // 2, 4, 4, _S2_TY, _S2_TX, 1, ci, 2, 2, _S2_OY, _S2_OX,
+                    False, None, None, None, 1, None, 0, False, None, th, tw)
+    _count(4)
+    return out
+
+
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, k: int, stride: int) -> torch.Tensor:
+    """fp32 ``[Co,Ci,k,k]`` weight gradient of :func:`conv_fprop`."""
+    n, ho, wo, co = dy.shape
+    ci = x.shape[3]
+    ty, tx = _taps(k)
+    dw = torch.zeros((k * k, co, ci), dtype=torch.float32, device=dy.device)
+    pix = E._wgrad_pixels(co, ci, ho, wo)
+    if stride > 1:
+        pix = min(pix, 128)                        # strided x box: stride * TW <= 256
+    th, tw = pick_tile(ho, wo, pix)
+    ext().wgrad_taps(dy, x, dw, ho, wo, 1, k * k, ty, tx, 1, [0], [0], th, tw, stride)
+    _count(2)
+    return dw.reshape(k, k, co, ci).permute(2, 3, 0, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd nodes
+# ---------------------------------------------------------------------------------------------
+class Conv(torch.autograd.Function):
+    """``y, stats = conv(x, w)``: NHWC activations in the operand dtype, fp32 master weights ``[Co,Ci,k,k]``."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, want_stats):
+        stats = torch.zeros((2, w.shape[0]), dtype=torch.float32, device=x.device) if want_stats else None
+        y = conv_fprop(x, w, stride, stats)
+        ctx.save_for_backward(x, w)
+        ctx.stride = int(stride)
+        if stats is None:
+            stats = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dw = conv_wgrad(dy, x, w.shape[2], ctx.stride).to(w.dtype) if ctx.needs_input_grad[1] else None
+        dx = conv_dgrad(dy, w, ctx.stride, x.shape[1], x.shape[2]) if ctx.needs_input_grad[0] else None
+        return dx, dw, None, None
+
+
+class BNAct(torch.autograd.Function):
+    """``a = [relu](BN(y) [+ residual])`` from the conv epilogue's batch sums; training or running statistics."""
+
+    @staticmethod
+    def forward(ctx, y, stats, gamma, beta, residual, relu, bn, reducer):
+        training = bn is None or bn.training
+        count = float(y.shape[0] * y.shape[1] * y.shape[2])
+        if training:
+            if stats.numel() == 0:
+                stats = ext().channel_stats(y)
+                _count()
+            if reducer is not None:
+                stats = reducer(stats.reshape(-1)).reshape(2, -1).contiguous()
+                count *= ctx_world(reducer)
+        else:
+            rm, rv = bn.running_mean.float(), bn.running_var.float()
+            stats = torch.stack([rm * count, (rv + rm * rm) * count]).contiguous()
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        a = ext().bn_res_act_fwd(y, stats, g32, b32, residual, bool(relu), count, BN_EPS)
+        _count()
+        if bn is not None and training:
+            with torch.no_grad():
+                mean = stats[0] / count
+                var = (stats[1] / count - mean * mean).clamp_min(0)
+                m = bn.momentum
+                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+                bn.running_var.mul_(1 - m).add_(var * (count / max(count - 1.0, 1.0)), alpha=m)
+                bn.num_batches_tracked += 1
+        ctx.save_for_backward(y, a, stats, g32, b32)
+        ctx.cfg = (bool(relu), count, reducer, residual is not None, training)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        y, a, stats, g32, b32 = ctx.saved_tensors
+        relu, count, reducer, has_res, training = ctx.cfg
+        g, sums = ext().bn_res_act_bwd_reduce(da.contiguous(), a, y, stats, g32, b32, relu, count, BN_EPS)
+        dgamma, dbeta = sums[1].clone(), sums[0].clone()
+        if not training:             # frozen statistics: BN is a per-channel affine map
+            sums = torch.zeros_like(sums)
+        elif reducer is not None:
+            sums = reducer(sums.reshape(-1)).reshape(2, -1).contiguous()
+        dy = ext().bn_bwd_apply(g, y, stats, g32, sums, 1, False, False, count, BN_EPS)[0]
+        _count(2)
+        return dy, None, dgamma.to(g32.dtype), dbeta.to(b32.dtype), (g if has_res else None), None, None, None
+
+
+def conv_bn_act(x, conv, bn, relu=True, residual=None, reducer=None):
+    stride = conv.stride[0]
+    y, stats = Conv.apply(x, conv.weight, stride, bn.training)
+    return BNAct.apply(y, stats, bn.weight, bn.bias, residual, relu, bn, reducer)
+
+
+# ---------------------------------------------------------------------------------------------
+# driver
+# ---------------------------------------------------------------------------------------------
+class EncoderEngine:
+    """Runs a :class:`mine_b200.models.encoder.ResnetEncoder` (any depth) on the engine; returns the five NCHW
+    (channels-last strided) feature maps ``ResnetEncoder.forward`` returns."""
+
+    def __init__(self, backbone):
+        self.backbone = backbone
+
+    def _reducer(self):
+        return self.backbone.encoder.bn1.reducer
+
+    def _block(self, blk, x, reducer):
+        if blk.downsample is not None:
+            idt = conv_bn_act(x, blk.downsample[0], blk.downsample[1], relu=False, reducer=reducer)
+        else:
+            idt = x
+        if hasattr(blk, "conv3"):                                   # bottleneck
+            out = conv_bn_act(x, blk.conv1, blk.bn1, reducer=reducer)
+            out = conv_bn_act(out, blk.conv2, blk.bn2, reducer=reducer)
+            return conv_bn_act(out, blk.conv3, blk.bn3, relu=True, residual=idt, reducer=reducer)
+        out = conv_bn_act(x, blk.conv1, blk.bn1, reducer=reducer)
+        return conv_bn_act(out, blk.conv2, blk.bn2, relu=True, residual=idt, reducer=reducer)
+
+    def __call__(self, img: torch.Tensor):
+        bb, e = self.backbone, self.backbone.encoder
+        reducer = self._reducer()
+        x = (img - bb.img_mean.to(img.dtype)) / bb.img_std.to(img.dtype)
+        amp = dict(device_type=img.device.type, dtype=torch.bfloat16, enabled=img.is_cuda and E.ACT_DTYPE == torch.bfloat16)
+        with torch.autocast(**amp):                                # stem: 7x7/2 on 3 channels stays a library conv
+            y = F.conv2d(x.contiguous(memory_format=torch.channels_last), e.conv1.weight, None, 2, 3)
+        y = y.permute(0, 2, 3, 1).to(E.ACT_DTYPE).contiguous()
+        c1 = BNAct.apply(y, torch.empty(0, device=y.device), e.bn1.weight, e.bn1.bias, None, True, e.bn1, reducer)
+        x = F.max_pool2d(c1.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+        feats = [c1]
+        for li in range(1, 5):
+            for blk in getattr(e, f"layer{li}"):
+                x = self._block(blk, x, reducer)
+            feats.append(x)
+        return tuple(f.permute(0, 3, 1, 2) for f in feats)

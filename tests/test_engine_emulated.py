@@ -114,7 +114,8 @@ def test_fused_layer_autograd_matches_module_chain():
         assert torch.allclose(g, r, rtol=2e-3, atol=2e-4 * r.abs().max().item() + 1e-5), name
 
 
-def test_whole_decoder_on_emulated_engine_matches_modules():
+@pytest.mark.parametrize("encoder_mode", ["cudnn", "tcgen05"])
+def test_whole_decoder_on_emulated_engine_matches_modules(encoder_mode):
     from mine_b200.models.decoder import DepthDecoder
     from mine_b200.models.encoder import ResnetEncoder
     torch.manual_seed(0)
@@ -122,7 +123,7 @@ def test_whole_decoder_on_emulated_engine_matches_modules():
     b, s, h, w = 1, 2, 64, 64
     img = torch.rand(b, 3, h, w)
     disp = torch.rand(b, s) * 0.8 + 0.1
-    outs = E.ConvEngine(enc, dec, {}, torch.device("cpu")).predict(img, disp)
+    outs = E.ConvEngine(enc, dec, {}, torch.device("cpu"), encoder_mode=encoder_mode).predict(img, disp)
     gouts = [torch.randn_like(o) for o in outs]
     sum((o * g).sum() for o, g in zip(outs, gouts)).backward()
     got = {k: p.grad.clone() for k, p in list(dec.named_parameters()) + [("enc." + k, p) for k, p in enc.named_parameters()]
@@ -145,3 +146,55 @@ def test_whole_decoder_on_emulated_engine_matches_modules():
         assert diff < 5e-3 * p.grad.norm().item() + 1e-3, (kname, diff, p.grad.norm().item())
         checked += 1
     assert checked > 80
+
+
+# ---- encoder on the engine ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,stride,h,w", [(1, 1, 6, 8), (3, 1, 7, 9), (1, 2, 8, 12), (3, 2, 8, 12), (1, 2, 7, 9)])
+def test_encoder_conv_directions(k, stride, h, w):
+    from mine_b200.ops import encoder_engine as EE
+    if k == 3 and stride == 2 and (h % 2 or w % 2):
+        pytest.skip("even sizes only")
+    n, ci, co = 2, 32, 64
+    x = _rand((n, ci, h, w), 0).requires_grad_()
+    wt = _rand((co, ci, k, k), 1, 0.1).requires_grad_()
+    ref = F.conv2d(x, wt, None, stride, k // 2)
+    stats = torch.zeros(2, co)
+    y = EE.conv_fprop(_nhwc(x.detach()), wt.detach(), stride, stats)
+    assert torch.allclose(_nchw(y), ref, atol=1e-4)
+    assert torch.allclose(stats[0], ref.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
+    dy = _rand(ref.shape, 2)
+    ref.backward(dy)
+    assert torch.allclose(_nchw(EE.conv_dgrad(_nhwc(dy), wt.detach(), stride, h, w)), x.grad, atol=1e-4)
+    assert torch.allclose(EE.conv_wgrad(_nhwc(dy), _nhwc(x.detach()), k, stride), wt.grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("layers,train", [(18, True), (50, True), (50, False)])
+def test_encoder_engine_matches_module(layers, train):
+    from mine_b200.models.encoder import ResnetEncoder
+    from mine_b200.ops.encoder_engine import EncoderEngine
+    torch.manual_seed(0)
+    enc = ResnetEncoder(layers, False)
+    enc.train(train)
+    # the deep variant is badly conditioned at random init (few samples per BatchNorm in layer4, gradient norms
+    # ~1e6): fp32 summation-order noise is amplified, so it gets more pixels and a looser bound than ResNet-18
+    img = torch.rand(2, 3, 64, 96) if layers == 18 else torch.rand(2, 3, 128, 128)
+    tol = 5e-3 if layers == 18 or not train else 5e-2
+    state = {k: v.clone() for k, v in enc.state_dict().items()}
+    outs = EncoderEngine(enc)(img)
+    gouts = [torch.randn_like(o) for o in outs]
+    sum((o * g).sum() for o, g in zip(outs, gouts)).backward()
+    got = {k: p.grad.clone() for k, p in enc.named_parameters()}
+    run_stats = {k: v.clone() for k, v in enc.state_dict().items() if "running" in k or "tracked" in k}
+    enc.load_state_dict(state)
+    for p in enc.parameters():
+        p.grad = None
+    refs = enc(img)
+    for o, r in zip(outs, refs):
+        assert o.shape == r.shape and torch.allclose(o, r, atol=2e-4 * max(1.0, r.abs().max().item()))
+    sum((o * g).sum() for o, g in zip(refs, gouts)).backward()
+    for k, p in enc.named_parameters():
+        diff = (got[k] - p.grad).norm().item()
+        assert diff < tol * p.grad.norm().item() + 1e-3, (k, diff, p.grad.norm().item())
+    for k, v in enc.state_dict().items():
+        if k in run_stats:
+            assert torch.allclose(run_stats[k].float(), v.float(), rtol=1e-4, atol=1e-5), k
