@@ -209,7 +209,7 @@ def wgrad_same_raw(dy, xpad):
     ci = xpad.shape[3]
     dw = torch.zeros((9, co, ci), dtype=torch.float32, device=dy.device)
     th, tw = pick_tile(h, w_, _wgrad_pixels(co, ci, h, w_))
-    ext().wgrad_taps(dy, xpad, dw, h, w_, 1, 9, SAME_TAPS_Y, SAME_TAPS_X, 1, [0], [0], th, tw)
+    ext().wgrad_taps(dy, xpad, dw, h, w_, 1, 9, SAME_TAPS_Y, SAME_TAPS_X, 1, [0], [0], th, tw, 1)
     _count(2)
     return dw.reshape(3, 3, co, ci).permute(2, 3, 0, 1)
 
@@ -221,7 +221,7 @@ def wgrad_up_raw(dy, xpad_lo):
     ci = xpad_lo.shape[3]
     dwp = torch.zeros((16, co, ci), dtype=torch.float32, device=dy.device)
     th, tw = pick_tile(h, w_, min(128, _wgrad_pixels(co, ci, h, w_)))      # strided dy box: 2*TW <= 256
-    ext().wgrad_taps(dy, xpad_lo, dwp, h, w_, 4, 4, UP_TAPS_Y, UP_TAPS_X, 2, UP_OY, UP_OX, th, tw)
+    ext().wgrad_taps(dy, xpad_lo, dwp, h, w_, 4, 4, UP_TAPS_Y, UP_TAPS_X, 2, UP_OY, UP_OX, th, tw, 1)
     _count(2)
     return unpack_up_grad(dwp.reshape(4, 4, co, ci))
 

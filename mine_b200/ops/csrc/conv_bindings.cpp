@@ -47,7 +47,15 @@ void conv_taps(const at::Tensor& x, const at::Tensor& wpack, at::Tensor out, int
     for (int t = 0; t < T; ++t) { p.tap_y[g][t] = (int16_t)tap_y[g * T + t]; p.tap_x[g][t] = (int16_t)tap_x[g * T + t]; }
     p.out_oy[g] = (int16_t)out_oy[g]; p.out_ox[g] = (int16_t)out_ox[g];
   }
-  p.Co = Co; p.BN = wpack.size(1);
+  // wide layers (encoder): Co is produced in blocks of 128 accumulator columns; <= 256 rows: one block (decoder)
+  const int64_t rows = wpack.size(1);
+  p.Co = Co;
+  if (rows <= 256) { p.BN = rows; p.CB = 1; }
+  else {
+    TORCH_CHECK(rows % 128 == 0 && rows == Co, "wide weight packs need Co == rows, a multiple of 128");
+    p.BN = 128; p.CB = rows / 128;
+  }
+  L.w_rows = rows;
   p.out_sy = out_sy; p.out_sx = out_sx;
   p.out = out.data_ptr();
   p.act = act; p.head_alpha = head_alpha;
@@ -93,7 +101,7 @@ at::Tensor pack_weights(const at::Tensor& w, int64_t mode) {
 
 void wgrad_taps(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_t Hg, int64_t Wg, int64_t G, int64_t T,
                 std::vector<int64_t> tap_y, std::vector<int64_t> tap_x, int64_t dy_stride, std::vector<int64_t> dy_oy,
-                std::vector<int64_t> dy_ox, int64_t TH, int64_t TW) {
+                std::vector<int64_t> dy_ox, int64_t TH, int64_t TW, int64_t x_stride) {
   check_bf16_nhwc(dy, "dy"); check_bf16_nhwc(x, "x");
   TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.is_contiguous() && dw.dim() == 3, "dw must be fp32 [G*T,Co,Ci]");
   TORCH_CHECK(dw.size(0) == G * T && dw.size(1) == dy.size(3) && dw.size(2) == x.size(3), "dw shape");
@@ -104,6 +112,7 @@ void wgrad_taps(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_
   p.N = x.size(0); p.Hg = Hg; p.Wg = Wg; p.TH = TH; p.TW = TW; p.KP = TH * TW;
   p.G = G; p.T = T; p.Co = dy.size(3); p.Ci = x.size(3);
   p.dy_stride = dy_stride;
+  p.x_stride = x_stride;
   for (int g = 0; g < G; ++g) {
     for (int t = 0; t < T; ++t) { p.tap_y[g][t] = (int16_t)tap_y[g * T + t]; p.tap_x[g][t] = (int16_t)tap_x[g * T + t]; }
     p.dy_oy[g] = (int16_t)dy_oy[g]; p.dy_ox[g] = (int16_t)dy_ox[g];
@@ -175,6 +184,56 @@ std::vector<at::Tensor> head_bwd(const at::Tensor& g_mpi, const at::Tensor& mpi,
   return {dz, dbias};
 }
 
+inline void check_channels(const at::Tensor& y) {
+  const int64_t C = y.size(3);
+  TORCH_CHECK((C & (C - 1)) == 0 && C >= 16 && C <= 2048, "channels must be a power of two in [16, 2048]");
+  TORCH_CHECK(y.numel() / 8 < (1ll << 31), "tensor too large for 32-bit indexing");
+}
+
+at::Tensor bn_res_act_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
+                          const c10::optional<at::Tensor>& residual, bool relu, double count, double eps) {
+  check_bf16_nhwc(y, "y"); check_channels(y);
+  TORCH_CHECK(stats.numel() == 2 * y.size(3) && opt_f32(stats, "stats") && opt_f32(gamma, "gamma") && opt_f32(beta, "beta"),
+              "stats/gamma/beta");
+  const void* res = nullptr;
+  if (residual.has_value() && residual->defined()) {
+    check_bf16_nhwc(*residual, "residual");
+    TORCH_CHECK(residual->sizes() == y.sizes(), "residual shape");
+    res = residual->data_ptr();
+  }
+  c10::cuda::CUDAGuard guard(y.device());
+  at::Tensor out = at::empty_like(y);
+  mine::launch_bn_res_act_fwd(y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(), res,
+                              out.data_ptr(), (size_t)(y.numel() / y.size(3)), (int)y.size(3), relu ? 1 : 0,
+                              (float)(1.0 / count), (float)eps, cur_stream());
+  return out;
+}
+
+std::vector<at::Tensor> bn_res_act_bwd_reduce(const at::Tensor& dout, const at::Tensor& out, const at::Tensor& y,
+                                              const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
+                                              bool relu, double count, double eps) {
+  check_bf16_nhwc(dout, "dout"); check_bf16_nhwc(out, "out"); check_bf16_nhwc(y, "y"); check_channels(y);
+  TORCH_CHECK(dout.sizes() == y.sizes() && out.sizes() == y.sizes(), "shape mismatch");
+  TORCH_CHECK(stats.numel() == 2 * y.size(3) && opt_f32(stats, "stats"), "stats");
+  (void)gamma; (void)beta;                     // the reduction needs mean / invstd only; kept for a uniform signature
+  c10::cuda::CUDAGuard guard(y.device());
+  at::Tensor g = at::empty_like(y);
+  at::Tensor sums = at::zeros({2, y.size(3)}, stats.options());
+  mine::launch_bn_res_act_bwd_reduce(dout.data_ptr(), out.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), g.data_ptr(),
+                                     sums.data_ptr<float>(), (size_t)(y.numel() / y.size(3)), (int)y.size(3),
+                                     relu ? 1 : 0, (float)(1.0 / count), (float)eps, cur_stream());
+  return {g, sums};
+}
+
+at::Tensor channel_stats(const at::Tensor& y) {
+  check_bf16_nhwc(y, "y"); check_channels(y);
+  c10::cuda::CUDAGuard guard(y.device());
+  at::Tensor sums = at::zeros({2, y.size(3)}, y.options().dtype(at::kFloat));
+  mine::launch_channel_stats(y.data_ptr(), sums.data_ptr<float>(), (size_t)(y.numel() / y.size(3)), (int)y.size(3),
+                             cur_stream());
+  return sums;
+}
+
 }  // namespace
 
 void register_conv(pybind11::module_& m) {
@@ -185,4 +244,7 @@ void register_conv(pybind11::module_& m) {
   m.def("bn_act_bwd_reduce", &bn_act_bwd_reduce);
   m.def("bn_bwd_apply", &bn_bwd_apply);
   m.def("head_bwd", &head_bwd);
+  m.def("bn_res_act_fwd", &bn_res_act_fwd);
+  m.def("bn_res_act_bwd_reduce", &bn_res_act_bwd_reduce);
+  m.def("channel_stats", &channel_stats);
 }

@@ -13,7 +13,9 @@ struct ConvParams {
   int in_stride;                         // 1, or 2 for the strided gather of the phase-conv dgrad
   int16_t tap_y[4][16], tap_x[4][16];    // input offset of every (group, tap), in input pixels
   // output tensor [N, Ho, Wo, Co]; GEMM pixel (oy, ox) of group g lands on (oy*out_sy + out_oy[g], ox*out_sx + out_ox[g])
-  int Co, BN, Ho, Wo, out_sy, out_sx;
+  // Co output channels are produced in CB blocks of BN (<= 256) accumulator columns: one work item = (tile, image,
+  // group, channel block); CB == 1 for the decoder (BN = Co padded to 16), > 1 for the wide encoder layers
+  int Co, BN, CB, Ho, Wo, out_sy, out_sx;
   int16_t out_oy[4], out_ox[4];
   void* out;
   int out_fp32, accumulate;
@@ -32,13 +34,14 @@ struct ConvParams {
 struct ConvLaunch {
   ConvParams p;
   const void* x; int Hi, Wi;             // NHWC bf16 input [N, Hi, Wi, Ci]
-  const void* w;                         // packed bf16 weights [G*T, BN, Ci]
+  const void* w; int w_rows;             // packed bf16 weights [G*T, w_rows = CB*BN, Ci]
 };
 
 struct WgradParams {
   int N, Hg, Wg, TH, TW, KP, tiles_x, tiles_y;
   int G, T, Co, Ci;
   int dy_stride;                         // 1, or 2 when dy is addressed through sub-pixel phases
+  int x_stride;                          // 1, or 2 for the weight gradient of a stride-2 convolution
   int16_t dy_oy[4], dy_ox[4];            // phase offsets into dy
   int16_t tap_y[4][16], tap_x[4][16];    // offsets into x
   float* dw;                             // fp32 [G*T, Co, Ci], accumulated with atomics

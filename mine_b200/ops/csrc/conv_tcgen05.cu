@@ -173,7 +173,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     s_tap[threadIdx.x >> 4][threadIdx.x & 15][1] = p.tap_x[threadIdx.x >> 4][threadIdx.x & 15];
   }
   const int tiles = p.tiles_x * p.tiles_y;
-  const int total_work = tiles * p.N * p.G;
+  const int total_work = tiles * p.N * p.G * p.CB;     // w -> (tile, image, group, channel block), tile fastest
 
   const int row_bytes = p.KB * 2;                     // == swizzle span
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
@@ -205,7 +205,8 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       bool ring_full = false;                           // becomes true once every slot has been used once
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int tile = w % tiles, wi = w / tiles;
-        const int n_img = wi % p.N, g = wi / p.N;
+        const int n_img = wi % p.N, gc = wi / p.N;
+        const int g = gc % p.G, wcol0 = (gc / p.G) * p.BN;
         const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
         const int oy0 = tile_y * p.TH * p.in_stride, ox0 = tile_x * p.TW * p.in_stride;
         const int wrow0 = g * p.T;
@@ -221,7 +222,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               slot = smem_aligned + (size_t)s * stage_bytes;
             }
             tma_load_4d(&map_x, &full_bar[s], slot, kb * p.KB, ix, iy, n_img);
-            tma_load_3d(&map_w, &full_bar[s], slot + a_bytes, kb * p.KB, 0, wrow0 + t);
+            tma_load_3d(&map_w, &full_bar[s], slot + a_bytes, kb * p.KB, wcol0, wrow0 + t);
             slot += sub_bytes;
             if (++u == n_in) {
               u = 0; remaining -= n_in;
@@ -272,13 +273,14 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int ty = r / p.TW, tx = r - ty * p.TW;
     // BN <= 32: BatchNorm partial sums stay in registers across ALL tiles of this CTA (one cross-lane
     // reduction at the end) instead of 2 x 16 x 5 shuffles per tile
-    const bool reg_stats = p.stats && p.BN <= 32;
+    const bool reg_stats = p.stats && p.BN <= 32 && p.CB == 1;
     float ra1[16], ra2[16], rb1[16], rb2[16];
 #pragma unroll
     for (int jj = 0; jj < 16; ++jj) ra1[jj] = ra2[jj] = rb1[jj] = rb2[jj] = 0.f;
     int j = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
-      const int tile = w % tiles, n_img = (w / tiles) % p.N, g = w / (tiles * p.N);
+      const int tile = w % tiles, n_img = (w / tiles) % p.N, gc = w / (tiles * p.N);
+      const int g = gc % p.G, cbase = (gc / p.G) * p.BN;     // first output channel of this work item's block
       const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
       const int oy = tile_y * p.TH + ty, ox = tile_x * p.TW + tx;
       const bool valid = (oy < p.Hg) && (ox < p.Wg);
@@ -288,24 +290,26 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       mbar_wait(&accum_full[as], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(as * p.BN) + ((uint32_t)(q * 32) << 16);
-      const float* pbias = p.plane_bias ? p.plane_bias + (size_t)n_img * p.Co : nullptr;
+      const float* pbias = p.plane_bias ? p.plane_bias + (size_t)n_img * p.Co + cbase : nullptr;
+      const float* cbias = p.chan_bias ? p.chan_bias + cbase : nullptr;
       const float* smap = nullptr;
       if (p.shared_map && valid)
-        smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
+        smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co + cbase;
+      const int co_left = p.Co - cbase;                      // real channels in this block (may be < BN: padding)
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_acc + (uint32_t)c0, v);
-        if (c0 >= p.Co) continue;
+        if (c0 >= co_left) continue;
         float f[16];
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(v[jj]);
-        if (p.chan_bias) {
+        if (cbias) {
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) if (c0 + jj < p.Co) f[jj] += p.chan_bias[c0 + jj];
+          for (int jj = 0; jj < 16; ++jj) if (c0 + jj < co_left) f[jj] += cbias[c0 + jj];
         }
         if (pbias) {
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) if (c0 + jj < p.Co) f[jj] += pbias[c0 + jj];
+          for (int jj = 0; jj < 16; ++jj) if (c0 + jj < co_left) f[jj] += pbias[c0 + jj];
         }
         if (smap) {
 #pragma unroll
@@ -338,7 +342,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             reinterpret_cast<float4*>(p.out)[out_pix] = o;
             if (p.raw_out) reinterpret_cast<int8_t*>(p.raw_out)[out_pix] = f[3] >= 0.f ? (int8_t)1 : (int8_t)-1;
           } else if (p.out_fp32) {
-            float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + c0;
+            float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + cbase + c0;
 #pragma unroll
             for (int jj = 0; jj < 16; jj += 4) {
               float4 o = make_float4(f[jj], f[jj + 1], f[jj + 2], f[jj + 3]);
@@ -346,7 +350,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               *reinterpret_cast<float4*>(dst + jj) = o;
             }
           } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + c0;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + cbase + c0;
             if (p.accumulate) {
               const uint4 e0 = *reinterpret_cast<const uint4*>(dst), e1 = *reinterpret_cast<const uint4*>(dst + 8);
               const __nv_bfloat16* eb0 = reinterpret_cast<const __nv_bfloat16*>(&e0);
@@ -372,6 +376,19 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&accum_empty[as]);
+      if (p.stats && p.CB > 1) {
+        // consecutive work items of this CTA may belong to different channel blocks: publish and clear the
+        // per-CTA partial sums after every tile (CB == 1 keeps them in shared memory until the end)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = threadIdx.x - 64; c < p.BN; c += 128) {
+          if (c < co_left) {
+            atomicAdd(p.stats + cbase + c, s_stats[0][c]);
+            atomicAdd(p.stats + p.Co + cbase + c, s_stats[1][c]);
+          }
+          s_stats[0][c] = 0.f; s_stats[1][c] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
     }
     if (reg_stats) {
 #pragma unroll
@@ -384,7 +401,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
       }
     }
-    if (p.stats) {
+    if (p.stats && p.CB == 1) {
       asm volatile("bar.sync 1, 128;" ::: "memory");         // epilogue warps only
       const int e = threadIdx.x - 64;                        // 0..127
       for (int c = e; c < p.Co; c += 128) {
@@ -461,7 +478,7 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
           tma_load_4d(&map_dy, &full_bar[s], a_dst + sl * a_slab, (mb * p.a_slabs + sl) * p.a_cb, dy_x, dy_y, n_img);
         for (int t = 0; t < ntaps; ++t) {
           uint8_t* b_dst = a_dst + a_bytes + (size_t)t * b_tap_bytes;
-          const int iy = oy0 + p.tap_y[g][t0 + t], ix = ox0 + p.tap_x[g][t0 + t];
+          const int iy = oy0 * p.x_stride + p.tap_y[g][t0 + t], ix = ox0 * p.x_stride + p.tap_x[g][t0 + t];
           for (int sl = 0; sl < p.b_slabs; ++sl)
             tma_load_4d(&map_x, &full_bar[s], b_dst + sl * b_slab, (nb * p.b_slabs + sl) * p.b_cb, ix, iy, n_img);
         }
@@ -655,6 +672,8 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   if (p.Ci % p.KB) return "Ci must be a multiple of KB";
   if (p.BN % 16 || p.BN < 16 || p.BN > 256) return "BN must be a multiple of 16 in [16,256]";
   if (p.T > 16 || p.G > 4) return "too many taps/groups";
+  if (p.CB < 1) p.CB = 1;
+  if (p.CB > 1 && (p.Co != p.CB * p.BN || p.act != 0)) return "channel blocks must tile Co exactly (and no head epilogue)";
   p.kblocks = p.Ci / p.KB;
   p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
   p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
@@ -688,7 +707,7 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   CUtensorMap mx, mw;
   const char* e = nhwc_map(&mx, L.x, p.Ci, L.Wi, L.Hi, p.N, p.KB, p.TW, p.TH, p.in_stride);
   if (e) return e;
-  e = weight_map(&mw, L.w, p.Ci, p.BN, p.G * p.T, p.KB, p.BN);
+  e = weight_map(&mw, L.w, p.Ci, L.w_rows, p.G * p.T, p.KB, p.BN);
   if (e) return e;
   static bool attr_set = false;
   if (!attr_set) {
@@ -697,7 +716,7 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   }
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int total_work = p.tiles_x * p.tiles_y * p.N * p.G;
+  const int total_work = p.tiles_x * p.tiles_y * p.N * p.G * p.CB;
   int grid_x = num_sms * ctas_per_sm;
   if (grid_x > total_work) grid_x = total_work;
   conv_taps_kernel<<<grid_x, kConvThreads, smem, stream>>>(mx, mw, p);
@@ -740,7 +759,9 @@ const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
   CUtensorMap mdy, mx;
   const char* e = nhwc_map(&mdy, L.dy, p.Co, L.dyW, L.dyH, p.N, p.a_cb, p.TW, p.TH, p.dy_stride);
   if (e) return e;
-  e = nhwc_map(&mx, L.x, p.Ci, L.xW, L.xH, p.N, p.b_cb, p.TW, p.TH, 1);
+  if (p.x_stride < 1) p.x_stride = 1;
+  if (p.TW * p.x_stride > 256 || p.TH * p.x_stride > 256) return "strided wgrad tile exceeds the TMA box limit";
+  e = nhwc_map(&mx, L.x, p.Ci, L.xW, L.xH, p.N, p.b_cb, p.TW, p.TH, p.x_stride);
   if (e) return e;
   static bool attr_set = false;
   if (!attr_set) {

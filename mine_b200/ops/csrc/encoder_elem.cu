@@ -1,0 +1,200 @@
+// Memory-bound companions of the conv engine for the ResNet encoder (NHWC bf16, 16-byte vectors = 8 channels,
+// C a power of two in [16, 2048]).  Same structure as decoder_elem.cu without the padded-buffer bookkeeping:
+//
+//   bn_res_act_fwd        : out = [relu](BN(y) [+ residual]) from the conv epilogue's batch sums - replaces ATen
+//                           batch_norm_elemt + add + relu (three passes) with one read of y (+ residual), one write.
+//   bn_res_act_bwd_reduce : g = dout * [out > 0] (also the gradient of the residual branch) and the two BatchNorm
+//                           backward sums per channel; the apply step is bn_bwd_apply of decoder_elem.cu.
+//   channel_stats         : per-channel sum / sum of squares for a tensor produced outside the engine (stem conv).
+//
+// Every thread keeps one 8-channel group for its whole grid-stride loop (the stride is a multiple of C/8), so
+// per-channel coefficients and partial sums live in registers; block partials are combined in shared memory and
+// published with one atomic per channel per block.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace mine {
+
+namespace {
+
+struct V8 {
+  float f[8];
+};
+__device__ __forceinline__ V8 ld8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  V8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    r.f[2 * i] = t.x; r.f[2 * i + 1] = t.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const V8& v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v.f[2 * i], v.f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// grid-stride over `total` 8-channel vectors with a stride that preserves (index mod cg)
+struct Walk {
+  unsigned i0, stride, total;
+  int c0;
+  bool active;
+};
+__device__ __forceinline__ Walk make_walk(unsigned total, int C) {
+  const int cg = C >> 3;
+  const int cg_shift = 31 - __clz(cg);
+  Walk w;
+  w.total = total;
+  w.stride = ((gridDim.x * blockDim.x) >> cg_shift) << cg_shift;
+  w.i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  w.active = w.i0 < w.stride;
+  w.c0 = (int)(w.i0 & (unsigned)(cg - 1)) * 8;
+  return w;
+}
+
+__global__ void __launch_bounds__(256) bn_res_act_fwd_kernel(
+    const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out,
+    unsigned total, int C, int relu, float inv_count, float eps) {
+  const Walk w = make_walk(total, C);
+  if (!w.active) return;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m = stats[w.c0 + j] * inv_count;
+    float var = stats[C + w.c0 + j] * inv_count - m * m;
+    var = var < 0.f ? 0.f : var;
+    a[j] = gamma[w.c0 + j] * rsqrtf(var + eps);
+    b[j] = beta[w.c0 + j] - m * a[j];
+  }
+  for (unsigned i = w.i0; i < w.total; i += w.stride) {
+    const size_t o = (size_t)i * 8;
+    V8 v = ld8(y + o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.f[j] = v.f[j] * a[j] + b[j];
+    if (res) {
+      const V8 r = ld8(res + o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.f[j] += r.f[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.f[j] = v.f[j] > 0.f ? v.f[j] : 0.f;
+    }
+    st8(out + o, v);
+  }
+}
+
+// publishes acc1/acc2 (8 channels starting at c0) through a [2][C] shared buffer
+__device__ __forceinline__ void publish_sums(float* s_sum, float* __restrict__ sums, int C, int c0, bool active,
+                                             const float* acc1, const float* acc2) {
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[c0 + j], acc1[j]); atomicAdd(&s_sum[C + c0 + j], acc2[j]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const float v = s_sum[i];
+    if (v != 0.f) atomicAdd(&sums[i], v);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_res_act_bwd_reduce_kernel(
+    const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ y,
+    const float* __restrict__ stats, __nv_bfloat16* __restrict__ g_out, float* __restrict__ sums, unsigned total, int C,
+    int relu, float inv_count, float eps) {
+  extern __shared__ float s_sum[];       // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
+  __syncthreads();
+  const Walk w = make_walk(total, C);
+  float mean[8], invstd[8], acc1[8], acc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m = stats[w.c0 + j] * inv_count;
+    float var = stats[C + w.c0 + j] * inv_count - m * m;
+    var = var < 0.f ? 0.f : var;
+    mean[j] = m; invstd[j] = rsqrtf(var + eps);
+    acc1[j] = acc2[j] = 0.f;
+  }
+  if (w.active) {
+    for (unsigned i = w.i0; i < w.total; i += w.stride) {
+      const size_t o = (size_t)i * 8;
+      V8 g = ld8(dout + o);
+      if (relu) {
+        const V8 a = ld8(out + o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.f[j] = a.f[j] > 0.f ? g.f[j] : 0.f;
+      }
+      const V8 yv = ld8(y + o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc1[j] += g.f[j];
+        acc2[j] += g.f[j] * (yv.f[j] - mean[j]) * invstd[j];
+      }
+      st8(g_out + o, g);
+    }
+  }
+  publish_sums(s_sum, sums, C, w.c0, w.active, acc1, acc2);
+}
+
+__global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ sums,
+                                                            unsigned total, int C) {
+  extern __shared__ float s_sum[];       // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
+  __syncthreads();
+  const Walk w = make_walk(total, C);
+  float acc1[8], acc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc1[j] = acc2[j] = 0.f;
+  if (w.active) {
+    for (unsigned i = w.i0; i < w.total; i += w.stride) {
+      const V8 v = ld8(y + (size_t)i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc1[j] += v.f[j]; acc2[j] += v.f[j] * v.f[j]; }
+    }
+  }
+  publish_sums(s_sum, sums, C, w.c0, w.active, acc1, acc2);
+}
+
+int blocks_for(size_t total, int C, int cap) {
+  size_t b = (total + 255) / 256;
+  if (b > (size_t)cap) b = cap;
+  const size_t min_blocks = ((size_t)(C / 8) + 255) / 256;       // the stride must cover one full channel period
+  if (b < min_blocks) b = min_blocks;
+  return (int)(b == 0 ? 1 : b);
+}
+
+}  // namespace
+
+void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
+                           void* out, size_t npix, int C, int relu, float inv_count, float eps, cudaStream_t stream) {
+  const size_t total = npix * (size_t)(C / 8);
+  bn_res_act_fwd_kernel<<<blocks_for(total, C, 148 * 16), 256, 0, stream>>>(
+      (const __nv_bfloat16*)y, stats, gamma, beta, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (unsigned)total, C,
+      relu, inv_count, eps);
+}
+
+void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void* y, const float* stats, void* g_out,
+                                  float* sums, size_t npix, int C, int relu, float inv_count, float eps,
+                                  cudaStream_t stream) {
+  const size_t total = npix * (size_t)(C / 8);
+  bn_res_act_bwd_reduce_kernel<<<blocks_for(total, C, 148 * 8), 256, 2 * C * sizeof(float), stream>>>(
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)y, stats, (__nv_bfloat16*)g_out, sums,
+      (unsigned)total, C, relu, inv_count, eps);
+}
+
+void launch_channel_stats(const void* y, float* sums, size_t npix, int C, cudaStream_t stream) {
+  const size_t total = npix * (size_t)(C / 8);
+  channel_stats_kernel<<<blocks_for(total, C, 148 * 8), 256, 2 * C * sizeof(float), stream>>>(
+      (const __nv_bfloat16*)y, sums, (unsigned)total, C);
+}
+
+}  // namespace mine

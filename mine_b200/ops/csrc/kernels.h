@@ -58,6 +58,16 @@ void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, v
 }  // namespace mine
 
 namespace mine {
+// ---- encoder_elem.cu (unpadded NHWC bf16, C a power of two in [16, 2048]) -------------------------------
+void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
+                           void* out, size_t npix, int C, int relu, float inv_count, float eps, cudaStream_t stream);
+void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void* y, const float* stats, void* g_out,
+                                  float* sums, size_t npix, int C, int relu, float inv_count, float eps,
+                                  cudaStream_t stream);
+void launch_channel_stats(const void* y, float* sums, size_t npix, int C, cudaStream_t stream);
+}  // namespace mine
+
+namespace mine {
 // ---- comm.cu (NVLink peer memory) -----------------------------------------------------------------
 struct PeerTable { void* ptr[16]; };
 // epoch counters are device-resident (advanced by the kernels): CUDA-graph replay safe
