@@ -8,7 +8,7 @@ step i computes; the consumer only waits on an event.
 from __future__ import annotations
 
 import math
-from typing import Dict, Iterable, Iterator, Optional, Tuple
+from typing import Iterable
 
 import torch
 import torch.utils.data as data

@@ -9,7 +9,7 @@ have positive depth in both cameras and project inside both images.
 from __future__ import annotations
 
 import math
-from typing import Dict, Iterator, Optional, Tuple
+from typing import Dict, Tuple
 
 import numpy as np
 import torch

@@ -21,7 +21,7 @@ Resolution: upsamples are size-matched to their skip tensors, so any H, W multip
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import torch
 import torch.nn as nn

@@ -13,7 +13,7 @@ mean/std normalisation inside ``forward`` and the outputs ``conv1 (64,H/2)``, ``
 """
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import Tuple
 
 import torch
 import torch.nn as nn

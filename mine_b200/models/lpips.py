@@ -14,7 +14,6 @@ from typing import Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 _VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
 _TAPS = (3, 8, 15, 22, 29)        # relu1_2, relu2_2, relu3_3, relu4_3, relu5_3 in vgg16.features indexing

@@ -15,8 +15,6 @@ explicitly (tests) - on a GPU the real extension is used or an error is raised.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
-
 import torch
 import torch.nn.functional as F
 

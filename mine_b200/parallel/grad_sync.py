@@ -16,7 +16,7 @@ the side stream before the optimizer runs.
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence
+from typing import List, Sequence
 
 import torch
 

@@ -8,7 +8,6 @@ two-shot in-place mean for gradient buckets, optional NVSwitch multicast ``multi
 from __future__ import annotations
 
 import os
-from typing import Optional
 
 import torch
 import torch.distributed as dist

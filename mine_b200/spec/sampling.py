@@ -5,7 +5,7 @@ Semantics: SURVEY 2.7 "Disparity sampling"; reference ``operations/rendering_uti
 """
 from __future__ import annotations
 
-from typing import Mapping, Optional, Sequence
+from typing import Mapping, Optional
 
 import numpy as np
 import torch

@@ -19,10 +19,9 @@ from __future__ import annotations
 import glob
 import itertools
 import os
-from typing import Dict, List, Mapping, Optional, Tuple
+from typing import Dict, List, Mapping, Optional
 
 import torch
-import torch.nn as nn
 
 from . import geometry as geo
 from .config import get as cfg_get

@@ -1,5 +1,5 @@
 """Kernel-level time table of one eager training step (CUPTI via torch.profiler; not a bench value)."""
-import sys, json, collections, re, torch
+import sys, collections, re, torch
 sys.path.insert(0, '.')
 from mine_b200 import config as C
 from mine_b200.data.synthetic import config_batch

@@ -8,7 +8,6 @@ it skip when it is absent; nothing from it is ever copied into the package.
 import importlib
 import os
 import sys
-import types
 
 import pytest
 import torch

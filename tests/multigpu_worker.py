@@ -11,7 +11,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     from mine_b200.parallel import bootstrap
-    from mine_b200.parallel.comm import TorchDistComm
     from mine_b200.parallel.p2p import P2PComm
     ctx = bootstrap.init_distributed()
     dev, rank, world = ctx.device, ctx.rank, ctx.world_size

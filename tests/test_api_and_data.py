@@ -1,6 +1,4 @@
 """Public API surface, config system, data pipeline, checkpoint/resume (CPU)."""
-import copy
-import json
 import os
 
 import numpy as np

@@ -213,7 +213,6 @@ def test_kernels_match_emulator_contract():
     """Same arguments through the sm_100a kernels and through the PyTorch specification (``ops/emu.py``) that the
     CPU tier uses to test the engine's orchestration: fprop with every epilogue term, strided phase dgrad, wgrad."""
     from mine_b200.ops import conv_engine as E
-    from mine_b200.ops import emu
     n, h, w, ci, co = 4, 12, 20, 32, 64
     xlo = _bf(_rand((n, h + 2, w + 2, ci), 0)).to(torch.bfloat16)
     wt = _bf(_rand((co, ci, 3, 3), 1, 0.1))

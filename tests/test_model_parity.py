@@ -1,6 +1,4 @@
 """Model parity vs upstream modules with shared random weights + checkpoint round trips."""
-import copy
-import io
 
 import pytest
 import torch
