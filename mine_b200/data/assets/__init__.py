@@ -49,3 +49,50 @@ def flowers_lightfield() -> Dict:
     return {"view_id": [str(v) for v in z["view_id"]], "intrinsics": z["intrinsics"], "distortion": z["distortion"],
             "pose": z["pose"],
             "train": [str(v) for v in z["train"]], "test": [str(v) for v in z["test"]]}
+
+
+def export_upstream_layout(dst_root: str) -> List[str]:
+    """Write the tables in the directory layout and text formats the reference keeps them in
+    (``input_pipelines/realestate10k/test_data_jsons/{test,validation}_pairs.json`` JSON lines,
+    ``input_pipelines/flowers/cam_params.txt``, ``input_pipelines/flowers/dataset_list/{train,test}.list``), for
+    tools written against those files.  Returns the paths written."""
+    import json
+    written = []
+    d = os.path.join(dst_root, "realestate10k", "test_data_jsons")
+    os.makedirs(d, exist_ok=True)
+    keys = {"src": "src_img_obj", "tgt_5_frames": "tgt_img_obj_5_frames", "tgt_10_frames": "tgt_img_obj_10_frames",
+            "tgt_random": "tgt_img_obj_random"}
+    for split in ("test", "validation"):
+        path = os.path.join(d, f"{split}_pairs.json")
+        with open(path, "w") as f:
+            for item in realestate10k_pairs(split):
+                row = {"sequence_id": item["sequence_id"]}
+                for ours, theirs in keys.items():
+                    v = item[ours]
+                    row[theirs] = {"sequence_id": item["sequence_id"],
+                                   "camera_intrinsics": [round(float(x), 9) for x in v["intrinsics"]],
+                                   "camera_pose": [round(float(x), 9) for x in np.asarray(v["pose"]).reshape(-1)],
+                                   "frame_ts": str(v["frame_ts"])}
+                f.write(json.dumps(row) + "\n")
+        written.append(path)
+    lf = flowers_lightfield()
+    d = os.path.join(dst_root, "flowers")
+    os.makedirs(os.path.join(d, "dataset_list"), exist_ok=True)
+    path = os.path.join(d, "cam_params.txt")
+    with open(path, "w") as f:
+        for vid, intr, dist, pose in zip(lf["view_id"], lf["intrinsics"], lf["distortion"], lf["pose"]):
+            vals = [float(x) for x in intr] + [float(x) for x in dist] + [float(x) for x in np.asarray(pose).reshape(-1)]
+            f.write(vid + " " + " ".join("%.6f" % x for x in vals) + "\n")
+    written.append(path)
+    for split in ("train", "test"):
+        path = os.path.join(d, "dataset_list", f"{split}.list")
+        with open(path, "w") as f:
+            f.write("\n".join(lf[split]) + "\n")
+        written.append(path)
+    return written
+
+
+if __name__ == "__main__":
+    import sys
+    for p in export_upstream_layout(sys.argv[1] if len(sys.argv) > 1 else "input_pipelines"):
+        print(p)

@@ -212,6 +212,27 @@ def test_static_assets():
     assert len(f["view_id"]) == 64 and len(f["train"]) == 3243 and len(f["test"]) == 100
 
 
+def test_static_assets_export_to_upstream_layout(tmp_path):
+    """The npz tables regenerate the files the reference ships value for value."""
+    import json
+    from mine_b200.data import assets as A
+    written = A.export_upstream_layout(str(tmp_path))
+    assert len(written) == 5
+    rows = [json.loads(l) for l in open(tmp_path / "realestate10k" / "test_data_jsons" / "validation_pairs.json")]
+    assert len(rows) == 250 and set(rows[0]) == {"sequence_id", "src_img_obj", "tgt_img_obj_5_frames",
+                                                 "tgt_img_obj_10_frames", "tgt_img_obj_random"}
+    assert len(rows[0]["src_img_obj"]["camera_pose"]) == 12 and len(rows[0]["src_img_obj"]["camera_intrinsics"]) == 4
+    ref = os.path.join(REF_ROOT, "input_pipelines")
+    if os.path.isdir(ref):
+        theirs = [json.loads(l) for l in open(os.path.join(ref, "realestate10k", "test_data_jsons", "validation_pairs.json"))]
+        for a, b in zip(rows, theirs):
+            assert a["sequence_id"] == b["sequence_id"] and str(b["tgt_img_obj_random"]["frame_ts"]) == a["tgt_img_obj_random"]["frame_ts"]
+            assert np.allclose(a["tgt_img_obj_10_frames"]["camera_pose"], b["tgt_img_obj_10_frames"]["camera_pose"], atol=1e-6)
+        ours = np.array([[float(v) for v in l.split()[1:]] for l in open(tmp_path / "flowers" / "cam_params.txt")])
+        ref_tab = np.array([[float(v) for v in l.split()[1:]] for l in open(os.path.join(ref, "flowers", "cam_params.txt"))])
+        assert ours.shape == (64, 18) and np.allclose(ours, ref_tab, atol=1e-6)
+
+
 def test_video_generator_cpu(tmp_path):
     import cv2
     from visualizations.image_to_video import VideoGenerator, path_planning
