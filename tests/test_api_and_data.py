@@ -222,7 +222,7 @@ def test_static_assets_export_to_upstream_layout(tmp_path):
     assert len(rows) == 250 and set(rows[0]) == {"sequence_id", "src_img_obj", "tgt_img_obj_5_frames",
                                                  "tgt_img_obj_10_frames", "tgt_img_obj_random"}
     assert len(rows[0]["src_img_obj"]["camera_pose"]) == 12 and len(rows[0]["src_img_obj"]["camera_intrinsics"]) == 4
-    ref = os.path.join(REF_ROOT, "input_pipelines")
+    ref = "/root/reference/input_pipelines"      # the data tables exist in the source tree only
     if os.path.isdir(ref):
         theirs = [json.loads(l) for l in open(os.path.join(ref, "realestate10k", "test_data_jsons", "validation_pairs.json"))]
         for a, b in zip(rows, theirs):
