@@ -335,14 +335,15 @@ class ConvEngine:
 
     def __init__(self, backbone, decoder, config, device, encoder_mode: str | None = None):
         self.backbone, self.decoder, self.config, self.device = backbone, decoder, config, device
-        # encoder: "cudnn" (library convolutions under bf16 autocast) or "tcgen05" (encoder_engine.py)
+        # encoder: "cudnn" (library convolutions + ATen BN under bf16 autocast), "hybrid" (library convolutions +
+        # our fused BN kernels) or "tcgen05" (everything on the engine, encoder_engine.py)
         self.encoder_mode = encoder_mode or os.environ.get("MINE_B200_ENCODER", "cudnn")
-        if self.encoder_mode not in ("cudnn", "tcgen05"):
-            raise ValueError("MINE_B200_ENCODER must be cudnn or tcgen05, got %r" % self.encoder_mode)
+        if self.encoder_mode not in ("cudnn", "tcgen05", "hybrid"):
+            raise ValueError("MINE_B200_ENCODER must be cudnn, hybrid or tcgen05, got %r" % self.encoder_mode)
         self.encoder_engine = None
-        if self.encoder_mode == "tcgen05":
+        if self.encoder_mode != "cudnn":
             from .encoder_engine import EncoderEngine
-            self.encoder_engine = EncoderEngine(backbone)
+            self.encoder_engine = EncoderEngine(backbone, library_conv=self.encoder_mode == "hybrid")
 
     def _reducer(self):
         from ..models.norm import BatchNorm
@@ -357,7 +358,7 @@ class ConvEngine:
         n = b * s
         amp = dict(device_type=src_imgs.device.type, dtype=torch.bfloat16,
                    enabled=src_imgs.is_cuda and ACT_DTYPE == torch.bfloat16)
-        if self.encoder_mode == "tcgen05":
+        if self.encoder_engine is not None:
             feats = self.encoder_engine(src_imgs)
         else:
             with torch.autocast(**amp):

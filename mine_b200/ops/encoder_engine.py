@@ -17,7 +17,10 @@ encoder FLOPs) and the max-pool stay on library kernels.
 
 Reference semantics: ``network/monodepth2/resnet_encoder.py:88-108`` (torchvision ResNet trunk, five outputs).
 Status: validated against the ``nn.Module`` encoder through the kernel specification (``ops/emu.py``,
-``tests/test_engine_emulated.py``); selected with ``MINE_B200_ENCODER=tcgen05`` (default: library convolutions).
+``tests/test_engine_emulated.py``) and on B200 (``tests/test_encoder_engine_gpu.py``); selected with
+``MINE_B200_ENCODER=tcgen05``.  ``MINE_B200_ENCODER=hybrid`` keeps the library's implicit GEMMs for the convolutions
+(they are small and latency bound) and uses only the fused BatchNorm / residual / ReLU kernels of this path.
+Default: ``cudnn`` (library convolutions and ATen BatchNorm under autocast).
 """
 from __future__ import annotations
 
@@ -216,9 +219,42 @@ class BNAct(torch.autograd.Function):
         return dy, None, dgamma.to(g32.dtype), dbeta.to(b32.dtype), (g if has_res else None), None, None, None
 
 
-def conv_bn_act(x, conv, bn, relu=True, residual=None, reducer=None):
+class ConvLib(torch.autograd.Function):
+    """Library convolution on the engine's NHWC operand layout (``hybrid`` mode: cuDNN implicit GEMMs for the small
+    encoder layers, this package's fused BatchNorm / residual / ReLU kernels around them).  The NHWC tensor is
+    handed over as a channels-last NCHW view, so no copies are made in either direction."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride):
+        k = w.shape[2]
+        w_op = w.detach().to(E.ACT_DTYPE)                               # keeps the (channels-last) weight strides
+        y = torch.ops.aten.convolution(x.permute(0, 3, 1, 2), w_op, None, [stride, stride], [k // 2, k // 2], [1, 1],
+                                       False, [0, 0], 1)
+        _count(2)
+        ctx.save_for_backward(x, w_op)
+        ctx.stride = int(stride)
+        return y.permute(0, 2, 3, 1).contiguous()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_op = ctx.saved_tensors
+        k, s = w_op.shape[2], ctx.stride
+        dx, dw, _ = torch.ops.aten.convolution_backward(
+            dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w_op, None, [s, s], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
+            [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]), False])
+        _count(2)
+        if dx is not None:
+            dx = dx.permute(0, 2, 3, 1).contiguous()
+        return dx, (dw.float() if dw is not None else None), None
+
+
+def conv_bn_act(x, conv, bn, relu=True, residual=None, reducer=None, library_conv=False):
     stride = conv.stride[0]
-    y, stats = Conv.apply(x, conv.weight, stride, bn.training)
+    if library_conv:
+        y = ConvLib.apply(x, conv.weight, stride)
+        stats = torch.empty(0, device=x.device)                         # BNAct computes them (channel_stats kernel)
+    else:
+        y, stats = Conv.apply(x, conv.weight, stride, bn.training)
     return BNAct.apply(y, stats, bn.weight, bn.bias, residual, relu, bn, reducer)
 
 
@@ -229,23 +265,25 @@ class EncoderEngine:
     """Runs a :class:`mine_b200.models.encoder.ResnetEncoder` (any depth) on the engine; returns the five NCHW
     (channels-last strided) feature maps ``ResnetEncoder.forward`` returns."""
 
-    def __init__(self, backbone):
+    def __init__(self, backbone, library_conv: bool = False):
         self.backbone = backbone
+        self.library_conv = bool(library_conv)       # "hybrid": library convolutions + our fused BN kernels
 
     def _reducer(self):
         return self.backbone.encoder.bn1.reducer
 
     def _block(self, blk, x, reducer):
+        kw = dict(reducer=reducer, library_conv=self.library_conv)
         if blk.downsample is not None:
-            idt = conv_bn_act(x, blk.downsample[0], blk.downsample[1], relu=False, reducer=reducer)
+            idt = conv_bn_act(x, blk.downsample[0], blk.downsample[1], relu=False, **kw)
         else:
             idt = x
         if hasattr(blk, "conv3"):                                   # bottleneck
-            out = conv_bn_act(x, blk.conv1, blk.bn1, reducer=reducer)
-            out = conv_bn_act(out, blk.conv2, blk.bn2, reducer=reducer)
-            return conv_bn_act(out, blk.conv3, blk.bn3, relu=True, residual=idt, reducer=reducer)
-        out = conv_bn_act(x, blk.conv1, blk.bn1, reducer=reducer)
-        return conv_bn_act(out, blk.conv2, blk.bn2, relu=True, residual=idt, reducer=reducer)
+            out = conv_bn_act(x, blk.conv1, blk.bn1, **kw)
+            out = conv_bn_act(out, blk.conv2, blk.bn2, **kw)
+            return conv_bn_act(out, blk.conv3, blk.bn3, relu=True, residual=idt, **kw)
+        out = conv_bn_act(x, blk.conv1, blk.bn1, **kw)
+        return conv_bn_act(out, blk.conv2, blk.bn2, relu=True, residual=idt, **kw)
 
     def __call__(self, img: torch.Tensor):
         bb, e = self.backbone, self.backbone.encoder

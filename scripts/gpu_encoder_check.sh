@@ -23,3 +23,11 @@ try:
 except Exception as e:
     print("encoder-engine no result", e); print(open("gpurun_out/bench_enc.err").read()[-1500:])
 PY
+MINE_B200_ENCODER=hybrid timeout 100 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_hybrid.json 2> gpurun_out/bench_hybrid.err; echo "bench hybrid rc=$?"
+python - <<'PY'
+import json
+try:
+    d = json.loads(open("gpurun_out/bench_hybrid.json").read().strip().splitlines()[-1]); print("hybrid", d["value"], d["ms_per_step"], d["gpu_launches"])
+except Exception as e:
+    print("hybrid no result", e); print(open("gpurun_out/bench_hybrid.err").read()[-1500:])
+PY

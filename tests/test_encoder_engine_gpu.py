@@ -80,15 +80,17 @@ def test_encoder_elementwise_match_specification(c, relu, res):
     assert _rel2(dy, dy2) < 5e-3
 
 
-def test_encoder_engine_matches_library_encoder():
-    """Whole ResNet-50 trunk on the engine vs the same module run by the library under bf16 autocast."""
+@pytest.mark.parametrize("library_conv", [False, True])
+def test_encoder_engine_matches_library_encoder(library_conv):
+    """Whole ResNet-50 trunk on the engine (or hybrid: library convolutions + our BN kernels) vs the same module
+    run by the library under bf16 autocast."""
     from mine_b200.models.encoder import ResnetEncoder
     from mine_b200.ops.encoder_engine import EncoderEngine
     torch.manual_seed(0)
     enc = ResnetEncoder(50, False).cuda()
     img = torch.rand(2, 3, 256, 384, device="cuda")
     state = {k: v.clone() for k, v in enc.state_dict().items()}
-    outs = EncoderEngine(enc)(img)
+    outs = EncoderEngine(enc, library_conv=library_conv)(img)
     gouts = [torch.randn_like(o.float()) for o in outs]
     sum((o.float() * g).sum() for o, g in zip(outs, gouts)).backward()
     got = {k: p.grad.clone() for k, p in enc.named_parameters()}

@@ -114,7 +114,7 @@ def test_fused_layer_autograd_matches_module_chain():
         assert torch.allclose(g, r, rtol=2e-3, atol=2e-4 * r.abs().max().item() + 1e-5), name
 
 
-@pytest.mark.parametrize("encoder_mode", ["cudnn", "tcgen05"])
+@pytest.mark.parametrize("encoder_mode", ["cudnn", "tcgen05", "hybrid"])
 def test_whole_decoder_on_emulated_engine_matches_modules(encoder_mode):
     from mine_b200.models.decoder import DepthDecoder
     from mine_b200.models.encoder import ResnetEncoder
@@ -168,8 +168,9 @@ def test_encoder_conv_directions(k, stride, h, w):
     assert torch.allclose(EE.conv_wgrad(_nhwc(dy), _nhwc(x.detach()), k, stride), wt.grad, rtol=1e-4, atol=1e-3)
 
 
-@pytest.mark.parametrize("layers,train", [(18, True), (50, True), (50, False)])
-def test_encoder_engine_matches_module(layers, train):
+@pytest.mark.parametrize("layers,train,lib", [(18, True, False), (50, True, False), (50, False, False), (18, True, True),
+                                              (50, True, True)])
+def test_encoder_engine_matches_module(layers, train, lib):
     from mine_b200.models.encoder import ResnetEncoder
     from mine_b200.ops.encoder_engine import EncoderEngine
     torch.manual_seed(0)
@@ -180,7 +181,7 @@ def test_encoder_engine_matches_module(layers, train):
     img = torch.rand(2, 3, 64, 96) if layers == 18 else torch.rand(2, 3, 128, 128)
     tol = 5e-3 if layers == 18 or not train else 5e-2
     state = {k: v.clone() for k, v in enc.state_dict().items()}
-    outs = EncoderEngine(enc)(img)
+    outs = EncoderEngine(enc, library_conv=lib)(img)
     gouts = [torch.randn_like(o) for o in outs]
     sum((o * g).sum() for o, g in zip(outs, gouts)).backward()
     got = {k: p.grad.clone() for k, p in enc.named_parameters()}
