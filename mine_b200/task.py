@@ -549,6 +549,13 @@ class SynthesisTask:
                 "loss_ssim_tgt", "loss_smooth_tgt", "loss_disp_pt3dtgt", "lpips_tgt", "psnr_tgt"]
         vals = torch.stack([loss_dict[k].detach().float().reshape(()) for k in keys]).cpu().tolist()   # one D2H
         v = dict(zip(keys, vals))
+        if not all(x == x and abs(x) != float("inf") for x in vals):
+            # failure detection the reference lacks: stop at the first logged non-finite loss instead of
+            # training on garbage; checkpoint_latest.pth still holds the last healthy state
+            bad = [k for k, x in v.items() if not (x == x and abs(x) != float("inf"))]
+            self.logger.info("non-finite training loss at global_step %d: %s" % (global_step, ", ".join(bad)))
+            raise FloatingPointError("non-finite loss terms at global_step %d: %s" % (global_step, ", ".join(bad)))
+        perf = self._throughput(global_step)
         self.logger.info(
             "epoch [%.3d] step [%d/%d] global_step = %d total_loss = %.4f encoder_lr = %.7f\n"
             "        src: rgb = %.4f\n        src: ssim = %.4f\n        src: smooth = %.4f\n"
@@ -557,7 +564,37 @@ class SynthesisTask:
             (epoch, step, dataset_length, global_step, v["loss"], self.optimizer.param_groups[0]["lr"],
              v["loss_rgb_src"], v["loss_ssim_src"], v["loss_smooth_src"], v["loss_disp_pt3dsrc"],
              v["loss_rgb_tgt"], v["loss_ssim_tgt"], v["loss_smooth_tgt"], v["loss_disp_pt3dtgt"]))
+        if perf:
+            self.logger.info("        perf: %.2f ms/step, %.1f images/s (this rank), peak memory %.2f GB" %
+                             (perf["ms_per_step"], perf["images_per_s"], perf["peak_mem_gb"]))
         for k, m in self.train_losses.items():
             if self.tb_writer is not None:
                 self.tb_writer.add_scalar(k + "/train", v[k], global_step)
             m.update(v[k])
+        if self.tb_writer is not None:
+            for k, x in perf.items():
+                self.tb_writer.add_scalar("perf/" + k, x, global_step)
+
+    def _throughput(self, global_step: int) -> Dict[str, float]:
+        """Step time since the previous log line (CUDA events on the compute stream - the log line's own D2H is
+        the only synchronisation), images/s of this rank and peak allocator memory (the reference
+        reports no throughput / latency / memory figures at all)."""
+        cuda = self.device.type == "cuda"
+        import time
+        now = torch.cuda.Event(enable_timing=True) if cuda else time.perf_counter()
+        if cuda:
+            now.record()
+        out: Dict[str, float] = {}
+        prev = getattr(self, "_perf_mark", None)
+        if prev is not None and global_step > prev[1]:
+            if cuda:
+                now.synchronize()
+                ms = prev[0].elapsed_time(now)
+            else:
+                ms = (now - prev[0]) * 1e3
+            steps = global_step - prev[1]
+            bsz = int(self.config["data.per_gpu_batch_size"])
+            out = {"ms_per_step": ms / steps, "images_per_s": bsz * steps / max(ms, 1e-9) * 1e3,
+                   "peak_mem_gb": torch.cuda.max_memory_allocated(self.device) / 2 ** 30 if cuda else 0.0}
+        self._perf_mark = (now, global_step)
+        return out

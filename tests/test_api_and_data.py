@@ -281,3 +281,25 @@ def test_rendering_demo_checks():
     demo.test_mpi_composition()
     demo.rotation_test()
     demo.test_homography_sample()
+
+
+def test_training_log_reports_throughput_and_stops_on_non_finite_loss():
+    import logging
+    task, cfg = _task()
+    records = []
+
+    class Grab(logging.Handler):
+        def emit(self, r):
+            records.append(r.getMessage())
+    log = logging.getLogger("mine_test_perf")
+    log.handlers, log.propagate = [Grab()], False
+    log.setLevel(logging.INFO)
+    task.logger = log
+    batch = config_batch(cfg)
+    for step in (1, 2):
+        task.log_training(1, step, task.global_step + 1, 10, task.train_step(batch))
+    assert any("perf:" in m and "images/s" in m for m in records)          # from the second log line on
+    ld = {k: v.clone() if torch.is_tensor(v) else torch.tensor(float(v)) for k, v in task.train_step(batch).items()}
+    ld["loss_ssim_tgt"] = torch.tensor(float("nan"))
+    with pytest.raises(FloatingPointError, match="loss_ssim_tgt"):
+        task.log_training(1, 3, 3, 10, ld)
