@@ -1,4 +1,6 @@
-"""The subset of monodepth2 layers MINE uses, re-expressed on our modules."""
+"""The subset of monodepth2 layers MINE uses, re-expressed on our modules (reference ``network/monodepth2/layers.py``:
+``ConvBlock`` :106-120, ``Conv3x3`` :123-138, ``upsample`` :198-201; the unused geometry utilities live in
+``mine_b200/models/geometry_layers.py``)."""
 import torch.nn as nn
 import torch.nn.functional as F
 
