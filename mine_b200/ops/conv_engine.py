@@ -294,6 +294,12 @@ class PlaneConvBNAct(torch.autograd.Function):
                 dbeta.to(b32.dtype), None, None, None, None, None)
 
 
+def head_mode() -> str:
+    """``MINE_B200_HEAD``: ``tcgen05`` (default: every head through conv_taps) or ``direct`` (CUDA-core kernel for the
+    16 / 32-channel heads; opt-in until measured on hardware)."""
+    return os.environ.get("MINE_B200_HEAD", "tcgen05")
+
+
 def ctx_world(reducer) -> int:
     return int(getattr(reducer, "world_size", None) or getattr(getattr(reducer, "__self__", None), "world_size", 1))
 
@@ -303,7 +309,14 @@ class HeadConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, apad, w, bias, use_alpha):
-        mpi, sign = conv_same_raw(apad, w, chan_bias=bias.detach().float().contiguous(), head=True, head_alpha=use_alpha)
+        if head_mode() == "direct" and apad.shape[3] in (16, 32):
+            # narrow full-resolution levels: bandwidth bound, CUDA-core kernel with one halo load (head_direct.cu)
+            wpk = w.detach().float().permute(2, 3, 1, 0).contiguous()                 # [ky, kx, ci, co] = [9, C, 4]
+            mpi, sign = ext().head_conv_direct(apad, wpk, bias.detach().float().contiguous(), bool(use_alpha))
+            _count(2)
+        else:
+            mpi, sign = conv_same_raw(apad, w, chan_bias=bias.detach().float().contiguous(), head=True,
+                                      head_alpha=use_alpha)
         ctx.save_for_backward(apad, w, mpi, sign)
         ctx.use_alpha = bool(use_alpha)
         return mpi

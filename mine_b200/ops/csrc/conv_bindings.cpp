@@ -184,6 +184,24 @@ std::vector<at::Tensor> head_bwd(const at::Tensor& g_mpi, const at::Tensor& mpi,
   return {dz, dbias};
 }
 
+std::vector<at::Tensor> head_conv_direct(const at::Tensor& apad, const at::Tensor& wpk, const at::Tensor& bias,
+                                         bool use_alpha) {
+  check_bf16_nhwc(apad, "apad");
+  const int64_t N = apad.size(0), H = apad.size(1) - 2, W = apad.size(2) - 2, C = apad.size(3);
+  TORCH_CHECK(C == 16 || C == 32, "head_conv_direct handles 16 or 32 input channels");
+  TORCH_CHECK(wpk.is_cuda() && wpk.scalar_type() == at::kFloat && wpk.is_contiguous() && wpk.numel() == 9 * C * 4,
+              "wpk must be contiguous fp32 [9, C, 4]");
+  TORCH_CHECK(bias.is_cuda() && bias.scalar_type() == at::kFloat && bias.is_contiguous() && bias.numel() == 4, "bias");
+  c10::cuda::CUDAGuard guard(apad.device());
+  at::Tensor mpi = at::empty({N, H, W, 4}, apad.options().dtype(at::kFloat));
+  at::Tensor sign = at::empty({N, H, W}, apad.options().dtype(at::kChar));
+  const char* err = mine::launch_head_conv_direct(apad.data_ptr(), wpk.data_ptr<float>(), bias.data_ptr<float>(),
+                                                  mpi.data_ptr<float>(), sign.data_ptr<int8_t>(), (int)N, (int)H, (int)W,
+                                                  (int)C, use_alpha ? 1 : 0, cur_stream());
+  TORCH_CHECK(err == nullptr, err ? err : "");
+  return {mpi, sign};
+}
+
 inline void check_channels(const at::Tensor& y) {
   const int64_t C = y.size(3);
   TORCH_CHECK((C & (C - 1)) == 0 && C >= 16 && C <= 2048, "channels must be a power of two in [16, 2048]");
@@ -247,4 +265,5 @@ void register_conv(pybind11::module_& m) {
   m.def("bn_res_act_fwd", &bn_res_act_fwd);
   m.def("bn_res_act_bwd_reduce", &bn_res_act_bwd_reduce);
   m.def("channel_stats", &channel_stats);
+  m.def("head_conv_direct", &head_conv_direct);
 }

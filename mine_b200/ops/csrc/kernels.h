@@ -58,6 +58,12 @@ void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, v
 }  // namespace mine
 
 namespace mine {
+// ---- head_direct.cu (CUDA-core MPI head for the 16 / 32-channel levels) ----------------------------------
+const char* launch_head_conv_direct(const void* apad, const float* wpk, const float* bias, float* mpi, int8_t* sign, int N,
+                                    int H, int W, int C, int use_alpha, cudaStream_t stream);
+}  // namespace mine
+
+namespace mine {
 // ---- encoder_elem.cu (unpadded NHWC bf16, C a power of two in [16, 2048]) -------------------------------
 void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
                            void* out, size_t npix, int C, int relu, float inv_count, float eps, cudaStream_t stream);

@@ -204,3 +204,19 @@ def channel_stats(y):
     """``[sum, sum of squares]`` per channel of an NHWC tensor (for convolutions that ran outside the engine)."""
     yf = y.float()
     return torch.stack([yf.sum(dim=(0, 1, 2)), (yf * yf).sum(dim=(0, 1, 2))])
+
+
+def head_conv_direct(apad, wpk, bias, use_alpha):
+    """MPI head on a pre-padded input: ``apad [N,H+2,W+2,C]``, ``wpk [9,C,4]`` (tap-major, output channel last),
+    returns the packed fp32 MPI ``[N,H,W,4]`` and the sign of the sigma pre-activation (``csrc/head_direct.cu``)."""
+    n, hp, wp_, c = apad.shape
+    h, w = hp - 2, wp_ - 2
+    xf, wf = apad.float(), wpk.float().reshape(9, c, 4)
+    z = bias.float().reshape(1, 1, 1, 4).expand(n, h, w, 4).clone()
+    for ky in range(3):
+        for kx in range(3):
+            z = z + xf[:, ky:ky + h, kx:kx + w] @ wf[ky * 3 + kx]
+    last = torch.sigmoid(z[..., 3:]) if use_alpha else z[..., 3:].abs() + 1e-4
+    mpi = torch.cat([torch.sigmoid(z[..., :3]), last], dim=-1).contiguous()
+    sign = torch.where(z[..., 3] >= 0, 1, -1).to(torch.int8)
+    return [mpi, sign]

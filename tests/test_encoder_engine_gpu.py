@@ -9,7 +9,7 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MINE_B200_TEST_ENCODER", "0") != "1",
+              pytest.mark.skipif(os.environ.get("MINE_B200_TEST_ENCODER", os.environ.get("MINE_B200_TEST_OPTIN", "0")) != "1",
                                  reason="encoder-on-engine path is opt-in (MINE_B200_TEST_ENCODER=1)")]
 
 

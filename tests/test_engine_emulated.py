@@ -81,7 +81,13 @@ def test_upsample_conv_all_directions(n, h, w, ci, co):
     assert torch.allclose(E.pack(wt, 1)[:, :co].reshape(4, 4, co, ci), E.pack_up(wt.detach()), atol=1e-6)
 
 
-def test_fused_layer_autograd_matches_module_chain():
+@pytest.mark.parametrize("head", ["tcgen05", "direct"])
+def test_fused_layer_autograd_matches_module_chain(head, monkeypatch):
+    monkeypatch.setenv("MINE_B200_HEAD", head)
+    _fused_layer_check()
+
+
+def _fused_layer_check():
     """PlaneConvBNAct (conv + shared skip + plane bias -> BN -> ELU -> pad) and HeadConv against torch autograd."""
     b, s, h, w, ci, co = 2, 3, 6, 8, 32, 16
     n = b * s
