@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -177,6 +178,84 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], s_sum[i]);
 }
 
+// Variant 2 of the reduction above (MINE_B200_BN_REDUCE=v2, opt-in until measured): the per-channel affine (a, b)
+// lives in 16 registers like in the forward kernel instead of four shared-memory arrays (32 LDS per 8 elements made
+// v1 issue bound at 0.23 of HBM peak), and the second sum is accumulated as sum(g * y); every thread converts its
+// partial to sum(g * xhat) = invstd * (sum(g*y) - mean * sum(g)) once, before the block reduction.
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_v2_kernel(
+    const __nv_bfloat16* __restrict__ dapad, const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ g_out,
+    float* __restrict__ sums, int N, int H, int W, int C, int pad_mode, float inv_count, float eps) {
+  extern __shared__ float s_mem[];     // [2][C] block partial sums
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_mem[i] = 0.f;
+  __syncthreads();
+  const int cg = C >> 3;
+  const int cg_shift = 31 - __clz(cg);
+  const int Hp = H + 2, Wp = W + 2;
+  const unsigned total = (unsigned)N * H * W * cg;
+  const unsigned stride = ((gridDim.x * blockDim.x) >> cg_shift) << cg_shift;
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 & (cg - 1)) * 8;
+  float a[8], b[8], acc1[8], acc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {        // only (a, b) stay live in the loop; mean / invstd are recomputed at the end
+    const float m = stats[c0 + j] * inv_count;
+    float var = stats[C + c0 + j] * inv_count - m * m;
+    var = var < 0.f ? 0.f : var;
+    a[j] = gamma[c0 + j] * rsqrtf(var + eps);
+    b[j] = beta[c0 + j] - m * a[j];
+    acc1[j] = acc2[j] = 0.f;
+  }
+  const int lo = pad_mode == 0 ? 1 : 0;
+  if (i0 < stride) {
+    for (unsigned i = i0; i < total; i += stride) {
+      unsigned pix = i >> cg_shift;
+      const int x = (int)(pix % (unsigned)W); pix /= (unsigned)W;
+      const int yy = (int)(pix % (unsigned)H);
+      const int n = (int)(pix / (unsigned)H);
+      const __nv_bfloat16* base = dapad + ((size_t)n * Hp * Wp) * C + c0;
+      V8 d = load_bf16x8(base + ((size_t)(yy + 1) * Wp + (x + 1)) * C);
+      const bool top = (yy == lo), bot = (yy == H - 1 - lo), lef = (x == lo), rig = (x == W - 1 - lo);
+      if (top | bot | lef | rig) {
+        int ry[3], rx[3], ny = 1, nx = 1;
+        ry[0] = yy + 1; rx[0] = x + 1;
+        if (top) ry[ny++] = 0;
+        if (bot) ry[ny++] = H + 1;
+        if (lef) rx[nx++] = 0;
+        if (rig) rx[nx++] = W + 1;
+        for (int p = 0; p < ny; ++p)
+          for (int q = 0; q < nx; ++q) {
+            if (p == 0 && q == 0) continue;
+            const V8 t = load_bf16x8(base + ((size_t)ry[p] * Wp + rx[q]) * C);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d.f[j] += t.f[j];
+          }
+      }
+      const size_t o = (((size_t)n * H + yy) * W + x) * C + c0;
+      const V8 yv = load_bf16x8(y + o);
+      V8 g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float u = fmaf(yv.f[j], a[j], b[j]);
+        g.f[j] = d.f[j] * (u > 0.f ? 1.f : __expf(u));
+        acc1[j] += g.f[j];
+        acc2[j] = fmaf(g.f[j], yv.f[j], acc2[j]);
+      }
+      store_bf16x8(g_out + o, g);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m = stats[c0 + j] * inv_count;
+    float var = stats[C + c0 + j] * inv_count - m * m;
+    var = var < 0.f ? 0.f : var;
+    atomicAdd(&s_mem[c0 + j], acc1[j]);
+    atomicAdd(&s_mem[C + c0 + j], rsqrtf(var + eps) * (acc2[j] - m * acc1[j]));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], s_mem[i]);
+}
+
 // One thread = 8 channels of one pixel of one IMAGE; loops over its S planes.
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats,
@@ -299,6 +378,13 @@ void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* sta
                               float inv_count, float eps, cudaStream_t stream) {
   const size_t total = (size_t)N * H * W * (C / 8);
   int blocks = grid_for(total, 148 * 8);
+  static const bool v2 = getenv("MINE_B200_BN_REDUCE") && getenv("MINE_B200_BN_REDUCE")[0] == 'v';
+  if (v2) {
+    bn_act_bwd_reduce_v2_kernel<<<blocks, 256, 2 * C * sizeof(float), stream>>>(
+        (const __nv_bfloat16*)dapad, (const __nv_bfloat16*)y, stats, gamma, beta, (__nv_bfloat16*)g_out, sums, N, H, W, C,
+        pad_mode, inv_count, eps);
+    return;
+  }
   // the grid-stride must be a multiple of the channel-group count so every thread keeps its channels
   bn_act_bwd_reduce_kernel<<<blocks, 256, 6 * C * sizeof(float), stream>>>(
       (const __nv_bfloat16*)dapad, (const __nv_bfloat16*)y, stats, gamma, beta, (__nv_bfloat16*)g_out, sums, N, H, W, C,

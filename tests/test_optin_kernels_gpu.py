@@ -1,0 +1,71 @@
+"""Opt-in kernel variants: the CUDA-core MPI head (``csrc/head_direct.cu``) vs the tcgen05 head and the PyTorch
+specification, and variant 2 of the BatchNorm backward reduction vs the default kernel.
+Opt-in (``MINE_B200_TEST_OPTIN=1``) until the kernel has been run on hardware."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MINE_B200_TEST_OPTIN", "0") != "1",
+                                 reason="opt-in kernels (MINE_B200_TEST_OPTIN=1)")]
+
+
+@pytest.mark.parametrize("c,n,h,w,alpha", [(16, 3, 40, 72, False), (32, 2, 33, 50, False), (16, 2, 16, 32, True)])
+def test_head_direct_matches_tcgen05_head_and_spec(c, n, h, w, alpha, monkeypatch):
+    from mine_b200.ops import conv_engine as E
+    from mine_b200.ops import emu
+    g = torch.Generator().manual_seed(0)
+    apad = torch.randn((n, h + 2, w + 2, c), generator=g).cuda().to(torch.bfloat16)
+    wt = (torch.randn((4, c, 3, 3), generator=g) * 0.2).cuda()
+    bias = torch.randn(4, generator=g).cuda()
+    monkeypatch.setenv("MINE_B200_HEAD", "direct")
+    got = E.HeadConv.apply(apad, wt, bias, alpha)
+    monkeypatch.setenv("MINE_B200_HEAD", "tcgen05")
+    ref = E.HeadConv.apply(apad, wt, bias, alpha)           # bf16-rounded weights on the tensor cores
+    spec, sign = emu.head_conv_direct(apad, wt.permute(2, 3, 1, 0).contiguous(), bias, alpha)
+    assert got.shape == ref.shape == spec.shape
+    assert (got - spec).abs().max().item() < 2e-3            # fp32 weights, fp32 accumulation: only summation order
+    assert (got - ref).abs().max().item() < 3e-2
+    mpi2, sign2 = E.ext().head_conv_direct(apad, wt.permute(2, 3, 1, 0).contiguous(), bias, alpha)
+    far = spec[..., 3] > 1e-2 if not alpha else torch.ones_like(sign, dtype=torch.bool)
+    assert torch.equal(sign2[far], sign[far])
+
+
+_REDUCE_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, {repo!r})
+from mine_b200.ops import conv_engine as E
+g = torch.Generator().manual_seed(1)
+out = {{}}
+for c, pad in ((16, 0), (64, 1), (256, 0)):
+    n, h, w = 6, 20, 36
+    dapad = torch.randn((n, h + 2, w + 2, c), generator=g).cuda().to(torch.bfloat16)
+    y = torch.randn((n, h, w, c), generator=g).cuda().to(torch.bfloat16)
+    yf = y.float()
+    stats = torch.stack([yf.sum((0, 1, 2)), (yf * yf).sum((0, 1, 2))])
+    gamma, beta = torch.rand(c, generator=g).cuda() + 0.5, torch.randn(c, generator=g).cuda()
+    gg, sums = E.ext().bn_act_bwd_reduce(dapad, y, stats, gamma, beta, pad, float(n * h * w), 1e-5)
+    out[(c, pad)] = (gg.float().cpu(), sums.cpu())
+torch.save(out, sys.argv[1])
+"""
+
+
+def test_bn_backward_reduce_variant2_matches_variant1(tmp_path):
+    """``MINE_B200_BN_REDUCE=v2`` (register coefficients, sum(g*y) form) against the default kernel; the switch is
+    read once per process, so each variant runs in its own interpreter."""
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("v1", {}), ("v2", {"MINE_B200_BN_REDUCE": "v2"})):
+        path = str(tmp_path / (tag + ".pt"))
+        r = subprocess.run([sys.executable, "-c", _REDUCE_SNIPPET.format(repo=repo), path], env=dict(os.environ, **env),
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = torch.load(path)
+    for key in res["v1"]:
+        g1, s1 = res["v1"][key]
+        g2, s2 = res["v2"][key]
+        assert torch.equal(g1, g2), key
+        assert torch.allclose(s1, s2, rtol=2e-3, atol=2e-2 * s1.abs().max().item()), key
