@@ -24,7 +24,10 @@ class ModelRunner:
         self.device = torch.device(device)
         mode = os.environ.get("MINE_B200_CONV", config.get("engine.conv", "auto"))
         if self.device.type != "cuda":
-            mode = "spec"
+            # off-GPU the modules run as plain PyTorch - unless the kernel specification has been switched on
+            # (tests / analysis tools), in which case the engine orchestration itself runs through ops/emu.py
+            from .ops import conv_engine
+            mode = "tcgen05" if (mode == "tcgen05" and conv_engine._emulated) else "spec"
         elif mode == "auto":
             from .ops import conv_engine
             mode = "tcgen05" if conv_engine.AVAILABLE else "cudnn"

@@ -119,5 +119,22 @@ def sparse_disparity(disp_map: torch.Tensor, k: torch.Tensor, xyz: torch.Tensor)
     return S.gather_nearest(disp_map, S.project_points(k, xyz))
 
 
+def sparse_point_loss(disp_map: torch.Tensor, k: torch.Tensor, xyz: torch.Tensor,
+                      scale: Optional[torch.Tensor] = None, calibrate: bool = True):
+    """``(mean |log(d / scale) - log(1/z)|, scale)`` at the projections of sparse camera-frame points; the scale is
+    calibrated from these points when none is given (``calibrate=False``: ones - datasets with metric poses).
+    Default: composition of specification ops; ``MINE_B200_SPARSE=fused`` on CUDA: one kernel per direction."""
+    if scale is None and not calibrate:
+        scale = torch.ones(xyz.shape[0], dtype=torch.float32, device=xyz.device)
+    if _use_kernels(disp_map) and os.environ.get("MINE_B200_SPARSE", "spec") == "fused":
+        from .sparse import sparse_point_loss as fused
+        return fused(disp_map, k, xyz, scale)
+    disp_gt = torch.reciprocal(xyz[:, 2:, :])
+    disp_syn = sparse_disparity(disp_map, k, xyz)
+    if scale is None:
+        scale = L.scale_factor_from_points(disp_syn, disp_gt)
+    return L.log_disparity_l1(disp_syn, disp_gt, scale), scale
+
+
 def image_pyramid(img: torch.Tensor, levels: int = 4):
     return [L.nearest_downsample(img, s) for s in range(levels)]

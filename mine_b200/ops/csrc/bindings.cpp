@@ -125,6 +125,45 @@ std::vector<at::Tensor> masked_l1_fwd(const at::Tensor& a, const at::Tensor& b, 
   return {sum, sign};
 }
 
+// disp [B,1,H,W] (or [B,H,W]); k [B,3,3]; xyz [B,3,N]; scale_in [B] or none
+// -> {loss (0-dim), scale [B], idx int32 [B,N], d_syn [B,N], sgn [B,N]}
+std::vector<at::Tensor> sparse_point_fwd(const at::Tensor& disp, const at::Tensor& k, const at::Tensor& xyz,
+                                         const c10::optional<at::Tensor>& scale_in) {
+  check_f32(disp, "disp"); check_f32(k, "k"); check_f32(xyz, "xyz");
+  const int B = disp.size(0), H = disp.size(-2), W = disp.size(-1), N = xyz.size(2);
+  TORCH_CHECK(disp.numel() == (int64_t)B * H * W && k.numel() == B * 9 && xyz.size(0) == B && xyz.size(1) == 3, "shapes");
+  const float* sc = nullptr;
+  if (scale_in.has_value() && scale_in->defined()) { check_f32(*scale_in, "scale"); TORCH_CHECK(scale_in->numel() == B, "scale"); sc = scale_in->data_ptr<float>(); }
+  c10::cuda::CUDAGuard guard(disp.device());
+  at::Tensor loss = at::zeros({}, disp.options());
+  at::Tensor scale = at::empty({B}, disp.options());
+  at::Tensor idx = at::empty({B, N}, disp.options().dtype(at::kInt));
+  at::Tensor d_syn = at::empty({B, N}, disp.options());
+  at::Tensor sgn = at::empty({B, N}, disp.options());
+  mine::launch_sparse_point_fwd(disp.data_ptr<float>(), k.data_ptr<float>(), xyz.data_ptr<float>(), sc, idx.data_ptr<int>(),
+                                d_syn.data_ptr<float>(), sgn.data_ptr<float>(), scale.data_ptr<float>(),
+                                loss.data_ptr<float>(), B, H, W, N, cur_stream());
+  return {loss, scale, idx, d_syn, sgn};
+}
+
+// -> {grad_disp (shape of disp), grad_scale_in [B] (zeros when the scale was computed in the forward)}
+std::vector<at::Tensor> sparse_point_bwd(const at::Tensor& g_loss, const c10::optional<at::Tensor>& g_scale,
+                                         const at::Tensor& idx, const at::Tensor& d_syn, const at::Tensor& sgn,
+                                         const at::Tensor& scale, std::vector<int64_t> disp_shape, bool computed_scale) {
+  check_f32(g_loss, "g_loss"); check_f32(d_syn, "d_syn"); check_f32(sgn, "sgn"); check_f32(scale, "scale");
+  const int B = d_syn.size(0), N = d_syn.size(1);
+  const int H = disp_shape[disp_shape.size() - 2], W = disp_shape[disp_shape.size() - 1];
+  const float* gs = nullptr;
+  if (g_scale.has_value() && g_scale->defined()) { check_f32(*g_scale, "g_scale"); gs = g_scale->data_ptr<float>(); }
+  c10::cuda::CUDAGuard guard(d_syn.device());
+  at::Tensor grad_disp = at::zeros(disp_shape, d_syn.options());
+  at::Tensor grad_scale = at::zeros({B}, d_syn.options());
+  mine::launch_sparse_point_bwd(g_loss.data_ptr<float>(), gs, idx.data_ptr<int>(), d_syn.data_ptr<float>(),
+                                sgn.data_ptr<float>(), scale.data_ptr<float>(), grad_disp.data_ptr<float>(),
+                                grad_scale.data_ptr<float>(), computed_scale ? 1 : 0, B, H, W, N, cur_stream());
+  return {grad_disp, grad_scale};
+}
+
 void fused_adam(at::Tensor p, const at::Tensor& g, at::Tensor m, at::Tensor v, const at::Tensor& hyper, double beta1,
                 double beta2, double eps, double wd) {
   check_f32(p, "p"); check_f32(g, "g"); check_f32(m, "m"); check_f32(v, "v"); check_f32(hyper, "hyper");
@@ -199,6 +238,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ssim_fwd", &ssim_fwd);
   m.def("ssim_bwd", &ssim_bwd);
   m.def("masked_l1_fwd", &masked_l1_fwd);
+  m.def("sparse_point_fwd", &sparse_point_fwd);
+  m.def("sparse_point_bwd", &sparse_point_bwd);
   m.def("fused_adam", &fused_adam);
   m.def("smooth_v2_fwd", &smooth_v2_fwd);
   m.def("smooth_v2_bwd", &smooth_v2_bwd);

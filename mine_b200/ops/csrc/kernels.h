@@ -58,6 +58,16 @@ void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, v
 }  // namespace mine
 
 namespace mine {
+// ---- sparse.cu (sparse-point disparity supervision: projection, gather, scale calibration, log-L1) -------
+void launch_sparse_point_fwd(const float* disp, const float* K, const float* xyz, const float* scale_in, int* idx,
+                             float* d_syn, float* sgn, float* scale_out, float* loss, int B, int H, int W, int N,
+                             cudaStream_t stream);
+void launch_sparse_point_bwd(const float* g_loss, const float* g_scale, const int* idx, const float* d_syn,
+                             const float* sgn, const float* scale, float* grad_disp, float* grad_scale_in,
+                             int computed_scale, int B, int H, int W, int N, cudaStream_t stream);
+}  // namespace mine
+
+namespace mine {
 // ---- head_direct.cu (CUDA-core MPI head for the 16 / 32-channel levels) ----------------------------------
 const char* launch_head_conv_direct(const void* apad, const float* wpk, const float* bias, float* mpi, int8_t* sign, int N,
                                     int H, int W, int C, int use_alpha, cudaStream_t stream);

@@ -220,3 +220,37 @@ def head_conv_direct(apad, wpk, bias, use_alpha):
     mpi = torch.cat([torch.sigmoid(z[..., :3]), last], dim=-1).contiguous()
     sign = torch.where(z[..., 3] >= 0, 1, -1).to(torch.int8)
     return [mpi, sign]
+
+
+# ---- sparse-point supervision (csrc/sparse.cu) -------------------------------------------------------------------
+def sparse_point_fwd(disp, k, xyz, scale_in):
+    b, n = xyz.shape[0], xyz.shape[2]
+    h, w = disp.shape[-2], disp.shape[-1]
+    p = k.float() @ xyz.float()
+    u, v = p[:, 0] / p[:, 2], p[:, 1] / p[:, 2]
+    ix = torch.round(u).long().clamp(0, w - 1)
+    iy = torch.round(v).long().clamp(0, h - 1)
+    idx = iy * w + ix                                                          # [B,N]
+    d = torch.gather(disp.float().reshape(b, h * w), 1, idx)
+    g = torch.reciprocal(xyz[:, 2].float())
+    scale = scale_in.float().clone() if scale_in is not None else torch.exp((torch.log(d) - torch.log(g)).mean(dim=1))
+    t = torch.log(d / scale[:, None]) - torch.log(g)
+    return [t.abs().sum() / (b * n), scale, idx.to(torch.int32), d, torch.sign(t)]
+
+
+def sparse_point_bwd(g_loss, g_scale, idx, d_syn, sgn, scale, disp_shape, computed_scale):
+    b, n = d_syn.shape
+    h, w = disp_shape[-2], disp_shape[-1]
+    c = g_loss.reshape(()) / (b * n)
+    dl_ds = -c * sgn.sum(dim=1) / scale
+    through = torch.zeros(b, dtype=torch.float32, device=d_syn.device)
+    grad_scale = torch.zeros(b, dtype=torch.float32, device=d_syn.device)
+    if computed_scale:
+        gs = dl_ds + (g_scale if g_scale is not None else 0.0)
+        through = gs * scale / n
+    else:
+        grad_scale = dl_ds
+    gd = (c * sgn + through[:, None]) / d_syn
+    grad = torch.zeros((b, h * w), dtype=torch.float32, device=d_syn.device)
+    grad.scatter_add_(1, idx.long(), gd)
+    return [grad.reshape(disp_shape), grad_scale]

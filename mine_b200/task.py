@@ -247,10 +247,8 @@ class SynthesisTask:
         src_imgs_syn, src_disparity_syn, mpi_for_tgt = src["rgb"], src["disparity"], src["mpi"]
 
         # --- sparse points in the source frame, scale calibration ------------------------------
-        src_pt_disp = torch.reciprocal(self.pt3d_src[:, 2:, :])
-        src_pt_disp_syn = ops.sparse_disparity(src_disparity_syn, K_src, self.pt3d_src)
-        if scale_factor is None:
-            scale_factor = self.compute_scale_factor(src_pt_disp_syn, src_pt_disp)
+        loss_disp_src, scale_factor = ops.sparse_point_loss(src_disparity_syn, K_src, self.pt3d_src, scale_factor,
+                                                            calibrate=c["data.name"] not in NO_SCALE_DATASETS)
 
         # --- target view (true dependency on the scale factor) --------------------
         with self.profiler.phase("render_tgt"):
@@ -270,10 +268,8 @@ class SynthesisTask:
                 loss_rgb_src = (src_imgs_syn - src_img).abs().mean()
                 loss_ssim_src = 1 - ops.ssim(src_imgs_syn, src_img)
                 loss_smooth_src = ops.edge_aware_loss(src_img, src_disparity_syn, gmin, ratio)
-            loss_disp_src = disp_lambda * L.log_disparity_l1(src_pt_disp_syn, src_pt_disp, scale_factor)
-            tgt_pt_disp = torch.reciprocal(self.pt3d_tgt[:, 2:, :])
-            tgt_pt_disp_syn = ops.sparse_disparity(tgt_disparity_syn, K_tgt, self.pt3d_tgt)
-            loss_disp_tgt = disp_lambda * L.log_disparity_l1(tgt_pt_disp_syn, tgt_pt_disp, scale_factor)
+            loss_disp_src = disp_lambda * loss_disp_src
+            loss_disp_tgt = disp_lambda * ops.sparse_point_loss(tgt_disparity_syn, K_tgt, self.pt3d_tgt, scale_factor)[0]
             loss_rgb_tgt = ops.masked_l1(tgt_rgb, tgt_img, tgt_mask, float(c["mpi.valid_mask_threshold"]))
             if lam1 != 0.0:
                 loss_smooth_tgt = lam1 * ops.edge_aware_loss(tgt_img, tgt_disparity_syn, gmin, ratio)

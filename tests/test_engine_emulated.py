@@ -205,3 +205,60 @@ def test_encoder_engine_matches_module(layers, train, lib):
     for k, v in enc.state_dict().items():
         if k in run_stats:
             assert torch.allclose(run_stats[k].float(), v.float(), rtol=1e-4, atol=1e-5), k
+
+
+def test_training_step_through_emulated_engine_matches_module_path(monkeypatch):
+    """The whole task step (prediction, rendering, losses, backward, Adam) with the engine orchestration in the loop
+    reproduces the plain-module path: same losses, same updated parameters."""
+    from mine_b200 import config as C
+    from mine_b200.data.synthetic import config_batch
+    from mine_b200.task import SynthesisTask
+    shape = {"data.img_w": 64, "data.img_h": 64, "mpi.num_bins_coarse": 3, "data.per_gpu_batch_size": 1,
+             "data.visible_point_count": 16, "model.imagenet_pretrained": False}
+
+    def run(mode):
+        monkeypatch.setenv("MINE_B200_CONV", mode)
+        cfg = C.config_for_dataset("llff", shape)
+        cfg["device"] = torch.device("cpu")
+        torch.manual_seed(0)
+        task = SynthesisTask(cfg, None)
+        assert task.runner.mode == mode
+        torch.manual_seed(1)
+        out = task.train_step(config_batch(cfg))
+        losses = {k: float(v.detach()) for k, v in out.items() if torch.is_tensor(v) and v.numel() == 1}
+        return losses, torch.cat([p.detach().reshape(-1) for p in task.decoder.parameters()])
+    la, pa = run("tcgen05")
+    lb, pb = run("spec")
+    for k in lb:
+        assert la[k] == pytest.approx(lb[k], rel=2e-3, abs=1e-4), k
+    assert torch.allclose(pa, pb, atol=2.5e-3)          # one Adam step moves every weight by ~lr = 1e-3
+
+
+def test_sparse_point_node_matches_spec_composition():
+    """One autograd node for projection + gather + scale calibration + log-L1 (``ops/sparse.py`` on the kernel
+    specification) against the composition of specification ops, including the gradient that reaches the source
+    disparity map THROUGH the scale factor used by the other view and the other pyramid levels."""
+    from mine_b200.ops import api
+    from mine_b200.ops.sparse import sparse_point_loss as fused
+    g = torch.Generator().manual_seed(0)
+    b, h, w, n = 3, 24, 40, 50
+    k = torch.tensor([[30.0, 0, 20], [0, 30.0, 12], [0, 0, 1]]).expand(b, 3, 3).contiguous()
+    z = torch.rand(b, 1, n, generator=g) * 4 + 1
+    xy = (torch.rand(b, 2, n, generator=g) - 0.5) * torch.tensor([1.6, 1.0]).view(1, 2, 1)      # a few fall outside
+    xyz = torch.cat([xy * z, z], dim=1)
+
+    def run(fn):
+        ds = (torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(1)) + 0.2).requires_grad_()
+        dt = (torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(2)) + 0.2).requires_grad_()
+        l_src, scale = fn(ds, k, xyz, None)
+        l_tgt, _ = fn(dt, k, xyz * 1.1, scale)
+        l_lo, _ = fn(ds[..., ::2, ::2] * 1.0, k * torch.tensor([0.5, 0.5, 1.0]).view(1, 3, 1), xyz, scale)
+        total = l_src + 2.0 * l_tgt + 0.5 * l_lo + 0.1 * scale.sum()
+        total.backward()
+        return [float(v.detach()) for v in (l_src, l_tgt, l_lo)], scale.detach(), ds.grad, dt.grad
+    want = run(lambda d, kk, p, s: api.sparse_point_loss(d, kk, p, s))
+    got = run(fused)
+    assert got[0] == pytest.approx(want[0], rel=1e-5)
+    assert torch.allclose(got[1], want[1], rtol=1e-5)
+    assert torch.allclose(got[2], want[2], rtol=1e-4, atol=1e-7) and torch.allclose(got[3], want[3], rtol=1e-4, atol=1e-7)
+    assert (want[2] != 0).sum() > 10

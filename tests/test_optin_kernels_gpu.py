@@ -69,3 +69,34 @@ def test_bn_backward_reduce_variant2_matches_variant1(tmp_path):
         g2, s2 = res["v2"][key]
         assert torch.allclose(g1, g2, rtol=1e-2, atol=1e-3), key          # bf16 storage, 1-ulp differences in the affine
         assert torch.allclose(s1, s2, rtol=2e-3, atol=2e-2 * s1.abs().max().item()), key
+
+
+def test_sparse_point_kernels_match_specification():
+    """``csrc/sparse.cu`` (MINE_B200_SPARSE=fused) vs its PyTorch specification, forward values and the scattered
+    disparity-map gradient, with the scale calibrated in the node and with a given scale."""
+    from mine_b200.ops import conv_engine as E
+    from mine_b200.ops.sparse import sparse_point_loss as fused
+    g = torch.Generator().manual_seed(0)
+    b, h, w, n = 2, 256, 384, 256
+    k = torch.tensor([[300.0, 0, 192], [0, 300.0, 128], [0, 0, 1]]).expand(b, 3, 3).contiguous().cuda()
+    z = torch.rand(b, 1, n, generator=g) * 4 + 1
+    xy = (torch.rand(b, 2, n, generator=g) - 0.5) * torch.tensor([1.4, 0.9]).view(1, 2, 1)
+    xyz = torch.cat([xy * z, z], dim=1).cuda()
+
+    def run():
+        ds = (torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(1)) + 0.2).cuda().requires_grad_()
+        dt = (torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(2)) + 0.2).cuda().requires_grad_()
+        l_src, scale = fused(ds, k, xyz, None)
+        l_tgt, _ = fused(dt, k, xyz * 1.05, scale)
+        (l_src + 2.0 * l_tgt + 0.1 * scale.sum()).backward()
+        return l_src.detach(), l_tgt.detach(), scale.detach(), ds.grad, dt.grad
+    got = run()
+    E.use_emulator(True)
+    try:
+        want = run()
+    finally:
+        E.use_emulator(False)
+    for a, r in zip(got[:3], want[:3]):
+        assert torch.allclose(a, r, rtol=1e-4, atol=1e-6)
+    for a, r in zip(got[3:], want[3:]):
+        assert torch.allclose(a, r, rtol=1e-3, atol=1e-8)
