@@ -87,6 +87,16 @@ def broadcast_module_state(*modules: torch.nn.Module, src: int = 0) -> None:
             dist.broadcast(t.data, src=src)
 
 
+def any_rank(flag: bool, device: Optional[torch.device] = None) -> bool:
+    """True on every rank if ``flag`` is true on at least one (MAX all-reduce of one integer; cold path)."""
+    if world_size() == 1:
+        return bool(flag)
+    dev = device if (device is not None and dist.get_backend() == "nccl") else torch.device("cpu")
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(t.item())
+
+
 def broadcast_object(obj, src: int = 0):
     if world_size() == 1:
         return obj

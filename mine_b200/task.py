@@ -38,6 +38,7 @@ from .spec import losses as L
 from .spec import sampling as S
 from .spec.embedder import get_embedder
 from .utils import AverageMeter, NullLogger, PhaseProfiler, disparity_normalization_vis, run_shell_cmd
+from .utils.misc import StopRequest
 from .utils.misc import rng_state, set_rng_state
 
 NO_SCALE_DATASETS = ("flowers", "kitti_raw", "dtu")     # disp_lambda = 0 and scale factor = 1
@@ -143,6 +144,8 @@ class SynthesisTask:
         self.val_losses = {k: AverageMeter("val_" + k) for k in _LOSS_KEYS_VAL}
         self.current_epoch = 0
         self.epoch_step = 0                     # batches of the current epoch already consumed (mid-epoch resume)
+        self.stop_request = None                # utils.misc.StopRequest installed by train(): SIGTERM -> save + exit
+        self.stopped = False
         self.global_step = 0
         self.profiler = PhaseProfiler(enabled=False)
         self._gen = None
@@ -432,6 +435,11 @@ class SynthesisTask:
                 self._eval_and_checkpoint(val_data_loader)
             if max_steps and self.global_step >= max_steps:
                 return self.epoch_step >= len(train_data_loader)
+            if step % log_every == 0 and self.stop_request is not None:
+                # all ranks reach this poll at the same step and leave together (no rank is left in a collective)
+                if bootstrap.any_rank(self.stop_request.is_set(), self.device):
+                    self.stopped = True
+                    return self.epoch_step >= len(train_data_loader)
         return True
 
     def _eval_and_checkpoint(self, val_data_loader):
@@ -481,19 +489,24 @@ class SynthesisTask:
     def train(self, train_data_loader, val_data_loader):
         max_steps = int(cfg_get(self.config, "training.max_steps", 0))
         start_epoch = max(self.current_epoch, 1) if self.resume_meta else 1
+        if self.stop_request is None:
+            self.stop_request = StopRequest()
         for epoch in range(start_epoch, int(self.config["training.epochs"]) + 1):
             finished = self.train_epoch(train_data_loader, val_data_loader, epoch)
             if finished:
                 self.lr_scheduler.step()
                 self.current_epoch, self.epoch_step = epoch + 1, 0        # a restart begins the next epoch
             if self._is_main():
-                self.logger.info("Epoch finished, average losses: " if finished else "Stopped at training.max_steps: ")
+                self.logger.info("Epoch finished, average losses: " if finished else
+                                 ("Stop requested (signal): state saved, exiting. " if self.stopped
+                                  else "Stopped at training.max_steps: "))
                 for v in self.train_losses.values():
                     self.logger.info("    {}".format(v))
                 # the state a restart continues from (upstream only writes it every checkpoint interval)
                 self.save_checkpoint("checkpoint_latest.pth", with_optimizer=True)
-            if max_steps and self.global_step >= max_steps:
+            if self.stopped or (max_steps and self.global_step >= max_steps):
                 break
+        self.stop_request.uninstall()
 
     # ------------------------------------------------------------------------------------------
     # evaluation / logging

@@ -106,3 +106,44 @@ def set_rng_state(st: dict) -> None:
     torch.set_rng_state(st["torch"])
     if "cuda" in st and torch.cuda.is_available():
         torch.cuda.set_rng_state(st["cuda"])
+
+
+class StopRequest:
+    """Cooperative shutdown on SIGTERM / SIGUSR1 (preemption, ``torchrun`` tearing the job down): the handler only
+    sets a flag; the training loop polls it at a step boundary where all ranks agree, writes the resumable
+    ``checkpoint_latest.pth`` and returns.  The reference has no failure handling at all."""
+
+    def __init__(self, install: bool = True):
+        self._flag = False
+        self._previous = {}
+        if install:
+            self.install()
+
+    def install(self) -> None:
+        import signal
+        import threading
+        if threading.current_thread() is not threading.main_thread():
+            return                                   # signal handlers can only be set from the main thread
+        for sig in (signal.SIGTERM, signal.SIGUSR1):
+            try:
+                self._previous[sig] = signal.signal(sig, self._handle)
+            except (ValueError, OSError):
+                pass
+
+    def uninstall(self) -> None:
+        import signal
+        for sig, prev in self._previous.items():
+            try:
+                signal.signal(sig, prev)
+            except (ValueError, OSError):
+                pass
+        self._previous = {}
+
+    def _handle(self, signum, frame) -> None:
+        self._flag = True
+
+    def set(self) -> None:
+        self._flag = True
+
+    def is_set(self) -> bool:
+        return self._flag

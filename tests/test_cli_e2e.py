@@ -92,3 +92,42 @@ def test_train_cli_on_llff_layout_with_heldout_split(tmp_path):
     r = subprocess.run(cmd + ["--extra_config", json.dumps(extra)], cwd=REPO, env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode != 0 and "no training images under" in (r.stdout + r.stderr)
+
+
+@pytest.mark.timeout(900)
+def test_sigterm_saves_resumable_state_and_exits_cleanly(tmp_path):
+    """Preemption: SIGTERM -> the loop stops at the next agreed step boundary, writes checkpoint_latest.pth, exits 0;
+    the same command then resumes from that step."""
+    import signal
+    import time
+    extra = dict(EXTRA, **{"data.training_set_path": "synthetic:64", "training.epochs": 50, "training.max_steps": 0})
+    cmd = [sys.executable, os.path.join(REPO, "train.py"), "--config_path", os.path.join(REPO, "configs/params_llff.yaml"),
+           "--workspace", str(tmp_path / "ws"), "--version", "v0", "--extra_config", json.dumps(extra)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", MASTER_ADDR="127.0.0.1", MASTER_PORT="29641")
+    log_path = str(tmp_path / "ws" / "v0" / "training.log")
+    proc = subprocess.Popen(cmd, cwd=REPO, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        deadline = time.time() + 300
+        while time.time() < deadline:
+            if os.path.exists(log_path) and "global_step = 2 " in open(log_path).read():
+                break
+            assert proc.poll() is None, proc.stdout.read()[-3000:]
+            time.sleep(0.5)
+        else:
+            pytest.fail("training did not start")
+        proc.send_signal(signal.SIGTERM)
+        out, _ = proc.communicate(timeout=120)
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+    assert proc.returncode == 0, out[-3000:]
+    log = open(log_path).read()
+    assert "Stop requested (signal)" in log
+    ck = torch.load(str(tmp_path / "ws" / "v0" / "checkpoint_latest.pth"), map_location="cpu", weights_only=False)
+    step = int(ck["meta"]["global_step"])
+    assert step >= 2 and "optimizer" in ck
+    extra["training.max_steps"] = step + 1
+    cmd[-1] = json.dumps(extra)
+    r = subprocess.run(cmd, cwd=REPO, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "global_step %d" % step in open(log_path).read().split("Stop requested (signal)")[-1]
