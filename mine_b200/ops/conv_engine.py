@@ -259,13 +259,7 @@ class PlaneConvBNAct(torch.autograd.Function):
         apad = ext().bn_act_pad_fwd(y, stats, g32, b32, int(pad_out), count, BN_EPS)
         _count()
         if bn is not None and training:
-            with torch.no_grad():
-                mean = stats[0] / count
-                var = (stats[1] / count - mean * mean).clamp_min(0)
-                m = bn.momentum
-                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                bn.running_var.mul_(1 - m).add_(var * (count / max(count - 1.0, 1.0)), alpha=m)
-                bn.num_batches_tracked += 1
+            update_running_stats(bn, stats, count)
         ctx.save_for_backward(xpad, w, y, stats, g32, b32)
         ctx.cfg = (bool(up), int(planes), int(pad_out), count, reducer, chan_bias is not None, plane_bias is not None,
                    shared_map is not None)
@@ -292,6 +286,23 @@ class PlaneConvBNAct(torch.autograd.Function):
             dx = (dgrad_up_raw if up else dgrad_same_raw)(dy, w)
         return (dx, dw, dcb, dpb if has_pb else None, dshared if has_sm else None, dgamma.to(g32.dtype),
                 dbeta.to(b32.dtype), None, None, None, None, None)
+
+
+def update_running_stats(bn, stats: torch.Tensor, count: float) -> None:
+    """Momentum update of ``bn``'s buffers from the reduced batch sums ``[2, C]``.  ``MINE_B200_BN_RUNNING=fused``:
+    one kernel (``bn_update_running``, opt-in until measured); default: the equivalent framework ops."""
+    with torch.no_grad():
+        if os.environ.get("MINE_B200_BN_RUNNING", "aten") == "fused" and (_emulated or stats.is_cuda):
+            ext().bn_update_running(stats, bn.running_mean, bn.running_var, bn.num_batches_tracked, float(count),
+                                    float(bn.momentum))
+            _count()
+            return
+        mean = stats[0] / count
+        var = (stats[1] / count - mean * mean).clamp_min(0)
+        m = bn.momentum
+        bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+        bn.running_var.mul_(1 - m).add_(var * (count / max(count - 1.0, 1.0)), alpha=m)
+        bn.num_batches_tracked += 1
 
 
 def head_mode() -> str:

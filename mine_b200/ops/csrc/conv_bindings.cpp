@@ -252,6 +252,19 @@ at::Tensor channel_stats(const at::Tensor& y) {
   return sums;
 }
 
+void bn_update_running(const at::Tensor& stats, at::Tensor running_mean, at::Tensor running_var,
+                       at::Tensor num_batches_tracked, double count, double momentum) {
+  const int64_t C = running_mean.numel();
+  TORCH_CHECK(opt_f32(stats, "stats") && stats.numel() == 2 * C, "stats must be fp32 [2, C]");
+  TORCH_CHECK(opt_f32(running_mean, "running_mean") && opt_f32(running_var, "running_var") && running_var.numel() == C,
+              "running statistics must be contiguous CUDA fp32");
+  TORCH_CHECK(num_batches_tracked.is_cuda() && num_batches_tracked.scalar_type() == at::kLong, "num_batches_tracked");
+  c10::cuda::CUDAGuard guard(stats.device());
+  mine::launch_bn_update_running(stats.data_ptr<float>(), running_mean.data_ptr<float>(), running_var.data_ptr<float>(),
+                                 reinterpret_cast<long long*>(num_batches_tracked.data_ptr<int64_t>()), (int)C,
+                                 (float)count, (float)momentum, cur_stream());
+}
+
 }  // namespace
 
 void register_conv(pybind11::module_& m) {
@@ -266,4 +279,5 @@ void register_conv(pybind11::module_& m) {
   m.def("bn_res_act_bwd_reduce", &bn_res_act_bwd_reduce);
   m.def("channel_stats", &channel_stats);
   m.def("head_conv_direct", &head_conv_direct);
+  m.def("bn_update_running", &bn_update_running);
 }

@@ -164,6 +164,21 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16*
   publish_sums(s_sum, sums, C, w.c0, w.active, acc1, acc2);
 }
 
+// running_mean/var <- (1 - m) * running + m * batch statistic (unbiased variance), num_batches_tracked += 1:
+// one launch instead of the ~11 framework ops per BatchNorm layer and step
+__global__ void bn_update_running_kernel(const float* __restrict__ stats, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, long long* __restrict__ num_batches, int C,
+                                         float inv_count, float unbias, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  const float mean = stats[c] * inv_count;
+  float var = stats[C + c] * inv_count - mean * mean;
+  var = var < 0.f ? 0.f : var;
+  running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+  running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+}
+
 int blocks_for(size_t total, int C, int cap) {
   size_t b = (total + 255) / 256;
   if (b > (size_t)cap) b = cap;
@@ -189,6 +204,13 @@ void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void*
   bn_res_act_bwd_reduce_kernel<<<blocks_for(total, C, 148 * 8), 256, 2 * C * sizeof(float), stream>>>(
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)y, stats, (__nv_bfloat16*)g_out, sums,
       (unsigned)total, C, relu, inv_count, eps);
+}
+
+void launch_bn_update_running(const float* stats, float* running_mean, float* running_var, long long* num_batches, int C,
+                              float count, float momentum, cudaStream_t stream) {
+  const float unbias = count > 1.f ? count / (count - 1.f) : 1.f;
+  bn_update_running_kernel<<<(C + 255) / 256, 256, 0, stream>>>(stats, running_mean, running_var, num_batches, C,
+                                                               1.f / count, unbias, momentum);
 }
 
 void launch_channel_stats(const void* y, float* sums, size_t npix, int C, cudaStream_t stream) {

@@ -81,6 +81,8 @@ void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void*
                                   float* sums, size_t npix, int C, int relu, float inv_count, float eps,
                                   cudaStream_t stream);
 void launch_channel_stats(const void* y, float* sums, size_t npix, int C, cudaStream_t stream);
+void launch_bn_update_running(const float* stats, float* running_mean, float* running_var, long long* num_batches, int C,
+                              float count, float momentum, cudaStream_t stream);
 }  // namespace mine
 
 namespace mine {

@@ -200,6 +200,15 @@ def bn_res_act_bwd_reduce(dout, out, y, stats, gamma, beta, relu, count, eps):
     return [g.to(y.dtype), sums]
 
 
+def bn_update_running(stats, running_mean, running_var, num_batches_tracked, count, momentum):
+    """In-place momentum update of the BatchNorm buffers from the reduced batch sums (unbiased variance)."""
+    mean = stats[0].float() / count
+    var = (stats[1].float() / count - mean * mean).clamp_min(0)
+    running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+    running_var.mul_(1 - momentum).add_((var * (count / max(count - 1.0, 1.0))).to(running_var.dtype), alpha=momentum)
+    num_batches_tracked += 1
+
+
 def channel_stats(y):
     """``[sum, sum of squares]`` per channel of an NHWC tensor (for convolutions that ran outside the engine)."""
     yf = y.float()

@@ -193,13 +193,7 @@ class BNAct(torch.autograd.Function):
         a = ext().bn_res_act_fwd(y, stats, g32, b32, residual, bool(relu), count, BN_EPS)
         _count()
         if bn is not None and training:
-            with torch.no_grad():
-                mean = stats[0] / count
-                var = (stats[1] / count - mean * mean).clamp_min(0)
-                m = bn.momentum
-                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                bn.running_var.mul_(1 - m).add_(var * (count / max(count - 1.0, 1.0)), alpha=m)
-                bn.num_batches_tracked += 1
+            E.update_running_stats(bn, stats, count)
         ctx.save_for_backward(y, a, stats, g32, b32)
         ctx.cfg = (bool(relu), count, reducer, residual is not None, training)
         return a

@@ -37,6 +37,7 @@ class Counter(TorchDispatchMode):
         self.sites = collections.Counter()
         self.ops = collections.Counter()
         self.kernel_regions = collections.Counter()
+        self.backward_ops = collections.Counter()
 
     def __torch_dispatch__(self, func, types, args=(), kwargs=None):
         out = func(*args, **(kwargs or {}))
@@ -51,6 +52,8 @@ class Counter(TorchDispatchMode):
                 break
         self.sites[site] += 1
         self.ops[name] += 1
+        if "_train_step_eager" in site or site == "<autograd>":
+            self.backward_ops[name] += 1
         return out
 
 
@@ -175,6 +178,9 @@ def main():
     print("\nby call site:")
     for site, n in counter.sites.most_common(a.top):
         print("%6d  %s" % (n, site))
+    print("\nautograd-generated backward operators of glue code:")
+    for op, n in counter.backward_ops.most_common(25):
+        print("%6d  %s" % (n, op))
     print("\nby operator:")
     for op, n in counter.ops.most_common(25):
         print("%6d  %s" % (n, op))

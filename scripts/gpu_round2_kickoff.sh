@@ -25,4 +25,5 @@ run_bench default X=1
 run_bench head MINE_B200_HEAD=direct
 run_bench bnv2 MINE_B200_BN_REDUCE=v2
 run_bench sparse MINE_B200_SPARSE=fused
-run_bench all MINE_B200_HEAD=direct MINE_B200_BN_REDUCE=v2 MINE_B200_SPARSE=fused
+run_bench running MINE_B200_BN_RUNNING=fused
+run_bench all MINE_B200_HEAD=direct MINE_B200_BN_REDUCE=v2 MINE_B200_SPARSE=fused MINE_B200_BN_RUNNING=fused

@@ -262,3 +262,15 @@ def test_sparse_point_node_matches_spec_composition():
     assert torch.allclose(got[1], want[1], rtol=1e-5)
     assert torch.allclose(got[2], want[2], rtol=1e-4, atol=1e-7) and torch.allclose(got[3], want[3], rtol=1e-4, atol=1e-7)
     assert (want[2] != 0).sum() > 10
+
+
+def test_fused_running_stat_update_matches_framework_ops(monkeypatch):
+    from mine_b200.models.norm import BatchNorm
+    stats = torch.stack([_rand((16,), 0) * 50, torch.rand(16, generator=torch.Generator().manual_seed(1)) * 500 + 300])
+    a, b = BatchNorm(16), BatchNorm(16)
+    monkeypatch.setenv("MINE_B200_BN_RUNNING", "aten")
+    E.update_running_stats(a, stats, 96.0)
+    monkeypatch.setenv("MINE_B200_BN_RUNNING", "fused")
+    E.update_running_stats(b, stats, 96.0)
+    assert torch.allclose(a.running_mean, b.running_mean) and torch.allclose(a.running_var, b.running_var)
+    assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 1

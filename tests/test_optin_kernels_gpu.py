@@ -100,3 +100,18 @@ def test_sparse_point_kernels_match_specification():
         assert torch.allclose(a, r, rtol=1e-4, atol=1e-6)
     for a, r in zip(got[3:], want[3:]):
         assert torch.allclose(a, r, rtol=1e-3, atol=1e-8)
+
+
+def test_fused_running_stat_update_kernel(monkeypatch):
+    from mine_b200.models.norm import BatchNorm
+    from mine_b200.ops import conv_engine as E
+    g = torch.Generator().manual_seed(0)
+    stats = torch.stack([torch.randn(256, generator=g) * 50, torch.rand(256, generator=g) * 500 + 300]).cuda()
+    a, b = BatchNorm(256).cuda(), BatchNorm(256).cuda()
+    monkeypatch.setenv("MINE_B200_BN_RUNNING", "aten")
+    E.update_running_stats(a, stats, 4096.0)
+    monkeypatch.setenv("MINE_B200_BN_RUNNING", "fused")
+    E.update_running_stats(b, stats, 4096.0)
+    assert torch.allclose(a.running_mean, b.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(a.running_var, b.running_var, rtol=1e-5, atol=1e-6)
+    assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 1
