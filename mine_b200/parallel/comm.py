@@ -62,12 +62,29 @@ class TorchDistComm(Communicator):
         dist.barrier(group=self.group)
 
 
+def single_node(world_size: int, env=None) -> bool:
+    """True when every rank of the job lives on this node (``LOCAL_WORLD_SIZE`` / ``GROUP_WORLD_SIZE`` exported by
+    ``torch.distributed.run``).  The peer-memory kernels map buffers over NVLink/NVSwitch, i.e. inside one node."""
+    import os
+    env = os.environ if env is None else env
+    if int(env.get("GROUP_WORLD_SIZE", "1")) > 1:
+        return False
+    local = env.get("LOCAL_WORLD_SIZE")
+    return local is None or int(local) >= world_size
+
+
 def make_communicator(kind: str = "auto", device: Optional[torch.device] = None) -> Communicator:
     """``kind``: ``p2p`` (own NVLink kernels; CUDA only), ``nccl``/``torch`` (library baseline),
-    ``auto`` (p2p on CUDA, torch.distributed otherwise)."""
+    ``auto`` (p2p on CUDA, torch.distributed otherwise).  Jobs that span several nodes use the library
+    collectives for now (the peer-memory kernels are node-local; a hierarchical NVLink + network scheme is not
+    implemented)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return Communicator()
     on_cuda = device is not None and torch.device(device).type == "cuda"
+    if kind in ("p2p", "auto") and on_cuda and not single_node(dist.get_world_size()):
+        import warnings
+        warnings.warn("multi-node job: peer-memory (NVLink) collectives are node-local, using NCCL")
+        return TorchDistComm()
     if kind in ("p2p", "auto") and on_cuda:
         try:
             from .p2p import P2PComm

@@ -93,3 +93,10 @@ def test_sharded_sampler_partitions_dataset():
     full = list(s)
     s.set_start(3)
     assert list(s) == full[3:] and list(s) == full
+
+
+def test_single_node_detection_for_peer_memory_collectives():
+    from mine_b200.parallel.comm import single_node
+    assert single_node(8, {"LOCAL_WORLD_SIZE": "8"}) and single_node(8, {})
+    assert not single_node(16, {"LOCAL_WORLD_SIZE": "8"})
+    assert not single_node(16, {"LOCAL_WORLD_SIZE": "16", "GROUP_WORLD_SIZE": "2"})
