@@ -209,7 +209,7 @@ inline void check_channels(const at::Tensor& y) {
 }
 
 at::Tensor bn_res_act_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
-                          const c10::optional<at::Tensor>& residual, bool relu, double count, double eps) {
+                          const c10::optional<at::Tensor>& residual, double slope, double count, double eps) {
   check_bf16_nhwc(y, "y"); check_channels(y);
   TORCH_CHECK(stats.numel() == 2 * y.size(3) && opt_f32(stats, "stats") && opt_f32(gamma, "gamma") && opt_f32(beta, "beta"),
               "stats/gamma/beta");
@@ -222,14 +222,14 @@ at::Tensor bn_res_act_fwd(const at::Tensor& y, const at::Tensor& stats, const at
   c10::cuda::CUDAGuard guard(y.device());
   at::Tensor out = at::empty_like(y);
   mine::launch_bn_res_act_fwd(y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(), res,
-                              out.data_ptr(), (size_t)(y.numel() / y.size(3)), (int)y.size(3), relu ? 1 : 0,
+                              out.data_ptr(), (size_t)(y.numel() / y.size(3)), (int)y.size(3), (float)slope,
                               (float)(1.0 / count), (float)eps, cur_stream());
   return out;
 }
 
 std::vector<at::Tensor> bn_res_act_bwd_reduce(const at::Tensor& dout, const at::Tensor& out, const at::Tensor& y,
                                               const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
-                                              bool relu, double count, double eps) {
+                                              double slope, double count, double eps) {
   check_bf16_nhwc(dout, "dout"); check_bf16_nhwc(out, "out"); check_bf16_nhwc(y, "y"); check_channels(y);
   TORCH_CHECK(dout.sizes() == y.sizes() && out.sizes() == y.sizes(), "shape mismatch");
   TORCH_CHECK(stats.numel() == 2 * y.size(3) && opt_f32(stats, "stats"), "stats");
@@ -239,7 +239,7 @@ std::vector<at::Tensor> bn_res_act_bwd_reduce(const at::Tensor& dout, const at::
   at::Tensor sums = at::zeros({2, y.size(3)}, stats.options());
   mine::launch_bn_res_act_bwd_reduce(dout.data_ptr(), out.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), g.data_ptr(),
                                      sums.data_ptr<float>(), (size_t)(y.numel() / y.size(3)), (int)y.size(3),
-                                     relu ? 1 : 0, (float)(1.0 / count), (float)eps, cur_stream());
+                                     (float)slope, (float)(1.0 / count), (float)eps, cur_stream());
   return {g, sums};
 }
 

@@ -1,7 +1,8 @@
 // Memory-bound companions of the conv engine for the ResNet encoder (NHWC bf16, 16-byte vectors = 8 channels,
 // C a power of two in [16, 2048]).  Same structure as decoder_elem.cu without the padded-buffer bookkeeping:
 //
-//   bn_res_act_fwd        : out = [relu](BN(y) [+ residual]) from the conv epilogue's batch sums - replaces ATen
+//   bn_res_act_fwd        : out = act(BN(y) [+ residual]) from the conv epilogue's batch sums; act(v) = v > 0 ? v :
+//                           slope * v covers ReLU (0), LeakyReLU (0.1) and identity (1) - replaces ATen
 //                           batch_norm_elemt + add + relu (three passes) with one read of y (+ residual), one write.
 //   bn_res_act_bwd_reduce : g = dout * [out > 0] (also the gradient of the residual branch) and the two BatchNorm
 //                           backward sums per channel; the apply step is bn_bwd_apply of decoder_elem.cu.
@@ -63,7 +64,7 @@ __device__ __forceinline__ Walk make_walk(unsigned total, int C) {
 __global__ void __launch_bounds__(256) bn_res_act_fwd_kernel(
     const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out,
-    unsigned total, int C, int relu, float inv_count, float eps) {
+    unsigned total, int C, float slope, float inv_count, float eps) {
   const Walk w = make_walk(total, C);
   if (!w.active) return;
   float a[8], b[8];
@@ -85,10 +86,8 @@ __global__ void __launch_bounds__(256) bn_res_act_fwd_kernel(
 #pragma unroll
       for (int j = 0; j < 8; ++j) v.f[j] += r.f[j];
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v.f[j] = v.f[j] > 0.f ? v.f[j] : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) v.f[j] = v.f[j] > 0.f ? v.f[j] : slope * v.f[j];
     st8(out + o, v);
   }
 }
@@ -110,7 +109,7 @@ __device__ __forceinline__ void publish_sums(float* s_sum, float* __restrict__ s
 __global__ void __launch_bounds__(256) bn_res_act_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ y,
     const float* __restrict__ stats, __nv_bfloat16* __restrict__ g_out, float* __restrict__ sums, unsigned total, int C,
-    int relu, float inv_count, float eps) {
+    float slope, float inv_count, float eps) {
   extern __shared__ float s_sum[];       // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
   __syncthreads();
@@ -128,10 +127,10 @@ __global__ void __launch_bounds__(256) bn_res_act_bwd_reduce_kernel(
     for (unsigned i = w.i0; i < w.total; i += w.stride) {
       const size_t o = (size_t)i * 8;
       V8 g = ld8(dout + o);
-      if (relu) {
+      if (slope != 1.f) {
         const V8 a = ld8(out + o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g.f[j] = a.f[j] > 0.f ? g.f[j] : 0.f;
+        for (int j = 0; j < 8; ++j) g.f[j] = a.f[j] > 0.f ? g.f[j] : slope * g.f[j];
       }
       const V8 yv = ld8(y + o);
 #pragma unroll
@@ -190,20 +189,20 @@ int blocks_for(size_t total, int C, int cap) {
 }  // namespace
 
 void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
-                           void* out, size_t npix, int C, int relu, float inv_count, float eps, cudaStream_t stream) {
+                           void* out, size_t npix, int C, float slope, float inv_count, float eps, cudaStream_t stream) {
   const size_t total = npix * (size_t)(C / 8);
   bn_res_act_fwd_kernel<<<blocks_for(total, C, 148 * 16), 256, 0, stream>>>(
       (const __nv_bfloat16*)y, stats, gamma, beta, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (unsigned)total, C,
-      relu, inv_count, eps);
+      slope, inv_count, eps);
 }
 
 void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void* y, const float* stats, void* g_out,
-                                  float* sums, size_t npix, int C, int relu, float inv_count, float eps,
+                                  float* sums, size_t npix, int C, float slope, float inv_count, float eps,
                                   cudaStream_t stream) {
   const size_t total = npix * (size_t)(C / 8);
   bn_res_act_bwd_reduce_kernel<<<blocks_for(total, C, 148 * 8), 256, 2 * C * sizeof(float), stream>>>(
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)y, stats, (__nv_bfloat16*)g_out, sums,
-      (unsigned)total, C, relu, inv_count, eps);
+      (unsigned)total, C, slope, inv_count, eps);
 }
 
 void launch_bn_update_running(const float* stats, float* running_mean, float* running_var, long long* num_batches, int C,

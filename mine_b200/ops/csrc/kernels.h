@@ -76,9 +76,9 @@ const char* launch_head_conv_direct(const void* apad, const float* wpk, const fl
 namespace mine {
 // ---- encoder_elem.cu (unpadded NHWC bf16, C a power of two in [16, 2048]) -------------------------------
 void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
-                           void* out, size_t npix, int C, int relu, float inv_count, float eps, cudaStream_t stream);
+                           void* out, size_t npix, int C, float slope, float inv_count, float eps, cudaStream_t stream);
 void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void* y, const float* stats, void* g_out,
-                                  float* sums, size_t npix, int C, int relu, float inv_count, float eps,
+                                  float* sums, size_t npix, int C, float slope, float inv_count, float eps,
                                   cudaStream_t stream);
 void launch_channel_stats(const void* y, float* sums, size_t npix, int C, cudaStream_t stream);
 void launch_bn_update_running(const float* stats, float* running_mean, float* running_var, long long* num_batches, int C,

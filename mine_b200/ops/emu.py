@@ -178,23 +178,23 @@ def head_bwd(g_mpi, mpi, sign, use_alpha):
 
 
 # ---- encoder companions (csrc/encoder_elem.cu) ------------------------------------------------------------------
-def bn_res_act_fwd(y, stats, gamma, beta, residual, relu, count, eps):
-    """``[relu](BN(y) [+ residual])`` on an unpadded NHWC tensor."""
+def bn_res_act_fwd(y, stats, gamma, beta, residual, slope, count, eps):
+    """``act(BN(y) [+ residual])`` on an unpadded NHWC tensor; ``act(v) = v if v > 0 else slope * v``
+    (0: ReLU, 0.1: LeakyReLU, 1: identity)."""
     _, _, a, b = _bn_coef(stats.float(), gamma.float(), beta.float(), count, eps)
     u = y.float() * a + b
     if residual is not None:
         u = u + residual.float()
-    if relu:
-        u = torch.relu(u)
+    u = torch.where(u > 0, u, u * slope)
     return u.to(y.dtype)
 
 
-def bn_res_act_bwd_reduce(dout, out, y, stats, gamma, beta, relu, count, eps):
-    """``g = dout * [out > 0]`` (also the gradient of the residual branch) and ``[sum g, sum g*xhat]``."""
+def bn_res_act_bwd_reduce(dout, out, y, stats, gamma, beta, slope, count, eps):
+    """``g = dout * act'`` (also the gradient of the residual branch) and ``[sum g, sum g*xhat]``."""
     mean, invstd, _, _ = _bn_coef(stats.float(), gamma.float(), beta.float(), count, eps)
     g = dout.float()
-    if relu:
-        g = g * (out.float() > 0).to(g.dtype)
+    if slope != 1.0:
+        g = torch.where(out.float() > 0, g, g * slope)
     xhat = (y.float() - mean) * invstd
     sums = torch.stack([g.sum(dim=(0, 1, 2)), (g * xhat).sum(dim=(0, 1, 2))])
     return [g.to(y.dtype), sums]

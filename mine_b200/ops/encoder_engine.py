@@ -172,11 +172,16 @@ class Conv(torch.autograd.Function):
         return dx, dw, None, None
 
 
+RELU, LEAKY, IDENTITY = 0.0, 0.1, 1.0        # activation slopes: act(v) = v if v > 0 else slope * v
+
+
 class BNAct(torch.autograd.Function):
-    """``a = [relu](BN(y) [+ residual])`` from the conv epilogue's batch sums; training or running statistics."""
+    """``a = act(BN(y) [+ residual])`` from the conv epilogue's batch sums; training or running statistics.
+    ``relu``: ``True`` / ``False`` (ReLU / none) or the negative slope of a LeakyReLU."""
 
     @staticmethod
     def forward(ctx, y, stats, gamma, beta, residual, relu, bn, reducer):
+        slope = (RELU if relu else IDENTITY) if isinstance(relu, bool) else float(relu)
         training = bn is None or bn.training
         count = float(y.shape[0] * y.shape[1] * y.shape[2])
         if training:
@@ -190,19 +195,19 @@ class BNAct(torch.autograd.Function):
             rm, rv = bn.running_mean.float(), bn.running_var.float()
             stats = torch.stack([rm * count, (rv + rm * rm) * count]).contiguous()
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        a = ext().bn_res_act_fwd(y, stats, g32, b32, residual, bool(relu), count, BN_EPS)
+        a = ext().bn_res_act_fwd(y, stats, g32, b32, residual, slope, count, BN_EPS)
         _count()
         if bn is not None and training:
             E.update_running_stats(bn, stats, count)
         ctx.save_for_backward(y, a, stats, g32, b32)
-        ctx.cfg = (bool(relu), count, reducer, residual is not None, training)
+        ctx.cfg = (slope, count, reducer, residual is not None, training)
         return a
 
     @staticmethod
     def backward(ctx, da):
         y, a, stats, g32, b32 = ctx.saved_tensors
-        relu, count, reducer, has_res, training = ctx.cfg
-        g, sums = ext().bn_res_act_bwd_reduce(da.contiguous(), a, y, stats, g32, b32, relu, count, BN_EPS)
+        slope, count, reducer, has_res, training = ctx.cfg
+        g, sums = ext().bn_res_act_bwd_reduce(da.contiguous(), a, y, stats, g32, b32, slope, count, BN_EPS)
         dgamma, dbeta = sums[1].clone(), sums[0].clone()
         if not training:             # frozen statistics: BN is a per-channel affine map
             sums = torch.zeros_like(sums)

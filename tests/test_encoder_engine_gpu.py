@@ -59,8 +59,9 @@ def test_encoder_conv_directions(k, stride, n, h, w, ci, co):
     assert _rel2(EE.conv_wgrad(dyb, _nhwc(x.detach()).to(torch.bfloat16), k, stride), wt.grad) < 6e-3
 
 
-@pytest.mark.parametrize("c,relu,res", [(64, True, False), (256, True, True), (2048, False, False), (1024, True, True)])
+@pytest.mark.parametrize("c,relu,res", [(64, 0.0, False), (256, 0.0, True), (2048, 1.0, False), (1024, 0.1, True)])
 def test_encoder_elementwise_match_specification(c, relu, res):
+    """``relu`` is the activation slope: 0 = ReLU, 0.1 = LeakyReLU, 1 = identity."""
     from mine_b200.ops import conv_engine as E
     from mine_b200.ops import emu
     n, h, w = 2, 12, 20
