@@ -387,8 +387,13 @@ class ConvEngine:
         else:
             with torch.autocast(**amp):
                 feats = self.backbone(src_imgs.contiguous(memory_format=torch.channels_last))
-        with torch.autocast(**amp):
-            top = dec.receptive_field_extension(feats[-1])
+        own_convs = self.encoder_mode == "tcgen05"          # no library convolution anywhere on the prediction path
+        if own_convs:
+            from . import encoder_engine as EE
+            top = EE.receptive_field_extension(dec, feats[-1], self._reducer())
+        else:
+            with torch.autocast(**amp):
+                top = dec.receptive_field_extension(feats[-1])
         emb = dec.embed(disparity).float()                                       # [N, E]
         reducer = self._reducer()
         use_alpha = bool(dec.use_alpha)
@@ -397,7 +402,9 @@ class ConvEngine:
             wp, ws, we = blk.split_weights()
             bias = blk.conv.conv.bias
             smap = None
-            if feat is not None:
+            if feat is not None and own_convs:
+                smap = EE.shared_skip_map(feat, ws)                               # [B,H,W,Co] fp32
+            elif feat is not None:
                 with torch.autocast(**amp):
                     smap = F.conv2d(F.pad(feat, (1, 1, 1, 1), mode="reflect"), ws)
                 smap = smap.permute(0, 2, 3, 1).float().contiguous()            # [B,H,W,Co] fp32

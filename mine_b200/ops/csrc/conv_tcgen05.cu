@@ -736,6 +736,7 @@ const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
   p.co_blocks = (p.Co + 127) / 128;
   p.NB = p.Ci < 128 ? p.Ci : 128;                        // N per accumulator
   p.b_slabs = p.NB / p.b_cb;
+  if (p.Ci % p.NB) return "Ci must be <= 128 or a multiple of 128";
   p.ci_blocks = p.Ci / p.NB;
   p.taps_per_chunk = 512 / p.NB;
   if (p.taps_per_chunk > p.T) p.taps_per_chunk = p.T;

@@ -12,8 +12,10 @@ forward, data gradient and weight gradient - is a tap table for ``conv_taps`` / 
 
 BatchNorm statistics come out of the conv epilogue (per-channel sum / sum of squares); normalise + residual add +
 ReLU is one elementwise kernel, its backward two (reduce, apply) with the cross-GPU reduction of the 2C sums in
-between - the same structure as the decoder layers.  Only the 7x7 stem convolution (3 input channels, 0.6 % of the
-encoder FLOPs) and the max-pool stay on library kernels.
+between - the same structure as the decoder layers.  The 7x7 stem runs as a single-tap GEMM on an unfolded image,
+and the decoder's per-image convolutions (receptive-field extension, shared skip maps) use the same entry points,
+so in this mode no library convolution is left on the prediction path (max-pool / nearest upsampling / unfold are
+framework data-movement ops).
 
 Reference semantics: ``network/monodepth2/resnet_encoder.py:88-108`` (torchvision ResNet trunk, five outputs).
 Status: validated against the ``nn.Module`` encoder through the kernel specification (``ops/emu.py``,
@@ -135,6 +137,8 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, k: int, stride: int) -> torch.
     """fp32 ``[Co,Ci,k,k]`` weight gradient of :func:`conv_fprop`."""
     n, ho, wo, co = dy.shape
     ci = x.shape[3]
+    if ci > 128 and ci % 128:
+        raise ValueError("wgrad_taps needs Ci <= 128 or a multiple of 128")
     ty, tx = _taps(k)
     dw = torch.zeros((k * k, co, ci), dtype=torch.float32, device=dy.device)
     pix = E._wgrad_pixels(co, ci, ho, wo)
@@ -258,6 +262,104 @@ def conv_bn_act(x, conv, bn, relu=True, residual=None, reducer=None, library_con
 
 
 # ---------------------------------------------------------------------------------------------
+# pieces that make the whole prediction path library-convolution free (MINE_B200_ENCODER=tcgen05)
+# ---------------------------------------------------------------------------------------------
+STEM_K = 256        # 7 * 7 * 3 = 147 im2col columns, zero padded: fprop needs a multiple of the 64-channel K block,
+                    # wgrad_taps a multiple of its 128-column accumulator block
+
+
+class StemConv(torch.autograd.Function):
+    """7x7 / stride 2 / pad 3 convolution of the 3-channel image as ONE GEMM tap: the image is unfolded into
+    ``[N, H/2, W/2, 147 -> 256]`` rows (a 25 MB gather at 384x256, no arithmetic) and multiplied with the
+    ``[Co, 256]`` weight matrix by ``conv_taps`` (BatchNorm sums in the epilogue).  The image needs no gradient."""
+
+    @staticmethod
+    def forward(ctx, x_nchw, w, want_stats):
+        n, _, h, w_ = x_nchw.shape
+        co = w.shape[0]
+        ho, wo = _out_size(h, 7, 2), _out_size(w_, 7, 2)
+        cols = F.unfold(x_nchw.float(), 7, padding=3, stride=2)                       # [N, 147, Ho*Wo], (c, ky, kx) order
+        a = torch.zeros((n, ho, wo, STEM_K), dtype=E.ACT_DTYPE, device=x_nchw.device)
+        a[..., :147] = cols.transpose(1, 2).reshape(n, ho, wo, 147).to(E.ACT_DTYPE)
+        wp = torch.zeros((1, co, STEM_K), dtype=E.ACT_DTYPE, device=w.device)
+        wp[0, :, :147] = w.detach().reshape(co, 147).to(E.ACT_DTYPE)
+        stats = torch.zeros((2, co), dtype=torch.float32, device=w.device) if want_stats else None
+        y = torch.empty((n, ho, wo, co), dtype=E.ACT_DTYPE, device=w.device)
+        th, tw = pick_tile(ho, wo)
+        ext().conv_taps(a, wp, y, ho, wo, 1, 1, [0], [0], 1, co, 1, 1, [0], [0], False, None, None, None, 1, stats, 0,
+                        False, None, th, tw)
+        _count(6)
+        ctx.save_for_backward(a)
+        ctx.wshape = tuple(w.shape)
+        if stats is None:
+            stats = torch.empty(0, device=w.device)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        (a,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, ho, wo, co = dy.shape
+        dw = torch.zeros((1, co, STEM_K), dtype=torch.float32, device=dy.device)
+        th, tw = pick_tile(ho, wo, E._wgrad_pixels(co, STEM_K, ho, wo))
+        ext().wgrad_taps(dy, a, dw, ho, wo, 1, 1, [0], [0], 1, [0], [0], th, tw, 1)
+        _count(2)
+        return None, dw[0, :, :147].reshape(ctx.wshape), None
+
+
+class SharedConv(torch.autograd.Function):
+    """Per-image skip-feature convolution of the factorised decoder: ``conv3x3(xpad) -> fp32 [B,H,W,Co]`` (the map the
+    per-plane conv epilogue adds to every plane); ``xpad`` is the reflection-padded NHWC feature map."""
+
+    @staticmethod
+    def forward(ctx, xpad, w):
+        n, hp, wp_, _ = xpad.shape
+        out = torch.empty((n, hp - 2, wp_ - 2, w.shape[0]), dtype=torch.float32, device=xpad.device)
+        E.conv_same_raw(xpad, w, out=out)
+        ctx.save_for_backward(xpad, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dmap):
+        xpad, w = ctx.saved_tensors
+        dy = dmap.to(E.ACT_DTYPE).contiguous()
+        dw = E.wgrad_same_raw(dy, xpad).to(w.dtype) if ctx.needs_input_grad[1] else None
+        dx = E.dgrad_same_raw(dy, w) if ctx.needs_input_grad[0] else None
+        return dx, dw
+
+
+def _pool_nhwc(x: torch.Tensor) -> torch.Tensor:
+    return F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+
+
+def _upsample_nhwc(x: torch.Tensor, size) -> torch.Tensor:
+    if tuple(x.shape[1:3]) == tuple(size):
+        return x
+    return F.interpolate(x.permute(0, 3, 1, 2), size=tuple(size), mode="nearest").permute(0, 2, 3, 1).contiguous()
+
+
+def receptive_field_extension(dec, top_nchw: torch.Tensor, reducer=None) -> torch.Tensor:
+    """``DepthDecoder.receptive_field_extension`` (reference ``depth_decoder.py:55-61,96-101``) on the engine:
+    pool -> 1x1 -> pool -> 3x3 -> up -> 3x3 -> up -> 1x1, every conv followed by BN + LeakyReLU(0.1)."""
+    top = top_nchw.permute(0, 2, 3, 1).to(E.ACT_DTYPE).contiguous()
+
+    def layer(x, blk):
+        y, stats = Conv.apply(x, blk[0].weight, 1, blk[1].training)
+        return BNAct.apply(y, stats, blk[1].weight, blk[1].bias, None, LEAKY, blk[1], reducer)
+    d1 = layer(_pool_nhwc(top), dec.conv_down1)
+    d2 = layer(_pool_nhwc(d1), dec.conv_down2)
+    u1 = layer(_upsample_nhwc(d2, d1.shape[1:3]), dec.conv_up1)
+    return layer(_upsample_nhwc(u1, top.shape[1:3]), dec.conv_up2).permute(0, 3, 1, 2)
+
+
+def shared_skip_map(feat_nchw: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``conv3x3(reflect_pad(feat))`` as the fp32 NHWC map the plane-conv epilogue consumes."""
+    x = F.pad(feat_nchw.float(), (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1).to(E.ACT_DTYPE).contiguous()
+    return SharedConv.apply(x, w)
+
+
+# ---------------------------------------------------------------------------------------------
 # driver
 # ---------------------------------------------------------------------------------------------
 class EncoderEngine:
@@ -288,11 +390,15 @@ class EncoderEngine:
         bb, e = self.backbone, self.backbone.encoder
         reducer = self._reducer()
         x = (img - bb.img_mean.to(img.dtype)) / bb.img_std.to(img.dtype)
-        amp = dict(device_type=img.device.type, dtype=torch.bfloat16, enabled=img.is_cuda and E.ACT_DTYPE == torch.bfloat16)
-        with torch.autocast(**amp):                                # stem: 7x7/2 on 3 channels stays a library conv
-            y = F.conv2d(x.contiguous(memory_format=torch.channels_last), e.conv1.weight, None, 2, 3)
-        y = y.permute(0, 2, 3, 1).to(E.ACT_DTYPE).contiguous()
-        c1 = BNAct.apply(y, torch.empty(0, device=y.device), e.bn1.weight, e.bn1.bias, None, True, e.bn1, reducer)
+        if self.library_conv or e.conv1.weight.shape[1] != 3:
+            amp = dict(device_type=img.device.type, dtype=torch.bfloat16,
+                       enabled=img.is_cuda and E.ACT_DTYPE == torch.bfloat16)
+            with torch.autocast(**amp):
+                y = F.conv2d(x.contiguous(memory_format=torch.channels_last), e.conv1.weight, None, 2, 3)
+            y, stats = y.permute(0, 2, 3, 1).to(E.ACT_DTYPE).contiguous(), torch.empty(0, device=img.device)
+        else:                                                      # stem as one im2col GEMM tap on the engine
+            y, stats = StemConv.apply(x, e.conv1.weight, e.bn1.training)
+        c1 = BNAct.apply(y, stats, e.bn1.weight, e.bn1.bias, None, True, e.bn1, reducer)
         x = F.max_pool2d(c1.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
         feats = [c1]
         for li in range(1, 5):

@@ -133,3 +133,57 @@ def test_encoder_engine_resnet50_forward_matches_library_encoder():
             refs = enc(img.contiguous(memory_format=torch.channels_last))
     for i, (o, r) in enumerate(zip(outs, refs)):
         assert o.shape == r.shape and _rel2(o, r) < 6e-2, (i, _rel2(o, r))     # measured in round 1: <= 3.7e-2
+
+
+def test_stem_as_single_tap_gemm():
+    from mine_b200.ops.encoder_engine import StemConv
+    x = _bf(_rand((2, 3, 128, 192), 0)).requires_grad_(False)
+    wt = _bf(_rand((64, 3, 7, 7), 1, 0.1)).requires_grad_()
+    ref = F.conv2d(x, wt, None, 2, 3)
+    y, stats = StemConv.apply(x, wt, True)
+    assert _rel2(_nchw(y), ref) < 6e-3
+    assert _rel2(stats[1], (ref * ref).sum(dim=(0, 2, 3))) < 5e-3
+    dy = _bf(_rand(ref.shape, 2))
+    ref.backward(dy)
+    want = wt.grad.clone()
+    wt.grad = None
+    (y.float() * _nhwc(dy)).sum().backward()
+    assert _rel2(wt.grad, want) < 1e-2
+
+
+def test_library_free_prediction_matches_specification():
+    """``ConvEngine(encoder_mode='tcgen05')``: stem, trunk, receptive-field extension, shared skip maps and the
+    per-plane decoder all on the engine - kernels vs the same orchestration through the specification."""
+    from mine_b200.models.decoder import DepthDecoder
+    from mine_b200.models.encoder import ResnetEncoder
+    from mine_b200.ops import conv_engine as E
+    torch.manual_seed(0)
+    enc, dec = ResnetEncoder(18, False).cuda(), DepthDecoder(num_ch_enc=[64, 64, 128, 256, 512]).cuda()
+    img = torch.rand(2, 3, 256, 256, device="cuda")
+    disp = torch.rand(2, 4, device="cuda") * 0.8 + 0.1
+    state = ({k: v.clone() for k, v in enc.state_dict().items()}, {k: v.clone() for k, v in dec.state_dict().items()})
+
+    def run():
+        enc.load_state_dict(state[0]); dec.load_state_dict(state[1])
+        for p in list(enc.parameters()) + list(dec.parameters()):
+            p.grad = None
+        outs = E.ConvEngine(enc, dec, {}, torch.device("cuda"), encoder_mode="tcgen05").predict(img, disp)
+        torch.manual_seed(1)
+        gouts = [torch.randn_like(o) for o in outs]
+        for g in gouts:
+            g[..., 3] = 0
+        sum((o * g).sum() for o, g in zip(outs, gouts)).backward()
+        grads = {k: p.grad.clone() for k, p in list(dec.named_parameters()) + list(enc.named_parameters())
+                 if p.grad is not None}
+        return [o.detach() for o in outs], grads
+    outs, grads = run()
+    E.use_emulator(True)
+    try:
+        ref_outs, ref_grads = run()
+    finally:
+        E.use_emulator(False)
+    for i, (o, r) in enumerate(zip(outs, ref_outs)):
+        assert _rel2(o, r) < 3e-2, (i, _rel2(o, r))
+    bad = [(k, round(_rel2(grads[k], ref_grads[k]), 3)) for k in grads
+           if not k.endswith("conv.conv.bias") and _rel2(grads[k], ref_grads[k]) > 0.15]
+    assert len(bad) <= 3, bad[:10]
