@@ -87,6 +87,14 @@ def test_train_cli_on_llff_layout_with_heldout_split(tmp_path):
     assert os.path.exists(os.path.join(out, "checkpoint_000000000002.pth"))       # written after the evaluation pass
     log = open(os.path.join(out, "training.log")).read()
     assert "number of images: 6" in log and "number of images: 2" in log and "val_psnr_tgt" in log
+    # stand-alone evaluation of the checkpoint on the held-out split
+    r = subprocess.run([sys.executable, os.path.join(REPO, "evaluate.py"), "--checkpoint_path",
+                        os.path.join(out, "checkpoint_latest.pth"), "--device", "cpu", "--output", str(tmp_path / "m.json")],
+                       cwd=REPO, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.loads(open(tmp_path / "m.json").read())
+    assert res["num_images"] == 2 and 5.0 < res["metrics"]["psnr_tgt"] < 60.0
+    assert set(res["metrics"]) >= {"loss_rgb_tgt", "loss_ssim_tgt", "lpips_tgt", "psnr_tgt"}
     # the default ratio points at folders that do not exist here: fail loudly instead of training on nothing
     extra["data.img_pre_downsample_ratio"] = 7.875
     r = subprocess.run(cmd + ["--extra_config", json.dumps(extra)], cwd=REPO, env=env, capture_output=True, text=True,
