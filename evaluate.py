@@ -49,8 +49,10 @@ def main(argv=None):
     task = SynthesisTask(config=config, logger=logger)
     task.run_eval(val_loader)
     n = max(m.count for m in task.val_losses.values())
-    line = json.dumps({"checkpoint": os.path.abspath(args.checkpoint_path), "num_images": int(n),
-                       "metrics": {k: m.avg for k, m in task.val_losses.items()}})
+    metrics = {k: m.avg for k, m in task.val_losses.items()}
+    if getattr(task, "lpips", None) is None:
+        metrics["lpips_tgt"] = None              # no LPIPS weights on this machine (MINE_LPIPS_WEIGHTS): not measured
+    line = json.dumps({"checkpoint": os.path.abspath(args.checkpoint_path), "num_images": int(n), "metrics": metrics})
     print(line)
     if args.output:
         with open(args.output, "w") as f:
