@@ -332,3 +332,17 @@ def test_llff_dataset_values_match_reference_dataset(tmp_path, ref):
         assert np.array_equal(np.asarray(it["xyzs_ids"]), np.asarray(rec["xyzs_ids"]))
         assert np.allclose(np.asarray(it["xyzs"]), rec["xyzs"], atol=1e-5)
         assert np.allclose(np.asarray(it["depths"]), rec["depths"], atol=1e-5)
+
+
+def test_trajectories_match_reference_path_planning(ref):
+    """Camera paths of the video generator vs the upstream ``path_planning`` (scipy splines there, closed form here)."""
+    try:
+        theirs = ref.load("visualizations.image_to_video").path_planning
+    except Exception as e:
+        pytest.skip("reference video module does not import here: %r" % (e,))
+    from visualizations.image_to_video import path_planning
+    for kind, n in (("straight-line", 30), ("double-straight-line", 90), ("circle", 60)):
+        a = path_planning(n, 0.1, -0.05, -0.3, kind)
+        b = theirs(n, 0.1, -0.05, -0.3, path_type=kind)
+        for u, v in zip(a, b):
+            assert np.asarray(u).shape == np.asarray(v).shape and np.allclose(u, v, atol=1e-9), kind
