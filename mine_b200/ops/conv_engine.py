@@ -96,11 +96,24 @@ def pack_up(w: torch.Tensor) -> torch.Tensor:
     return wp.reshape(4, 4, w.shape[0], w.shape[1])
 
 
+_FOLD_CACHE: Dict = {}
+
+
+def _fold_matrix(device, dtype) -> torch.Tensor:
+    """``[9, 16]``: which of the 16 (phase, tap) gradients of the sub-pixel form add up to each 3x3 tap."""
+    key = (str(device), dtype)
+    if key not in _FOLD_CACHE:
+        m = _PHASE                                                     # [p, a, k]
+        f = torch.einsum("pak,qbl->klpqab", m, m).reshape(9, 16)
+        _FOLD_CACHE[key] = f.to(device, dtype)
+    return _FOLD_CACHE[key]
+
+
 def unpack_up_grad(dwp: torch.Tensor) -> torch.Tensor:
-    """adjoint of :func:`pack_up`: [4,4,Co,Ci] -> [Co,Ci,3,3]."""
-    m = _phase(dwp.device, dwp.dtype)
+    """adjoint of :func:`pack_up`: [4,4,Co,Ci] -> [Co,Ci,3,3] (one small GEMM with a constant 9x16 matrix)."""
     co, ci = dwp.shape[-2:]
-    return torch.einsum("pak,qbl,pqaboi->oikl", m, m, dwp.reshape(2, 2, 2, 2, co, ci))
+    dw9 = _fold_matrix(dwp.device, dwp.dtype) @ dwp.reshape(16, co * ci)
+    return dw9.reshape(3, 3, co, ci).permute(2, 3, 0, 1)
 
 
 def pack(w: torch.Tensor, mode: int) -> torch.Tensor:
@@ -271,9 +284,11 @@ class PlaneConvBNAct(torch.autograd.Function):
         up, planes, pad_out, count, reducer, has_cb, has_pb, has_sm = ctx.cfg
         dapad = dapad.contiguous()
         g, sums = ext().bn_act_bwd_reduce(dapad, y, stats, g32, b32, pad_out, count, BN_EPS)
-        dgamma, dbeta = sums[1].clone(), sums[0].clone()
-        if reducer is not None:
+        if reducer is not None:          # the local sums are the parameter gradients; the reduction is in place
+            dgamma, dbeta = sums[1].clone(), sums[0].clone()
             sums = reducer(sums.reshape(-1)).reshape(2, -1).contiguous()
+        else:
+            dgamma, dbeta = sums[1], sums[0]
         dy, dshared, dpb = ext().bn_bwd_apply(g, y, stats, g32, sums, planes, has_sm, has_pb, count, BN_EPS)
         _count(2)
         dcb = None

@@ -212,10 +212,11 @@ class BNAct(torch.autograd.Function):
         y, a, stats, g32, b32 = ctx.saved_tensors
         slope, count, reducer, has_res, training = ctx.cfg
         g, sums = ext().bn_res_act_bwd_reduce(da.contiguous(), a, y, stats, g32, b32, slope, count, BN_EPS)
-        dgamma, dbeta = sums[1].clone(), sums[0].clone()
+        dgamma, dbeta = sums[1], sums[0]
         if not training:             # frozen statistics: BN is a per-channel affine map
             sums = torch.zeros_like(sums)
-        elif reducer is not None:
+        elif reducer is not None:    # the local sums are the parameter gradients; the reduction is in place
+            dgamma, dbeta = sums[1].clone(), sums[0].clone()
             sums = reducer(sums.reshape(-1)).reshape(2, -1).contiguous()
         dy = ext().bn_bwd_apply(g, y, stats, g32, sums, 1, False, False, count, BN_EPS)[0]
         _count(2)
