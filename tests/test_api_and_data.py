@@ -346,3 +346,26 @@ def test_trajectories_match_reference_path_planning(ref):
         b = theirs(n, 0.1, -0.05, -0.3, path_type=kind)
         for u, v in zip(a, b):
             assert np.asarray(u).shape == np.asarray(v).shape and np.allclose(u, v, atol=1e-9), kind
+
+
+@pytest.mark.parametrize("dataset", ["realestate10k", "kitti_raw", "flowers", "dtu"])
+def test_every_dataset_preset_trains_one_step(dataset):
+    """Each upstream YAML drives a training step (resolution / plane count scaled down for the CPU tier).  For
+    kitti_raw / flowers / dtu the poses are metric: no scale calibration, and the sparse-disparity terms carry zero
+    weight (reference ``synthesis_task.py:213-214, 305-323``)."""
+    from synthesis_task import SynthesisTask
+    name = {"realestate10k": "realestate"}.get(dataset, dataset)
+    cfg = C.build_config(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs",
+                                      "params_%s.yaml" % name),
+                         '{"data.img_w": 96, "data.img_h": 64, "mpi.num_bins_coarse": 3, "data.per_gpu_batch_size": 1, '
+                         '"data.visible_point_count": 16, "model.imagenet_pretrained": false}')
+    cfg.update({"device": torch.device("cpu"), "global_rank": 0})
+    assert cfg["data.name"] == dataset
+    torch.manual_seed(0)
+    task = SynthesisTask(cfg, None)
+    ld = task.train_step(config_batch(cfg))
+    assert torch.isfinite(ld["loss"]) and task.arena.grad.abs().sum() > 0
+    if dataset == "realestate10k":
+        assert float(ld["loss_disp_pt3dsrc"].detach()) > 0
+    else:
+        assert float(ld["loss_disp_pt3dsrc"].detach()) == 0.0 and float(ld["loss_disp_pt3dtgt"].detach()) == 0.0
