@@ -252,6 +252,39 @@ at::Tensor channel_stats(const at::Tensor& y) {
   return sums;
 }
 
+void conv_taps_splitk(const at::Tensor& x, const at::Tensor& wpack, at::Tensor out32, int64_t Hg, int64_t Wg, int64_t T,
+                      std::vector<int64_t> tap_y, std::vector<int64_t> tap_x, int64_t in_stride, int64_t Co, int64_t TH,
+                      int64_t TW, int64_t ksplit) {
+  check_bf16_nhwc(x, "x");
+  TORCH_CHECK(wpack.is_cuda() && wpack.scalar_type() == at::kBFloat16 && wpack.is_contiguous() && wpack.dim() == 3 &&
+                  wpack.size(0) == T && wpack.size(2) == x.size(3), "wpack must be bf16 [T, rows, Ci]");
+  TORCH_CHECK((int64_t)tap_y.size() == T && (int64_t)tap_x.size() == T, "tap table size");
+  TORCH_CHECK(out32.is_cuda() && out32.scalar_type() == at::kFloat && out32.is_contiguous() && out32.dim() == 4 &&
+                  out32.size(0) == x.size(0) && out32.size(1) == Hg && out32.size(2) == Wg && out32.size(3) == Co,
+              "out32 must be a zero-initialised fp32 [N, Hg, Wg, Co] tensor");
+  c10::cuda::CUDAGuard guard(x.device());
+  std::vector<int> ty(tap_y.begin(), tap_y.end()), tx(tap_x.begin(), tap_x.end());
+  const char* err = mine::launch_conv_splitk(x.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2), (int)x.size(3),
+                                             wpack.data_ptr(), (int)wpack.size(1), (int)T, ty.data(), tx.data(),
+                                             (int)in_stride, out32.data_ptr<float>(), (int)Hg, (int)Wg, (int)Co, (int)TH,
+                                             (int)TW, (int)ksplit, cur_stream());
+  TORCH_CHECK(err == nullptr, "conv_taps_splitk: ", err ? err : "");
+}
+
+// fp32 partial-sum tensor -> {bf16 tensor, stats [2, C] (empty when not wanted)}
+std::vector<at::Tensor> splitk_finalize(const at::Tensor& acc, bool want_stats) {
+  TORCH_CHECK(acc.is_cuda() && acc.scalar_type() == at::kFloat && acc.is_contiguous() && acc.dim() == 4, "acc");
+  const int64_t C = acc.size(3);
+  TORCH_CHECK((C & (C - 1)) == 0 && C >= 16 && C <= 2048, "channels must be a power of two in [16, 2048]");
+  TORCH_CHECK(acc.numel() / 8 < (1ll << 31), "tensor too large for 32-bit indexing");
+  c10::cuda::CUDAGuard guard(acc.device());
+  at::Tensor y = at::empty(acc.sizes(), acc.options().dtype(at::kBFloat16));
+  at::Tensor stats = want_stats ? at::zeros({2, C}, acc.options()) : at::empty({0}, acc.options());
+  mine::launch_splitk_finalize(acc.data_ptr<float>(), y.data_ptr(), want_stats ? stats.data_ptr<float>() : nullptr,
+                               (size_t)(acc.numel() / C), (int)C, cur_stream());
+  return {y, stats};
+}
+
 void bn_update_running(const at::Tensor& stats, at::Tensor running_mean, at::Tensor running_var,
                        at::Tensor num_batches_tracked, double count, double momentum) {
   const int64_t C = running_mean.numel();
@@ -280,4 +313,6 @@ void register_conv(pybind11::module_& m) {
   m.def("channel_stats", &channel_stats);
   m.def("head_conv_direct", &head_conv_direct);
   m.def("bn_update_running", &bn_update_running);
+  m.def("conv_taps_splitk", &conv_taps_splitk);
+  m.def("splitk_finalize", &splitk_finalize);
 }

@@ -58,6 +58,14 @@ void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, v
 }  // namespace mine
 
 namespace mine {
+// ---- conv_splitk.cu (split-K implicit GEMM for layers with few output tiles; fp32 partial sums + finalize) -------
+const char* launch_conv_splitk(const void* x, int N, int Hi, int Wi, int Ci, const void* wpack, int w_rows, int T,
+                               const int* tap_y, const int* tap_x, int in_stride, float* out32, int Hg, int Wg, int Co,
+                               int TH, int TW, int ksplit, cudaStream_t stream);
+void launch_splitk_finalize(const float* acc, void* y, float* stats, size_t npix, int C, cudaStream_t stream);
+}  // namespace mine
+
+namespace mine {
 // ---- sparse.cu (sparse-point disparity supervision: projection, gather, scale calibration, log-L1) -------
 void launch_sparse_point_fwd(const float* disp, const float* K, const float* xyz, const float* scale_in, int* idx,
                              float* d_syn, float* sgn, float* scale_out, float* loss, int B, int H, int W, int N,

@@ -263,3 +263,20 @@ def sparse_point_bwd(g_loss, g_scale, idx, d_syn, sgn, scale, disp_shape, comput
     grad = torch.zeros((b, h * w), dtype=torch.float32, device=d_syn.device)
     grad.scatter_add_(1, idx.long(), gd)
     return [grad.reshape(disp_shape), grad_scale]
+
+
+# ---- split-K convolution for small maps (csrc/conv_splitk.cu) ----------------------------------------------------
+def conv_taps_splitk(x, wpack, out32, Hg, Wg, T, tap_y, tap_x, in_stride, Co, TH, TW, ksplit):
+    """``out32 += conv_taps(...)`` with one tap group, accumulated in fp32 (the K range is split over CTAs)."""
+    tmp = torch.zeros_like(out32)
+    conv_taps(x, wpack, tmp, Hg, Wg, 1, T, list(tap_y), list(tap_x), in_stride, Co, 1, 1, [0], [0], False, None, None,
+              None, 1, None, 0, False, None, TH, TW)
+    out32 += tmp
+
+
+def splitk_finalize(acc, want_stats):
+    y = acc.to(ACT_DTYPE)
+    if not want_stats:
+        return [y, torch.empty(0, device=acc.device)]
+    a = acc.float()
+    return [y, torch.stack([a.sum(dim=(0, 1, 2)), (a * a).sum(dim=(0, 1, 2))])]

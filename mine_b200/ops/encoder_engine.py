@@ -26,6 +26,7 @@ Default: ``cudnn`` (library convolutions and ATen BatchNorm under autocast).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -88,18 +89,47 @@ _S2_OX = [px for py in range(2) for px in range(2)]
 # ---------------------------------------------------------------------------------------------
 # raw wrappers
 # ---------------------------------------------------------------------------------------------
+NUM_SMS = 148
+
+
+def split_factor(work_items: int, iters: int) -> int:
+    """K-split for layers whose output tiles cannot fill the machine (``MINE_B200_SPLITK=1``, opt-in): enough CTAs
+    for ~2 per SM, at least 4 (tap, channel-block) iterations per CTA, at most 16 partial sums per output."""
+    if os.environ.get("MINE_B200_SPLITK", "0") != "1" or work_items >= NUM_SMS:
+        return 1
+    ks = min((2 * NUM_SMS + work_items - 1) // work_items, iters // 4, 16)
+    return max(ks, 1)
+
+
+def _taps_conv(x, wpack, hg: int, wg: int, ty, tx, stride: int, co: int, stats) -> torch.Tensor:
+    """One tap group through ``conv_taps`` - or, when the output has too few tiles to fill the GPU and
+    ``MINE_B200_SPLITK=1``, through the split-K kernel (fp32 partial sums) + finalize (bf16 + BatchNorm sums)."""
+    n, ci, t = x.shape[0], x.shape[3], len(ty)
+    th, tw = pick_tile(hg, wg)
+    work = ((hg + th - 1) // th) * ((wg + tw - 1) // tw) * n * (1 if co <= 256 else co // 128)
+    ks = split_factor(work, t * max(1, ci // 64))
+    if ks > 1 and co >= 16 and (co & (co - 1)) == 0:
+        acc = torch.zeros((n, hg, wg, co), dtype=torch.float32, device=x.device)
+        ext().conv_taps_splitk(x, wpack, acc, hg, wg, t, ty, tx, stride, co, th, tw, ks)
+        out, st = ext().splitk_finalize(acc, stats is not None)
+        if stats is not None:
+            stats += st
+        _count(3)
+        return out
+    out = torch.empty((n, hg, wg, co), dtype=E.ACT_DTYPE, device=x.device)
+    ext().conv_taps(x, wpack, out, hg, wg, 1, t, ty, tx, stride, co, 1, 1, [0], [0], False, None, None, None, 1, stats, 0,
+                    False, None, th, tw)
+    _count()
+    return out
+
+
 def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int, stats: Optional[torch.Tensor]) -> torch.Tensor:
     """``x [N,H,W,Ci]`` -> ``conv(x, w, stride, padding=k//2) [N,Ho,Wo,Co]``; ``stats [2,Co]`` accumulates BN sums."""
-    n, h, w_, ci = x.shape
+    _, h, w_, _ = x.shape
     co, _, k, _ = w.shape
-    ho, wo = _out_size(h, k, stride), _out_size(w_, k, stride)
     ty, tx = _taps(k)
-    out = torch.empty((n, ho, wo, co), dtype=E.ACT_DTYPE, device=x.device)
-    th, tw = pick_tile(ho, wo)
-    ext().conv_taps(x, _pack_fprop(w), out, ho, wo, 1, k * k, ty, tx, stride, co, 1, 1, [0], [0], False,
-                    None, None, None, 1, stats, 0, False, None, th, tw)
-    _count(2)
-    return out
+    _count()
+    return _taps_conv(x, _pack_fprop(w), _out_size(h, k, stride), _out_size(w_, k, stride), ty, tx, stride, co, stats)
 
 
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, h: int, w_: int) -> torch.Tensor:
@@ -108,12 +138,8 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, h: int, w_: int) 
     ci, k = w.shape[1], w.shape[2]
     if stride == 1:
         ty, tx = _taps(k)
-        out = torch.empty((n, h, w_, ci), dtype=E.ACT_DTYPE, device=dy.device)
-        th, tw = pick_tile(h, w_)
-        ext().conv_taps(dy, _pack_dgrad(w), out, h, w_, 1, k * k, [-t for t in ty], [-t for t in tx], 1, ci, 1, 1,
-                        [0], [0], False, None, None, None, 1, None, 0, False, None, th, tw)
-        _count(2)
-        return out
+        _count()
+        return _taps_conv(dy, _pack_dgrad(w), h, w_, [-t for t in ty], [-t for t in tx], 1, ci, None)
     if stride != 2:
         raise ValueError("stride must be 1 or 2")
     if k == 1:

@@ -27,3 +27,5 @@ run_bench bnv2 MINE_B200_BN_REDUCE=v2
 run_bench sparse MINE_B200_SPARSE=fused
 run_bench running MINE_B200_BN_RUNNING=fused
 run_bench all MINE_B200_HEAD=direct MINE_B200_BN_REDUCE=v2 MINE_B200_SPARSE=fused MINE_B200_BN_RUNNING=fused
+run_bench enc_engine MINE_B200_ENCODER=tcgen05
+run_bench enc_splitk MINE_B200_ENCODER=tcgen05 MINE_B200_SPLITK=1

@@ -187,3 +187,23 @@ def test_library_free_prediction_matches_specification():
     bad = [(k, round(_rel2(grads[k], ref_grads[k]), 3)) for k in grads
            if not k.endswith("conv.conv.bias") and _rel2(grads[k], ref_grads[k]) > 0.15]
     assert len(bad) <= 3, bad[:10]
+
+
+@pytest.mark.parametrize("k,stride,n,h,w,ci,co", [(1, 1, 2, 8, 12, 2048, 512), (3, 1, 2, 8, 12, 512, 512),
+                                                  (3, 2, 2, 16, 24, 256, 256), (1, 1, 2, 16, 24, 1024, 256)])
+def test_split_k_convolution(k, stride, n, h, w, ci, co, monkeypatch):
+    """``conv_splitk.cu`` (MINE_B200_SPLITK=1): fprop + BatchNorm sums and the stride-1 data gradient."""
+    from mine_b200.ops import encoder_engine as EE
+    monkeypatch.setenv("MINE_B200_SPLITK", "1")
+    x = _bf(_rand((n, ci, h, w), 0)).requires_grad_()
+    wt = _bf(_rand((co, ci, k, k), 1, (ci * k * k) ** -0.5)).requires_grad_()
+    ref = F.conv2d(x, wt, None, stride, k // 2)
+    stats = torch.zeros(2, co, device="cuda")
+    y = EE.conv_fprop(_nhwc(x.detach()).to(torch.bfloat16), wt.detach(), stride, stats)
+    assert _rel2(_nchw(y), ref) < 6e-3
+    assert _rel2(stats[1], (ref * ref).sum(dim=(0, 2, 3))) < 5e-3
+    if stride == 1:
+        dy = _bf(_rand(ref.shape, 2))
+        ref.backward(dy)
+        got = EE.conv_dgrad(_nhwc(dy).to(torch.bfloat16), wt.detach(), 1, h, w)
+        assert _rel2(_nchw(got), x.grad) < 6e-3

@@ -274,3 +274,22 @@ def test_fused_running_stat_update_matches_framework_ops(monkeypatch):
     E.update_running_stats(b, stats, 96.0)
     assert torch.allclose(a.running_mean, b.running_mean) and torch.allclose(a.running_var, b.running_var)
     assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 1
+
+
+def test_split_k_path_of_encoder_convs(monkeypatch):
+    """MINE_B200_SPLITK=1 routes convolutions with few output tiles through the split-K entry points (fp32 partial
+    sums + finalize); values and BatchNorm sums are those of the single-pass form."""
+    from mine_b200.ops import encoder_engine as EE
+    x = _nhwc(_rand((2, 512, 8, 12), 0))
+    wt = _rand((256, 512, 3, 3), 1, 0.02)
+    monkeypatch.setenv("MINE_B200_SPLITK", "0")
+    s0 = torch.zeros(2, 256)
+    y0 = EE.conv_fprop(x, wt, 1, s0)
+    monkeypatch.setenv("MINE_B200_SPLITK", "1")
+    assert EE.split_factor(2, 72) == 16 and EE.split_factor(400, 72) == 1 and EE.split_factor(8, 8) == 2
+    s1 = torch.zeros(2, 256)
+    y1 = EE.conv_fprop(x, wt, 1, s1)
+    assert torch.allclose(y0, y1, atol=1e-4) and torch.allclose(s0, s1, rtol=1e-4, atol=1e-3)
+    y2 = EE.conv_fprop(x, wt, 2, None)
+    monkeypatch.setenv("MINE_B200_SPLITK", "0")
+    assert torch.allclose(y2, EE.conv_fprop(x, wt, 2, None), atol=1e-4)
