@@ -47,6 +47,9 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--shape", default="llff", choices=sorted(BENCH_SHAPES))
+    p.add_argument("--precision", default=os.environ.get("MINE_B200_PRECISION", "tf32"), choices=["tf32", "bf16"],
+                   help="conv-stack precision of OUR arm: tf32 (default; the reference's class) or bf16 (fast mode)")
+    p.add_argument("--no-fast", action="store_true", help="skip the informational bf16 'fast' line")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-render", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA-graph replay per step")
@@ -182,19 +185,24 @@ def max_over_ranks(ms, device):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
-    sys.path.insert(0, REPO)
+DTYPE_TEXT = {
+    "tf32": "tf32 (fp32 tensors, TF32 tensor-core convolutions with fp32 accumulation - the reference's precision class; "
+            "fp32 BN statistics / render / losses / Adam)",
+    "bf16": "bf16 conv stack (bf16 activations and operands, fp32 accumulation, fp32 master weights, fp32 BN statistics "
+            "/ render / losses / Adam)",
+}
+
+
+def measure_ours(args, shape, ctx, precision, with_e2e, with_render, with_phases):
+    """Build a task at the given conv precision and time it; returns the measurement dict (this rank's view,
+    times already max-reduced over ranks)."""
     import torch
     from mine_b200 import config as cfglib
-    from mine_b200.parallel import bootstrap
-    shape = BENCH_SHAPES[args.shape]
-    rank, local_rank, world = dist_env()
-    ctx = bootstrap.init_distributed()
-    device = ctx.device
+    rank, world, device = ctx.rank, ctx.world_size, ctx.device
     extra = {"data.img_w": shape["w"], "data.img_h": shape["h"], "mpi.num_bins_coarse": shape["planes"],
              "data.per_gpu_batch_size": shape["batch"], "model.imagenet_pretrained": False,
              "training.eval_interval": 10 ** 9, "engine.cuda_graph": not args.no_graph,
-             "engine.comm": os.environ.get("MINE_B200_COMM", "p2p")}
+             "engine.comm": os.environ.get("MINE_B200_COMM", "p2p"), "engine.precision": precision}
     config = cfglib.config_for_dataset(shape["dataset"], extra)
     config.update({"global_rank": ctx.rank, "local_rank": ctx.local_rank, "world_size": ctx.world_size, "device": device})
     torch.manual_seed(1234 + rank)
@@ -207,7 +215,7 @@ def run_ours(args):
     host_batches = make_batches(shape, n_pool, rank, int(config["data.visible_point_count"]))
     dev_batches = [to_device(b, device) for b in host_batches]
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)
-    sampler = ClockSampler(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None else local_rank)
+    sampler = ClockSampler(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None else ctx.local_rank)
 
     def step_dev(i):
         task.train_step(dev_batches[i % n_pool])
@@ -222,48 +230,77 @@ def run_ours(args):
         launches = int(task.launches_per_step) * args.steps
     clocks = sampler.stop(t0, t1)
     ms = max_over_ranks(ms, device)
-
-    result = {
-        "metric": "LLFF 384x256 N=32 training images/sec (whole job, device-timed, max over ranks)"
-        if args.shape == "llff" else f"{args.shape} training images/sec",
-        "impl": "ours",
-        "value": world * shape["batch"] * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 conv stack (fp32 accumulate, fp32 BN stats/render/losses/Adam)",
-        "data": "synthetic source/target pairs of the named shape, random-init weights",
-        "config": {"model": "MINE ResNet-50 encoder + disparity-conditioned MPI decoder (factorised)",
-                   "dataset_shape": f"{shape['dataset']} {shape['w']}x{shape['h']} N={shape['planes']}",
-                   "global_batch": world * shape["batch"], "per_gpu_batch": shape["batch"], "seq_len": shape["planes"],
-                   "parallelism": f"dp{world}", "conv_engine": task.runner.mode, "comm": task.comm.name,
-                   "cuda_graph": task._graph is not None,
-                   "l2": "256 MiB buffer rewritten between steps inside the timed region"},
-        "clocks": clocks, "gpu_launches": launches,
-    }
-
-    if not args.no_e2e:
+    out = {"precision": precision, "ms": ms, "launches": launches, "clocks": clocks, "mode": task.runner.mode,
+           "comm": task.comm.name, "graph": task._graph is not None,
+           "encoder": getattr(getattr(task.runner, "_engine", None), "encoder_mode", "module")}
+    if with_e2e:
         h2d = tree_bytes(host_batches[0])
 
         def step_e2e(i):
             loss = task.train_step(host_batches[i % n_pool])["loss"]
             return float(loss.item())            # D2H read of the step's result
 
-        ms2, _, _ = timed_region(step_e2e, args.steps, 2, device, flush)
+        ms2, _, _ = timed_region(step_e2e, args.steps, 3, device, flush)
         ms2 = max_over_ranks(ms2, device)
-        result["e2e"] = {"value": world * shape["batch"] * args.steps / (ms2 / 1e3), "unit": "images/s",
-                         "ms_per_step": ms2 / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                         "api": "SynthesisTask.train_step(batch in pinned host memory) + loss.item()"}
-
-    if args.profile_phases:
+        out["e2e"] = {"value": world * shape["batch"] * args.steps / (ms2 / 1e3), "unit": "images/s",
+                      "ms_per_step": ms2 / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                      "api": "SynthesisTask.train_step(batch in pinned host memory) + loss.item()"}
+    if with_phases:
         task._graph, task._want_graph = None, False
         task.profiler.enabled = True
         for i in range(5):
             step_dev(i)
-        result["phases_ms"] = task.profiler.summary()
+        out["phases_ms"] = task.profiler.summary()
         task.profiler.enabled = False
+    if with_render and rank == 0:
+        out["render"] = render_bench_ours(task, config, device)
+    if task.grad_sync is not None:
+        task.grad_sync.close()
+    del task, dev_batches, flush
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
 
-    if not args.no_render and rank == 0:
-        result["render"] = render_bench_ours(task, config, device)
 
+def run_ours(args):
+    sys.path.insert(0, REPO)
+    from mine_b200.parallel import bootstrap
+    shape = BENCH_SHAPES[args.shape]
+    rank, local_rank, world = dist_env()
+    ctx = bootstrap.init_distributed()
+    main = measure_ours(args, shape, ctx, args.precision, not args.no_e2e, not args.no_render, args.profile_phases)
+    ms = main["ms"]
+    result = {
+        "metric": "LLFF 384x256 N=32 training images/sec (whole job, device-timed, max over ranks)"
+        if args.shape == "llff" else f"{args.shape} training images/sec",
+        "impl": "ours",
+        "value": world * shape["batch"] * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_TEXT[main["precision"]],
+        "data": "synthetic source/target pairs of the named shape, random-init weights",
+        "config": {"model": "MINE ResNet-50 encoder + disparity-conditioned MPI decoder (factorised)",
+                   "dataset_shape": f"{shape['dataset']} {shape['w']}x{shape['h']} N={shape['planes']}",
+                   "global_batch": world * shape["batch"], "per_gpu_batch": shape["batch"], "seq_len": shape["planes"],
+                   "parallelism": f"dp{world}", "conv_engine": main["mode"], "encoder": main["encoder"],
+                   "precision": main["precision"], "comm": main["comm"], "cuda_graph": main["graph"],
+                   "l2": "256 MiB buffer rewritten between steps inside the timed region"},
+        "clocks": main["clocks"], "gpu_launches": main["launches"],
+    }
+    for k in ("e2e", "phases_ms", "render"):
+        if k in main:
+            result[k] = main[k]
+    if not args.no_fast and args.precision != "bf16":
+        # extra line: the same step in the reduced-precision fast mode (NOT the headline: lower precision than the reference)
+        try:
+            fast = measure_ours(args, shape, ctx, "bf16", not args.no_e2e, False, False)
+            result["fast"] = {"dtype": DTYPE_TEXT["bf16"], "value": world * shape["batch"] * args.steps / (fast["ms"] / 1e3),
+                              "unit": "images/s", "ms_per_step": fast["ms"] / args.steps, "gpu_launches": fast["launches"],
+                              "clocks": fast["clocks"], "note": "lower precision than the reference - informational only"}
+            if "e2e" in fast:
+                result["fast"]["e2e"] = fast["e2e"]
+        except Exception as e:          # never lose the headline because of the informational line
+            result["fast"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         print(json.dumps(result))
     bootstrap.barrier()

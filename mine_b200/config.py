@@ -81,7 +81,8 @@ SCHEMA: Dict[str, tuple] = {
     "training.use_multi_scale": (bool, True),
     "testing.frames_apart": ("any", "random"),      # dead
     # ---- extensions of this framework (absent upstream; all optional) ----
-    "engine.compute_dtype": (str, "bf16"),          # conv stack compute dtype on the CUDA path
+    "engine.precision": (str, "tf32"),              # tf32: fp32 tensors + TF32 tensor-core convs (reference numerics) | bf16: fast mode
+    "engine.compute_dtype": (str, "bf16"),          # deprecated alias, ignored (see engine.precision)
     "engine.cuda_graph": (bool, False),
     "engine.comm": (str, "p2p"),                    # p2p (own kernels over NVLink) | nccl (baseline)
     "engine.resume": (bool, True),                  # restore step/epoch/scheduler/RNG if present

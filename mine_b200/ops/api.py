@@ -123,10 +123,11 @@ def sparse_point_loss(disp_map: torch.Tensor, k: torch.Tensor, xyz: torch.Tensor
                       scale: Optional[torch.Tensor] = None, calibrate: bool = True):
     """``(mean |log(d / scale) - log(1/z)|, scale)`` at the projections of sparse camera-frame points; the scale is
     calibrated from these points when none is given (``calibrate=False``: ones - datasets with metric poses).
-    Default: composition of specification ops; ``MINE_B200_SPARSE=fused`` on CUDA: one kernel per direction."""
+    On CUDA: one kernel per direction (``csrc/sparse.cu``; ``MINE_B200_SPARSE=spec`` selects the ~150-op composition of
+    specification ops instead); off-GPU: the specification ops."""
     if scale is None and not calibrate:
         scale = torch.ones(xyz.shape[0], dtype=torch.float32, device=xyz.device)
-    if _use_kernels(disp_map) and os.environ.get("MINE_B200_SPARSE", "spec") == "fused":
+    if _use_kernels(disp_map) and os.environ.get("MINE_B200_SPARSE", "fused") == "fused":
         from .sparse import sparse_point_loss as fused
         return fused(disp_map, k, xyz, scale)
     disp_gt = torch.reciprocal(xyz[:, 2:, :])

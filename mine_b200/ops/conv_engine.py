@@ -28,10 +28,28 @@ from .counters import LAUNCHES
 
 AVAILABLE = True
 BN_EPS = 1e-5
-ACT_DTYPE = torch.bfloat16      # activation / operand storage type (fp32 only under the emulator, for tight tests)
+# Activation / operand storage type.  Two precisions (``engine.precision``):
+#   "tf32": fp32 NHWC activations and weight packs, tcgen05 ``kind::tf32`` MMAs, fp32 accumulation - the numerics class
+#           of the reference (fp32 tensors, cuDNN TF32 convolutions; it never autocasts).  DEFAULT.
+#   "bf16": bf16 activations / packs, ``kind::f16`` MMAs, fp32 accumulation and fp32 master weights - the fast mode.
+ACT_DTYPE = torch.float32
+PRECISION = "tf32"
 
 _ext = None
 _emulated = False
+
+
+def set_precision(precision: str) -> None:
+    """Select the operand storage type of every engine kernel ("tf32" or "bf16"); process-wide."""
+    global ACT_DTYPE, PRECISION
+    if precision not in ("tf32", "bf16"):
+        raise ValueError("engine.precision must be 'tf32' or 'bf16', got %r" % (precision,))
+    PRECISION = precision
+    ACT_DTYPE = torch.float32 if precision == "tf32" else torch.bfloat16
+    from . import emu
+    emu.ACT_DTYPE = ACT_DTYPE
+    if not _emulated and _ext is not None:
+        _ext.set_operand_size(4 if precision == "tf32" else 2)
 
 
 def use_emulator(flag: bool, dtype: torch.dtype = torch.bfloat16) -> None:
@@ -39,7 +57,10 @@ def use_emulator(flag: bool, dtype: torch.dtype = torch.bfloat16) -> None:
     global _emulated, ACT_DTYPE
     from . import emu
     _emulated = bool(flag)
-    ACT_DTYPE = dtype if flag else torch.bfloat16
+    if flag:
+        ACT_DTYPE = dtype
+    else:
+        ACT_DTYPE = torch.float32 if PRECISION == "tf32" else torch.bfloat16
     emu.ACT_DTYPE = ACT_DTYPE
 
 
@@ -51,6 +72,7 @@ def ext():
     if _ext is None:
         from . import cuda as C
         _ext = C._ext
+        _ext.set_operand_size(4 if ACT_DTYPE == torch.float32 else 2)
     return _ext
 
 
@@ -209,7 +231,8 @@ def dgrad_up_raw(dy, w):
 
 def _wgrad_pixels(co: int, ci: int, h: int, w: int) -> int:
     """Pixels per K step: aim at ~8 KB per TMA box (tiny boxes are issue-bound), keep the tile inside the map."""
-    kp = 8192 // (2 * min(64, max(co, ci)))
+    es = 4 if ACT_DTYPE == torch.float32 else 2
+    kp = 8192 // (es * min(128 // es, max(co, ci)))
     kp = max(32, min(256, kp))
     while kp > 32 and kp > h * w:
         kp //= 2
@@ -304,10 +327,10 @@ class PlaneConvBNAct(torch.autograd.Function):
 
 
 def update_running_stats(bn, stats: torch.Tensor, count: float) -> None:
-    """Momentum update of ``bn``'s buffers from the reduced batch sums ``[2, C]``.  ``MINE_B200_BN_RUNNING=fused``:
-    one kernel (``bn_update_running``, opt-in until measured); default: the equivalent framework ops."""
+    """Momentum update of ``bn``'s buffers from the reduced batch sums ``[2, C]``: one kernel (``bn_update_running``);
+    ``MINE_B200_BN_RUNNING=aten`` selects the equivalent ~11 framework ops."""
     with torch.no_grad():
-        if os.environ.get("MINE_B200_BN_RUNNING", "aten") == "fused" and (_emulated or stats.is_cuda):
+        if os.environ.get("MINE_B200_BN_RUNNING", "fused") == "fused" and (_emulated or stats.is_cuda):
             ext().bn_update_running(stats, bn.running_mean, bn.running_var, bn.num_batches_tracked, float(count),
                                     float(bn.momentum))
             _count()

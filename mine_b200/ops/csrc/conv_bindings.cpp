@@ -10,11 +10,20 @@ namespace {
 
 inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 
-inline void check_bf16_nhwc(const at::Tensor& t, const char* name) {
-  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.is_contiguous() && t.dim() == 4, name,
-              " must be a contiguous CUDA bf16 [N,H,W,C] tensor");
+// Operand storage type of the engine (set once per process by conv_engine.set_precision): 2 = bf16, 4 = fp32 (TF32 math).
+// Only the entry points whose OUTPUT type cannot be inferred from an input (weight packs, head gradient) read it.
+int g_operand_es = 2;
+inline at::ScalarType operand_dtype() { return g_operand_es == 4 ? at::kFloat : at::kBFloat16; }
+
+inline void check_act_nhwc(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && (t.scalar_type() == at::kBFloat16 || t.scalar_type() == at::kFloat) && t.is_contiguous() &&
+                  t.dim() == 4, name, " must be a contiguous CUDA bf16 or fp32 [N,H,W,C] tensor");
   TORCH_CHECK(t.size(3) % 8 == 0, name, ": channels must be a multiple of 8");
   TORCH_CHECK(reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, name, " must be 16-byte aligned");
+}
+inline int esize(const at::Tensor& t) { return t.scalar_type() == at::kFloat ? 4 : 2; }
+inline void check_same_type(const at::Tensor& a, const at::Tensor& b, const char* what) {
+  TORCH_CHECK(a.scalar_type() == b.scalar_type(), what, ": operand dtypes differ");
 }
 inline const float* opt_f32(const c10::optional<at::Tensor>& t, const char* name) {
   if (!t.has_value() || !t->defined()) return nullptr;
@@ -29,9 +38,9 @@ void conv_taps(const at::Tensor& x, const at::Tensor& wpack, at::Tensor out, int
                const c10::optional<at::Tensor>& shared_map, int64_t planes_per_image,
                const c10::optional<at::Tensor>& stats, int64_t act, bool head_alpha,
                const c10::optional<at::Tensor>& raw_out, int64_t TH, int64_t TW) {
-  check_bf16_nhwc(x, "x");
-  TORCH_CHECK(wpack.is_cuda() && wpack.scalar_type() == at::kBFloat16 && wpack.is_contiguous() && wpack.dim() == 3,
-              "wpack must be bf16 [G*T, BN, Ci]");
+  check_act_nhwc(x, "x");
+  TORCH_CHECK(wpack.is_cuda() && wpack.scalar_type() == x.scalar_type() && wpack.is_contiguous() && wpack.dim() == 3,
+              "wpack must be [G*T, BN, Ci] in the dtype of x");
   TORCH_CHECK(wpack.size(0) == G * T && wpack.size(2) == x.size(3), "wpack shape mismatch");
   TORCH_CHECK((int64_t)tap_y.size() == G * T && (int64_t)tap_x.size() == G * T, "tap table size");
   TORCH_CHECK((int64_t)out_oy.size() == G && (int64_t)out_ox.size() == G, "group offset size");
@@ -41,7 +50,8 @@ void conv_taps(const at::Tensor& x, const at::Tensor& wpack, at::Tensor out, int
   mine::ConvParams& p = L.p;
   p.N = x.size(0); p.Hg = Hg; p.Wg = Wg; p.TH = TH; p.TW = TW;
   p.G = G; p.T = T; p.Ci = x.size(3);
-  p.KB = p.Ci >= 64 ? 64 : p.Ci;
+  p.es = esize(x);
+  p.KB = p.Ci >= 128 / p.es ? 128 / p.es : p.Ci;
   p.in_stride = in_stride;
   for (int g = 0; g < G; ++g) {
     for (int t = 0; t < T; ++t) { p.tap_y[g][t] = (int16_t)tap_y[g * T + t]; p.tap_x[g][t] = (int16_t)tap_x[g * T + t]; }
@@ -86,6 +96,12 @@ void conv_taps(const at::Tensor& x, const at::Tensor& wpack, at::Tensor out, int
   TORCH_CHECK(err == nullptr, "conv_taps: ", err ? err : "");
 }
 
+void set_operand_size(int64_t es) {
+  TORCH_CHECK(es == 2 || es == 4, "operand element size must be 2 (bf16) or 4 (fp32 storage, TF32 math)");
+  g_operand_es = (int)es;
+}
+int64_t get_operand_size() { return g_operand_es; }
+
 at::Tensor pack_weights(const at::Tensor& w, int64_t mode) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.dim() == 4 && w.size(2) == 3 && w.size(3) == 3,
               "pack_weights expects a CUDA fp32 [Co,Ci,3,3] tensor (any strides)");
@@ -93,16 +109,16 @@ at::Tensor pack_weights(const at::Tensor& w, int64_t mode) {
   const int Co = w.size(0), Ci = w.size(1);
   const int rows = mode >= 2 ? Ci : Co, cols = mode >= 2 ? Co : Ci;
   const int rows_pad = (rows + 15) / 16 * 16;
-  at::Tensor out = at::empty({(mode & 1) ? 16 : 9, rows_pad, cols}, w.options().dtype(at::kBFloat16));
+  at::Tensor out = at::empty({(mode & 1) ? 16 : 9, rows_pad, cols}, w.options().dtype(operand_dtype()));
   mine::launch_pack_weights(w.data_ptr<float>(), w.stride(0), w.stride(1), w.stride(2), w.stride(3), Co, Ci, (int)mode,
-                            rows_pad, out.data_ptr(), cur_stream());
+                            rows_pad, out.data_ptr(), g_operand_es, cur_stream());
   return out;
 }
 
 void wgrad_taps(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_t Hg, int64_t Wg, int64_t G, int64_t T,
                 std::vector<int64_t> tap_y, std::vector<int64_t> tap_x, int64_t dy_stride, std::vector<int64_t> dy_oy,
                 std::vector<int64_t> dy_ox, int64_t TH, int64_t TW, int64_t x_stride) {
-  check_bf16_nhwc(dy, "dy"); check_bf16_nhwc(x, "x");
+  check_act_nhwc(dy, "dy"); check_act_nhwc(x, "x"); check_same_type(dy, x, "wgrad_taps");
   TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.is_contiguous() && dw.dim() == 3, "dw must be fp32 [G*T,Co,Ci]");
   TORCH_CHECK(dw.size(0) == G * T && dw.size(1) == dy.size(3) && dw.size(2) == x.size(3), "dw shape");
   TORCH_CHECK(dy.size(0) == x.size(0), "batch mismatch");
@@ -111,6 +127,7 @@ void wgrad_taps(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_
   mine::WgradParams& p = L.p;
   p.N = x.size(0); p.Hg = Hg; p.Wg = Wg; p.TH = TH; p.TW = TW; p.KP = TH * TW;
   p.G = G; p.T = T; p.Co = dy.size(3); p.Ci = x.size(3);
+  p.es = esize(x);
   p.dy_stride = dy_stride;
   p.x_stride = x_stride;
   for (int g = 0; g < G; ++g) {
@@ -126,21 +143,22 @@ void wgrad_taps(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_
 
 at::Tensor bn_act_pad_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
                           int64_t pad_mode, double count, double eps) {
-  check_bf16_nhwc(y, "y");
+  check_act_nhwc(y, "y");
   c10::cuda::CUDAGuard guard(y.device());
   const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
   TORCH_CHECK((C & (C - 1)) == 0 && C >= 16, "channels must be a power of two >= 16");
   TORCH_CHECK((int64_t)N * (H + 2) * (W + 2) * (C / 8) < (1ll << 31), "tensor too large for 32-bit indexing");
   at::Tensor out = at::empty({N, H + 2, W + 2, C}, y.options());
   mine::launch_bn_act_pad_fwd(y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(),
-                              out.data_ptr(), N, H, W, C, (int)pad_mode, (float)(1.0 / count), (float)eps, cur_stream());
+                              out.data_ptr(), N, H, W, C, (int)pad_mode, (float)(1.0 / count), (float)eps, esize(y),
+                              cur_stream());
   return out;
 }
 
 std::vector<at::Tensor> bn_act_bwd_reduce(const at::Tensor& dapad, const at::Tensor& y, const at::Tensor& stats,
                                           const at::Tensor& gamma, const at::Tensor& beta, int64_t pad_mode, double count,
                                           double eps) {
-  check_bf16_nhwc(dapad, "dapad"); check_bf16_nhwc(y, "y");
+  check_act_nhwc(dapad, "dapad"); check_act_nhwc(y, "y"); check_same_type(dapad, y, "bn_act_bwd_reduce");
   c10::cuda::CUDAGuard guard(y.device());
   const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
   TORCH_CHECK(dapad.size(1) == H + 2 && dapad.size(2) == W + 2 && dapad.size(3) == C, "dapad shape");
@@ -150,14 +168,14 @@ std::vector<at::Tensor> bn_act_bwd_reduce(const at::Tensor& dapad, const at::Ten
   at::Tensor sums = at::zeros({2, C}, stats.options());
   mine::launch_bn_act_bwd_reduce(dapad.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(),
                                  beta.data_ptr<float>(), g.data_ptr(), sums.data_ptr<float>(), N, H, W, C, (int)pad_mode,
-                                 (float)(1.0 / count), (float)eps, cur_stream());
+                                 (float)(1.0 / count), (float)eps, esize(y), cur_stream());
   return {g, sums};
 }
 
 std::vector<at::Tensor> bn_bwd_apply(const at::Tensor& g, const at::Tensor& y, const at::Tensor& stats,
                                      const at::Tensor& gamma, const at::Tensor& sums, int64_t planes_per_image,
                                      bool want_shared, bool want_plane_bias, double count, double eps) {
-  check_bf16_nhwc(g, "g"); check_bf16_nhwc(y, "y");
+  check_act_nhwc(g, "g"); check_act_nhwc(y, "y"); check_same_type(g, y, "bn_bwd_apply");
   c10::cuda::CUDAGuard guard(y.device());
   const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
   const int S = planes_per_image, B = N / S;
@@ -167,7 +185,7 @@ std::vector<at::Tensor> bn_bwd_apply(const at::Tensor& g, const at::Tensor& y, c
   mine::launch_bn_bwd_apply(g.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(),
                             sums.data_ptr<float>(), dy.data_ptr(), want_shared ? dshared.data_ptr<float>() : nullptr,
                             want_plane_bias ? dpb.data_ptr<float>() : nullptr, B, S, H, W, C, (float)(1.0 / count),
-                            (float)eps, cur_stream());
+                            (float)eps, esize(y), cur_stream());
   return {dy, dshared, dpb};
 }
 
@@ -177,16 +195,17 @@ std::vector<at::Tensor> head_bwd(const at::Tensor& g_mpi, const at::Tensor& mpi,
   c10::cuda::CUDAGuard guard(mpi.device());
   const int64_t npix = mpi.numel() / 4;
   auto sizes = sign.sizes().vec();           // [N, H, W]
-  at::Tensor dz = at::empty({sizes[0], sizes[1], sizes[2], 16}, mpi.options().dtype(at::kBFloat16));
+  at::Tensor dz = at::empty({sizes[0], sizes[1], sizes[2], 16}, mpi.options().dtype(operand_dtype()));
   at::Tensor dbias = at::zeros({4}, mpi.options());
   mine::launch_head_bwd(g_mpi.data_ptr<float>(), mpi.data_ptr<float>(), sign.data_ptr<int8_t>(), dz.data_ptr(),
-                        dbias.data_ptr<float>(), (size_t)npix, use_alpha ? 1 : 0, cur_stream());
+                        dbias.data_ptr<float>(), (size_t)npix, use_alpha ? 1 : 0, g_operand_es, cur_stream());
   return {dz, dbias};
 }
 
 std::vector<at::Tensor> head_conv_direct(const at::Tensor& apad, const at::Tensor& wpk, const at::Tensor& bias,
                                          bool use_alpha) {
-  check_bf16_nhwc(apad, "apad");
+  check_act_nhwc(apad, "apad");
+  TORCH_CHECK(apad.scalar_type() == at::kBFloat16, "head_conv_direct: bf16 operands only");
   const int64_t N = apad.size(0), H = apad.size(1) - 2, W = apad.size(2) - 2, C = apad.size(3);
   TORCH_CHECK(C == 16 || C == 32, "head_conv_direct handles 16 or 32 input channels");
   TORCH_CHECK(wpk.is_cuda() && wpk.scalar_type() == at::kFloat && wpk.is_contiguous() && wpk.numel() == 9 * C * 4,
@@ -210,12 +229,12 @@ inline void check_channels(const at::Tensor& y) {
 
 at::Tensor bn_res_act_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
                           const c10::optional<at::Tensor>& residual, double slope, double count, double eps) {
-  check_bf16_nhwc(y, "y"); check_channels(y);
+  check_act_nhwc(y, "y"); check_channels(y);
   TORCH_CHECK(stats.numel() == 2 * y.size(3) && opt_f32(stats, "stats") && opt_f32(gamma, "gamma") && opt_f32(beta, "beta"),
               "stats/gamma/beta");
   const void* res = nullptr;
   if (residual.has_value() && residual->defined()) {
-    check_bf16_nhwc(*residual, "residual");
+    check_act_nhwc(*residual, "residual"); check_same_type(*residual, y, "bn_res_act_fwd");
     TORCH_CHECK(residual->sizes() == y.sizes(), "residual shape");
     res = residual->data_ptr();
   }
@@ -223,15 +242,16 @@ at::Tensor bn_res_act_fwd(const at::Tensor& y, const at::Tensor& stats, const at
   at::Tensor out = at::empty_like(y);
   mine::launch_bn_res_act_fwd(y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(), res,
                               out.data_ptr(), (size_t)(y.numel() / y.size(3)), (int)y.size(3), (float)slope,
-                              (float)(1.0 / count), (float)eps, cur_stream());
+                              (float)(1.0 / count), (float)eps, esize(y), cur_stream());
   return out;
 }
 
 std::vector<at::Tensor> bn_res_act_bwd_reduce(const at::Tensor& dout, const at::Tensor& out, const at::Tensor& y,
                                               const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
                                               double slope, double count, double eps) {
-  check_bf16_nhwc(dout, "dout"); check_bf16_nhwc(out, "out"); check_bf16_nhwc(y, "y"); check_channels(y);
+  check_act_nhwc(dout, "dout"); check_act_nhwc(out, "out"); check_act_nhwc(y, "y"); check_channels(y);
   TORCH_CHECK(dout.sizes() == y.sizes() && out.sizes() == y.sizes(), "shape mismatch");
+  check_same_type(dout, y, "bn_res_act_bwd_reduce"); check_same_type(out, y, "bn_res_act_bwd_reduce");
   TORCH_CHECK(stats.numel() == 2 * y.size(3) && opt_f32(stats, "stats"), "stats");
   (void)gamma; (void)beta;                     // the reduction needs mean / invstd only; kept for a uniform signature
   c10::cuda::CUDAGuard guard(y.device());
@@ -239,25 +259,25 @@ std::vector<at::Tensor> bn_res_act_bwd_reduce(const at::Tensor& dout, const at::
   at::Tensor sums = at::zeros({2, y.size(3)}, stats.options());
   mine::launch_bn_res_act_bwd_reduce(dout.data_ptr(), out.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), g.data_ptr(),
                                      sums.data_ptr<float>(), (size_t)(y.numel() / y.size(3)), (int)y.size(3),
-                                     (float)slope, (float)(1.0 / count), (float)eps, cur_stream());
+                                     (float)slope, (float)(1.0 / count), (float)eps, esize(y), cur_stream());
   return {g, sums};
 }
 
 at::Tensor channel_stats(const at::Tensor& y) {
-  check_bf16_nhwc(y, "y"); check_channels(y);
+  check_act_nhwc(y, "y"); check_channels(y);
   c10::cuda::CUDAGuard guard(y.device());
   at::Tensor sums = at::zeros({2, y.size(3)}, y.options().dtype(at::kFloat));
   mine::launch_channel_stats(y.data_ptr(), sums.data_ptr<float>(), (size_t)(y.numel() / y.size(3)), (int)y.size(3),
-                             cur_stream());
+                             esize(y), cur_stream());
   return sums;
 }
 
 void conv_taps_splitk(const at::Tensor& x, const at::Tensor& wpack, at::Tensor out32, int64_t Hg, int64_t Wg, int64_t T,
                       std::vector<int64_t> tap_y, std::vector<int64_t> tap_x, int64_t in_stride, int64_t Co, int64_t TH,
                       int64_t TW, int64_t ksplit) {
-  check_bf16_nhwc(x, "x");
-  TORCH_CHECK(wpack.is_cuda() && wpack.scalar_type() == at::kBFloat16 && wpack.is_contiguous() && wpack.dim() == 3 &&
-                  wpack.size(0) == T && wpack.size(2) == x.size(3), "wpack must be bf16 [T, rows, Ci]");
+  check_act_nhwc(x, "x");
+  TORCH_CHECK(wpack.is_cuda() && wpack.scalar_type() == x.scalar_type() && wpack.is_contiguous() && wpack.dim() == 3 &&
+                  wpack.size(0) == T && wpack.size(2) == x.size(3), "wpack must be [T, rows, Ci] in the dtype of x");
   TORCH_CHECK((int64_t)tap_y.size() == T && (int64_t)tap_x.size() == T, "tap table size");
   TORCH_CHECK(out32.is_cuda() && out32.scalar_type() == at::kFloat && out32.is_contiguous() && out32.dim() == 4 &&
                   out32.size(0) == x.size(0) && out32.size(1) == Hg && out32.size(2) == Wg && out32.size(3) == Co,
@@ -267,7 +287,7 @@ void conv_taps_splitk(const at::Tensor& x, const at::Tensor& wpack, at::Tensor o
   const char* err = mine::launch_conv_splitk(x.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2), (int)x.size(3),
                                              wpack.data_ptr(), (int)wpack.size(1), (int)T, ty.data(), tx.data(),
                                              (int)in_stride, out32.data_ptr<float>(), (int)Hg, (int)Wg, (int)Co, (int)TH,
-                                             (int)TW, (int)ksplit, cur_stream());
+                                             (int)TW, (int)ksplit, esize(x), cur_stream());
   TORCH_CHECK(err == nullptr, "conv_taps_splitk: ", err ? err : "");
 }
 
@@ -278,8 +298,13 @@ std::vector<at::Tensor> splitk_finalize(const at::Tensor& acc, bool want_stats) 
   TORCH_CHECK((C & (C - 1)) == 0 && C >= 16 && C <= 2048, "channels must be a power of two in [16, 2048]");
   TORCH_CHECK(acc.numel() / 8 < (1ll << 31), "tensor too large for 32-bit indexing");
   c10::cuda::CUDAGuard guard(acc.device());
-  at::Tensor y = at::empty(acc.sizes(), acc.options().dtype(at::kBFloat16));
   at::Tensor stats = want_stats ? at::zeros({2, C}, acc.options()) : at::empty({0}, acc.options());
+  if (g_operand_es == 4) {       // fp32 operands: the partial-sum tensor IS the activation; only the BN sums are left
+    if (want_stats)
+      mine::launch_channel_stats(acc.data_ptr(), stats.data_ptr<float>(), (size_t)(acc.numel() / C), (int)C, 4, cur_stream());
+    return {acc, stats};
+  }
+  at::Tensor y = at::empty(acc.sizes(), acc.options().dtype(at::kBFloat16));
   mine::launch_splitk_finalize(acc.data_ptr<float>(), y.data_ptr(), want_stats ? stats.data_ptr<float>() : nullptr,
                                (size_t)(acc.numel() / C), (int)C, cur_stream());
   return {y, stats};
@@ -301,6 +326,8 @@ void bn_update_running(const at::Tensor& stats, at::Tensor running_mean, at::Ten
 }  // namespace
 
 void register_conv(pybind11::module_& m) {
+  m.def("set_operand_size", &set_operand_size);
+  m.def("get_operand_size", &get_operand_size);
   m.def("conv_taps", &conv_taps);
   m.def("wgrad_taps", &wgrad_taps);
   m.def("pack_weights", &pack_weights);

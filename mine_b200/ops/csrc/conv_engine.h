@@ -27,6 +27,7 @@ struct ConvParams {
   float* stats;                          // [2, Co] fp32 (sum, sum of squares) or null
   int act, head_alpha;                   // act = 1: MPI head (packed fp32 [.,4] output)
   void* raw_out;                         // head: sign of the sigma pre-activation, int8 [N, Ho, Wo] or null
+  int es;                                // operand element size: 2 = bf16 (kind::f16), 4 = fp32 storage (kind::tf32)
   // filled by the launcher
   int stages, tmem_cols, ipb;
 };
@@ -45,6 +46,7 @@ struct WgradParams {
   int16_t dy_oy[4], dy_ox[4];            // phase offsets into dy
   int16_t tap_y[4][16], tap_x[4][16];    // offsets into x
   float* dw;                             // fp32 [G*T, Co, Ci], accumulated with atomics
+  int es;                                // operand element size: 2 = bf16, 4 = fp32 storage / TF32 math
   // filled by the launcher
   int a_cb, b_cb, a_slabs, b_slabs, co_blocks, ci_blocks, NB, taps_per_chunk, tap_chunks, stages, tmem_cols;
 };
@@ -57,7 +59,7 @@ struct WgradLaunch {
 
 const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream);
 void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co, int Ci, int mode,
-                         int rows_pad, void* out, cudaStream_t stream);
+                         int rows_pad, void* out, int es, cudaStream_t stream);
 const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream);
 
 }  // namespace mine

@@ -79,6 +79,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -105,8 +114,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __device__ __forceinline__ uint32_t layout_type_for(int swizzle_bytes) {
   return swizzle_bytes == 128 ? 2u : (swizzle_bytes == 64 ? 4u : 6u);
 }
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, bool tf32) {
+  const uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 constexpr int kThreads = 192;
@@ -118,7 +128,7 @@ struct Params {
   int16_t tap_y[16], tap_x[16];
   int Co, BN, CB, Ho, Wo;
   float* out;                 // fp32 [N, Ho, Wo, Co], zero-initialised by the caller
-  int ksplit, tmem_cols;
+  int ksplit, tmem_cols, es;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -141,7 +151,7 @@ conv_splitk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int i1 = (int)(((long long)(blockIdx.y + 1) * iters) / p.ksplit);
   const int my_iters = i1 - i0;
 
-  const int row_bytes = p.KB * 2;
+  const int row_bytes = p.KB * p.es;
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) / 1024u) * 1024u;
   uint8_t* smem_aligned = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
@@ -175,9 +185,10 @@ conv_splitk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.BN);
+      const bool tf32 = p.es == 4;
+      const uint32_t idesc = make_idesc(128, p.BN, tf32);
       const uint64_t desc0 = make_smem_desc(0, 16, 8u * row_bytes, layout_type_for(row_bytes));
-      const int ksteps = p.KB / 16;
+      const int ksteps = row_bytes / 32;
       uint32_t first = 0;
       for (int i = 0; i < my_iters; ++i) {
         const int s = i % kStages, round = i / kStages;
@@ -186,7 +197,8 @@ conv_splitk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
         const uint64_t da = desc0 + (uint64_t)(a_addr >> 4), db = desc0 + (uint64_t)((a_addr + a_bytes) >> 4);
         for (int k = 0; k < ksteps; ++k) {
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
+          if (tf32) umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
+          else umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
           first = 1u;
         }
         umma_commit(&empty_bar[s]);
@@ -289,14 +301,16 @@ static CUtensorMapSwizzle swizzle_for(int bytes) {
 // x: bf16 [N, Hi, Wi, Ci]; wpack: bf16 [T, rows (= Co padded / CB*BN), Ci]; out32: fp32 [N, Ho, Wo, Co] zeroed
 const char* launch_conv_splitk(const void* x, int N, int Hi, int Wi, int Ci, const void* wpack, int w_rows, int T,
                                const int* tap_y, const int* tap_x, int in_stride, float* out32, int Hg, int Wg, int Co,
-                               int TH, int TW, int ksplit, cudaStream_t stream) {
+                               int TH, int TW, int ksplit, int es, cudaStream_t stream) {
   using namespace sk;
   Params p{};
   if (TH * TW != 128) return "tile must cover 128 pixels";
   if (T < 1 || T > 16) return "taps";
   p.N = N; p.Hg = Hg; p.Wg = Wg; p.TH = TH; p.TW = TW; p.T = T; p.Ci = Ci; p.in_stride = in_stride;
-  p.KB = Ci >= 64 ? 64 : Ci;
-  if (p.KB != 16 && p.KB != 32 && p.KB != 64) return "Ci must be 16, 32 or a multiple of 64";
+  if (es != 2 && es != 4) return "operand element size must be 2 or 4";
+  p.es = es;
+  p.KB = Ci >= 128 / es ? 128 / es : Ci;
+  if (p.KB * es != 32 && p.KB * es != 64 && p.KB * es != 128) return "the K block must span 32, 64 or 128 bytes";
   if (Ci % p.KB) return "Ci must be a multiple of the K block";
   p.kblocks = Ci / p.KB;
   for (int t = 0; t < T; ++t) { p.tap_y[t] = (int16_t)tap_y[t]; p.tap_x[t] = (int16_t)tap_x[t]; }
@@ -310,7 +324,7 @@ const char* launch_conv_splitk(const void* x, int N, int Hi, int Wi, int Ci, con
   p.ksplit = ksplit < 1 ? 1 : (ksplit > iters ? iters : ksplit);
   int cols = 32; while (cols < p.BN) cols <<= 1;
   p.tmem_cols = cols;
-  const uint32_t row_bytes = p.KB * 2;
+  const uint32_t row_bytes = p.KB * es;
   const uint32_t stage_bytes = 128u * row_bytes + (((uint32_t)p.BN * row_bytes + 1023u) / 1024u) * 1024u;
   const size_t smem = (size_t)kStages * stage_bytes + 1024;
   EncodeTiledFn enc = encode_tiled();
@@ -318,21 +332,21 @@ const char* launch_conv_splitk(const void* x, int N, int Hi, int Wi, int Ci, con
   CUtensorMap mx, mw;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Ci, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)Ci * 2, (cuuint64_t)Wi * Ci * 2, (cuuint64_t)Hi * Wi * Ci * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)Ci * es, (cuuint64_t)Wi * Ci * es, (cuuint64_t)Hi * Wi * Ci * es};
     cuuint32_t box[4] = {(cuuint32_t)p.KB, (cuuint32_t)(TW * in_stride), (cuuint32_t)(TH * in_stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)in_stride, (cuuint32_t)in_stride, 1};
-    if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.KB * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    if (enc(&mx, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.KB * es), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return "cuTensorMapEncodeTiled failed for the activation";
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)Ci, (cuuint64_t)w_rows, (cuuint64_t)T};
-    cuuint64_t strides[2] = {(cuuint64_t)Ci * 2, (cuuint64_t)w_rows * Ci * 2};
+    cuuint64_t strides[2] = {(cuuint64_t)Ci * es, (cuuint64_t)w_rows * Ci * es};
     cuuint32_t box[3] = {(cuuint32_t)p.KB, (cuuint32_t)p.BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    if (enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpack), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.KB * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    if (enc(&mw, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpack), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.KB * es), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return "cuTensorMapEncodeTiled failed for the weights";
   }

@@ -105,6 +105,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one K step = 32 bytes of the reduction dimension: 16 bf16 (kind::f16) or 8 fp32 containers read as TF32 (kind::tf32)
+__device__ __forceinline__ void umma(bool tf32, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if (tf32) umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -134,9 +149,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __device__ __forceinline__ uint32_t layout_type_for(int swizzle_bytes) {
   return swizzle_bytes == 128 ? 2u : (swizzle_bytes == 64 ? 4u : 6u);     // SWIZZLE_128B / 64B / 32B
 }
-// Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
-__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// Instruction descriptor: fp32 accumulation (c_format 1), operand format 1 = bf16 (kind::f16) or 2 = tf32 (kind::tf32).
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, bool tf32 = false) {
+  const uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -175,7 +191,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int tiles = p.tiles_x * p.tiles_y;
   const int total_work = tiles * p.N * p.G * p.CB;     // w -> (tile, image, group, channel block), tile fastest
 
-  const int row_bytes = p.KB * 2;                     // == swizzle span
+  const int row_bytes = p.KB * p.es;                  // == swizzle span
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
   const uint32_t sub_bytes = a_bytes + ((b_bytes + 1023u) / 1024u) * 1024u;   // one (tap, k-block) operand pair
   const uint32_t stage_bytes = sub_bytes * p.ipb;      // ipb iterations share one barrier round trip
@@ -234,11 +250,12 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
+      const bool tf32 = p.es == 4;
+      const uint32_t idesc = make_idesc(128, p.BN, 0, 0, tf32);
       const uint32_t lt = layout_type_for(row_bytes);
       const uint32_t sbo = 8u * row_bytes;
       const uint64_t desc0 = make_smem_desc(0, 16, sbo, lt);
-      const int ksteps = p.KB / 16;
+      const int ksteps = row_bytes / 32;
       int s = 0, j = 0;
       uint32_t par = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
@@ -255,7 +272,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int u = 0; u < n_in; ++u, a_addr += sub_bytes) {
             const uint64_t da = desc0 + (uint64_t)(a_addr >> 4), db = desc0 + (uint64_t)((a_addr + a_bytes) >> 4);
             for (int k = 0; k < ksteps; ++k) {
-              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
+              umma(tf32, d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
               first = 1u;
             }
           }
@@ -437,7 +454,7 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int t0 = tc * p.taps_per_chunk;
   const int ntaps = min(p.taps_per_chunk, p.T - t0);
 
-  const int a_row = p.a_cb * 2, b_row = p.b_cb * 2;          // bytes per pixel row in the A / B slabs
+  const int a_row = p.a_cb * p.es, b_row = p.b_cb * p.es;    // bytes per pixel row in the A / B slabs
   const uint32_t a_slab = (uint32_t)p.KP * a_row, b_slab = (uint32_t)p.KP * b_row;
   const uint32_t a_bytes = a_slab * p.a_slabs;
   const uint32_t b_tap_bytes = b_slab * p.b_slabs;
@@ -495,6 +512,8 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       // pipe busy for the 16/32-channel layers.
       const int total_blocks = ntaps * p.b_slabs;
       const int blk_per_mma = 256 / p.b_cb;
+      const bool tf32 = p.es == 4;
+      const int kpi = 32 / p.es;
       const uint64_t da0 = make_smem_desc(0, a_lbo, 8u * a_row, lta);
       const uint64_t db0 = make_smem_desc(0, b_slab, 8u * b_row, ltb);
       for (int i = 0; i < my_tiles; ++i) {
@@ -503,13 +522,13 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
         const uint32_t b_addr = a_addr + a_bytes;
-        for (int k = 0; k < p.KP / 16; ++k) {
-          // 16 K rows (pixels) per instruction = two 8-row groups, SBO apart
-          const uint64_t da = da0 + (uint64_t)((a_addr + k * 16 * a_row) >> 4);
+        for (int k = 0; k < p.KP / kpi; ++k) {
+          // kpi K rows (pixels) per instruction: 16 bf16 = two 8-row groups SBO apart, 8 tf32 = one group
+          const uint64_t da = da0 + (uint64_t)((a_addr + k * kpi * a_row) >> 4);
           for (int b0 = 0; b0 < total_blocks; b0 += blk_per_mma) {
             const int nblk = min(blk_per_mma, total_blocks - b0);
-            const uint64_t db = db0 + (uint64_t)((b_addr + b0 * b_slab + k * 16 * b_row) >> 4);
-            umma_bf16(tmem_base + b0 * p.b_cb, da, db, make_idesc(128, nblk * p.b_cb, 1, 1), (i > 0 || k > 0) ? 1u : 0u);
+            const uint64_t db = db0 + (uint64_t)((b_addr + b0 * b_slab + k * kpi * b_row) >> 4);
+            umma(tf32, tmem_base + b0 * p.b_cb, da, db, make_idesc(128, nblk * p.b_cb, 1, 1, tf32), (i > 0 || k > 0) ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[s]);
@@ -570,29 +589,31 @@ static CUtensorMapSwizzle swizzle_for(int bytes) {
 }
 
 struct MapKey {
-  const void* ptr; int d0, d1, d2, d3, b0, b1, b2, b3, e1, e2, rank;
+  const void* ptr; int d0, d1, d2, d3, b0, b1, b2, b3, e1, e2, rank, es;
   bool operator<(const MapKey& o) const {
-    return std::tie(ptr, d0, d1, d2, d3, b0, b1, b2, b3, e1, e2, rank) <
-           std::tie(o.ptr, o.d0, o.d1, o.d2, o.d3, o.b0, o.b1, o.b2, o.b3, o.e1, o.e2, o.rank);
+    return std::tie(ptr, d0, d1, d2, d3, b0, b1, b2, b3, e1, e2, rank, es) <
+           std::tie(o.ptr, o.d0, o.d1, o.d2, o.d3, o.b0, o.b1, o.b2, o.b3, o.e1, o.e2, o.rank, o.es);
   }
 };
+static CUtensorMapDataType dtype_for(int es) { return es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 static std::map<MapKey, CUtensorMap> g_maps;
 static std::mutex g_maps_mu;
 
 // NHWC activation: dims {C, W, H, N}; box {cb, bw, bh, 1}; element stride es on W and H.
-static const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int cb, int bw, int bh, int es) {
-  MapKey key{ptr, C, W, H, N, cb, bw * es, bh * es, 1, es, es, 4};
+static const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int cb, int bw, int bh, int es,
+                            int esz) {
+  MapKey key{ptr, C, W, H, N, cb, bw * es, bh * es, 1, es, es, 4, esz};
   std::lock_guard<std::mutex> lock(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return nullptr; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)C * esz, (cuuint64_t)W * C * esz, (cuuint64_t)H * W * C * esz};
   cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return "cuTensorMapEncodeTiled is not available from this driver";
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
-                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cb * 2),
+  CUresult r = enc(out, dtype_for(esz), 4, const_cast<void*>(ptr), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cb * esz),
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (bad shape / stride / alignment)";
   if (g_maps.size() > 4096) g_maps.clear();
@@ -601,19 +622,19 @@ static const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int
 }
 
 // packed weights: dims {Ci, Co_pad, GT}; box {kb, bn, 1}
-static const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop, int GT, int kb, int bn) {
-  MapKey key{ptr, Ci, Cop, GT, 0, kb, bn, 1, 0, 1, 1, 3};
+static const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop, int GT, int kb, int bn, int esz) {
+  MapKey key{ptr, Ci, Cop, GT, 0, kb, bn, 1, 0, 1, 1, 3, esz};
   std::lock_guard<std::mutex> lock(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return nullptr; }
   cuuint64_t dims[3] = {(cuuint64_t)Ci, (cuuint64_t)Cop, (cuuint64_t)GT};
-  cuuint64_t strides[2] = {(cuuint64_t)Ci * 2, (cuuint64_t)Cop * Ci * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)Ci * esz, (cuuint64_t)Cop * Ci * esz};
   cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)bn, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return "cuTensorMapEncodeTiled is not available from this driver";
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box,
-                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kb * 2),
+  CUresult r = enc(out, dtype_for(esz), 3, const_cast<void*>(ptr), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kb * esz),
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (bad shape / stride / alignment)";
   g_maps[key] = *out;
@@ -631,8 +652,11 @@ static int next_pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; 
 __device__ __forceinline__ bool phase_has(int p, int a, int k) {      // does 3-tap index k fold onto 2-tap index a?
   return p == 0 ? (a == 0 ? k == 0 : k >= 1) : (a == 0 ? k <= 1 : k == 2);
 }
+__device__ __forceinline__ void store_operand(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void store_operand(float* p, float v) { *p = v; }
+template <typename T>
 __global__ void pack_weights_kernel(const float* __restrict__ w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co,
-                                    int Ci, int mode, int rows_pad, __nv_bfloat16* __restrict__ out, int total) {
+                                    int Ci, int mode, int rows_pad, T* __restrict__ out, int total) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const bool dgrad = mode >= 2, up = (mode & 1) != 0;
@@ -653,22 +677,27 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int64_t so, int
           if (phase_has(py, a, ky) && phase_has(px, b, kx)) v += base[ky * sy + kx * sx];
     }
   }
-  out[idx] = __float2bfloat16(v);
+  store_operand(out + idx, v);
 }
 
 void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co, int Ci, int mode,
-                         int rows_pad, void* out, cudaStream_t stream) {
+                         int rows_pad, void* out, int es, cudaStream_t stream) {
   const int gt = (mode & 1) ? 16 : 9;
   const int cols = mode >= 2 ? Co : Ci;
   const int total = gt * rows_pad * cols;
-  pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, so, si, sy, sx, Co, Ci, mode, rows_pad,
-                                                               (__nv_bfloat16*)out, total);
+  if (es == 4)
+    pack_weights_kernel<float><<<(total + 255) / 256, 256, 0, stream>>>(w, so, si, sy, sx, Co, Ci, mode, rows_pad,
+                                                                        (float*)out, total);
+  else
+    pack_weights_kernel<__nv_bfloat16><<<(total + 255) / 256, 256, 0, stream>>>(w, so, si, sy, sx, Co, Ci, mode, rows_pad,
+                                                                                (__nv_bfloat16*)out, total);
 }
 
 const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   ConvParams p = L.p;
   if (p.TH * p.TW != 128) return "tile must cover 128 pixels";
-  if (p.KB != 16 && p.KB != 32 && p.KB != 64) return "KB must be 16/32/64";
+  if (p.es != 2 && p.es != 4) return "operand element size must be 2 (bf16) or 4 (fp32/tf32)";
+  if (p.KB * p.es != 32 && p.KB * p.es != 64 && p.KB * p.es != 128) return "K block must span 32/64/128 bytes";
   if (p.Ci % p.KB) return "Ci must be a multiple of KB";
   if (p.BN % 16 || p.BN < 16 || p.BN > 256) return "BN must be a multiple of 16 in [16,256]";
   if (p.T > 16 || p.G > 4) return "too many taps/groups";
@@ -678,7 +707,7 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
   p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
   p.tmem_cols = next_pow2_cols(2 * p.BN);                  // double-buffered accumulator
-  const uint32_t sub_bytes = 128u * p.KB * 2 + (((uint32_t)p.BN * p.KB * 2 + 1023u) / 1024u) * 1024u;
+  const uint32_t sub_bytes = 128u * p.KB * p.es + (((uint32_t)p.BN * p.KB * p.es + 1023u) / 1024u) * 1024u;
   int ipb = (int)(24u * 1024u / sub_bytes);                // (tap, k-block) iterations per barrier round trip
   if (ipb > p.T * p.kblocks) ipb = p.T * p.kblocks;
   if (ipb > 12) ipb = 12;
@@ -705,9 +734,9 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   if (smem < smem_floor) smem = smem_floor;
   if (smem > 200u * 1024u) smem = 200u * 1024u;
   CUtensorMap mx, mw;
-  const char* e = nhwc_map(&mx, L.x, p.Ci, L.Wi, L.Hi, p.N, p.KB, p.TW, p.TH, p.in_stride);
+  const char* e = nhwc_map(&mx, L.x, p.Ci, L.Wi, L.Hi, p.N, p.KB, p.TW, p.TH, p.in_stride, p.es);
   if (e) return e;
-  e = weight_map(&mw, L.w, p.Ci, L.w_rows, p.G * p.T, p.KB, p.BN);
+  e = weight_map(&mw, L.w, p.Ci, L.w_rows, p.G * p.T, p.KB, p.BN, p.es);
   if (e) return e;
   static bool attr_set = false;
   if (!attr_set) {
@@ -727,12 +756,18 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
 const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
   WgradParams p = L.p;
   if (p.TH * p.TW != p.KP || p.KP % 16 || p.KP < 32 || p.KP > 256) return "wgrad pixel tile must be 32..256 pixels";
-  // operand slabs: channel block = min(C, 64) with the matching swizzle
-  p.a_cb = p.Co < 64 ? p.Co : 64;
-  p.b_cb = p.Ci < 64 ? p.Ci : 64;
-  if (p.a_cb != 16 && p.a_cb != 32 && p.a_cb != 64) return "Co must be 16/32/multiple of 64";
-  if (p.b_cb != 16 && p.b_cb != 32 && p.b_cb != 64) return "Ci must be 16/32/multiple of 64";
-  p.a_slabs = p.Co >= 128 ? 2 : 1;                       // M = 128 rows: 2 real slabs, or 1 slab aliased by LBO = 0
+  if (p.es != 2 && p.es != 4) return "operand element size must be 2 (bf16) or 4 (fp32/tf32)";
+  // operand slabs: channel block = min(C, 128 bytes worth) with the matching swizzle
+  const int cbmax = 128 / p.es;
+  p.a_cb = p.Co < cbmax ? p.Co : cbmax;
+  p.b_cb = p.Ci < cbmax ? p.Ci : cbmax;
+  if (p.a_cb * p.es != 32 && p.a_cb * p.es != 64 && p.a_cb * p.es != 128) return "Co must span 32/64 bytes or a multiple of 128 bytes";
+  if (p.b_cb * p.es != 32 && p.b_cb * p.es != 64 && p.b_cb * p.es != 128) return "Ci must span 32/64 bytes or a multiple of 128 bytes";
+  if (p.Co % p.a_cb || p.Ci % p.b_cb) return "channels must be a multiple of the slab width";
+  // M = 128 rows = 128 / a_cb MN blocks LBO apart: all real when Co >= 128; one slab aliased by LBO = 0 when Co == a_cb;
+  // otherwise (fp32, Co = 64) the blocks past Co read the bytes that follow (finite operand data) and their
+  // accumulator rows are never stored
+  p.a_slabs = (p.Co < 128 ? p.Co : 128) / p.a_cb;
   p.co_blocks = (p.Co + 127) / 128;
   p.NB = p.Ci < 128 ? p.Ci : 128;                        // N per accumulator
   p.b_slabs = p.NB / p.b_cb;
@@ -742,7 +777,7 @@ const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
   if (p.taps_per_chunk > p.T) p.taps_per_chunk = p.T;
   // keep the stage under ~96 KB (>= 2 stages in flight)
   for (;;) {
-    const uint32_t sb = (uint32_t)p.KP * p.a_cb * 2 * p.a_slabs + (uint32_t)p.KP * p.b_cb * 2 * p.b_slabs * p.taps_per_chunk;
+    const uint32_t sb = (uint32_t)p.KP * p.a_cb * p.es * p.a_slabs + (uint32_t)p.KP * p.b_cb * p.es * p.b_slabs * p.taps_per_chunk;
     if (sb <= 96 * 1024 || p.taps_per_chunk == 1) break;
     p.taps_per_chunk = (p.taps_per_chunk + 1) / 2;
   }
@@ -751,18 +786,18 @@ const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
   p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
   p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
   const uint32_t stage_bytes =
-      (((uint32_t)p.KP * p.a_cb * 2 * p.a_slabs + (uint32_t)p.KP * p.b_cb * 2 * p.b_slabs * p.taps_per_chunk + 1023u) / 1024u) * 1024u;
+      (((uint32_t)p.KP * p.a_cb * p.es * p.a_slabs + (uint32_t)p.KP * p.b_cb * p.es * p.b_slabs * p.taps_per_chunk + 1023u) / 1024u) * 1024u;
   int stages = (int)(192u * 1024u / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   CUtensorMap mdy, mx;
-  const char* e = nhwc_map(&mdy, L.dy, p.Co, L.dyW, L.dyH, p.N, p.a_cb, p.TW, p.TH, p.dy_stride);
+  const char* e = nhwc_map(&mdy, L.dy, p.Co, L.dyW, L.dyH, p.N, p.a_cb, p.TW, p.TH, p.dy_stride, p.es);
   if (e) return e;
   if (p.x_stride < 1) p.x_stride = 1;
   if (p.TW * p.x_stride > 256 || p.TH * p.x_stride > 256) return "strided wgrad tile exceeds the TMA box limit";
-  e = nhwc_map(&mx, L.x, p.Ci, L.xW, L.xH, p.N, p.b_cb, p.TW, p.TH, p.x_stride);
+  e = nhwc_map(&mx, L.x, p.Ci, L.xW, L.xH, p.N, p.b_cb, p.TW, p.TH, p.x_stride, p.es);
   if (e) return e;
   static bool attr_set = false;
   if (!attr_set) {

@@ -17,32 +17,10 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "act_types.cuh"
 #include "kernels.h"
 
 namespace mine {
-
-struct V8 {
-  float f[8];
-};
-
-__device__ __forceinline__ V8 load_bf16x8(const __nv_bfloat16* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-  V8 r;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    r.f[2 * i] = t.x; r.f[2 * i + 1] = t.y;
-  }
-  return r;
-}
-__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const V8& v) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v.f[2 * i], v.f[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
 
 __device__ __forceinline__ int pad_src(int p, int n, int mode) {   // padded index -> source index
   int s = p - 1;
@@ -70,9 +48,10 @@ __device__ __forceinline__ BnCoef bn_coef(const float* __restrict__ stats, const
   return k;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) bn_act_pad_fwd_kernel(
-    const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
-    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C, int pad_mode,
+    const T* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, T* __restrict__ out, int N, int H, int W, int C, int pad_mode,
     float inv_count, float eps) {
   const int cg = C >> 3;                         // power of two (C in {16,...,256})
   const int cg_shift = 31 - __clz(cg);
@@ -89,22 +68,23 @@ __global__ void __launch_bounds__(256) bn_act_pad_fwd_kernel(
     const int py = (int)(pix % (unsigned)Hp);
     const int n = (int)(pix / (unsigned)Hp);
     const int sy = pad_src(py, H, pad_mode), sx = pad_src(px, W, pad_mode);
-    V8 v = load_bf16x8(y + (((size_t)n * H + sy) * W + sx) * C + c0);
+    V8 v = ld8(y + (((size_t)n * H + sy) * W + sx) * C + c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float u = v.f[j] * k.a[j] + k.b[j];
       v.f[j] = u > 0.f ? u : (__expf(u) - 1.f);
     }
-    store_bf16x8(out + (((size_t)n * Hp + py) * Wp + px) * C + c0, v);
+    st8(out + (((size_t)n * Hp + py) * Wp + px) * C + c0, v);
   }
 }
 
 // g = fold(dapad) * ELU'(bn(y)); sums[0][c] += g, sums[1][c] += g * xhat
 // BN coefficients live in shared memory (4 x C floats) instead of 32 registers per thread; interior pixels
 // (no pad adjoint) take a branch-free fast path.
+template <typename T>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
-    const __nv_bfloat16* __restrict__ dapad, const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats,
-    const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ g_out,
+    const T* __restrict__ dapad, const T* __restrict__ y, const float* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ g_out,
     float* __restrict__ sums, int N, int H, int W, int C, int pad_mode, float inv_count, float eps) {
   extern __shared__ float s_mem[];     // [2][C] sums, then a[C], b[C], mean[C], invstd[C]
   float* s_sum = s_mem;
@@ -139,8 +119,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
       const int x = (int)(pix % (unsigned)W); pix /= (unsigned)W;
       const int yy = (int)(pix % (unsigned)H);
       const int n = (int)(pix / (unsigned)H);
-      const __nv_bfloat16* base = dapad + ((size_t)n * Hp * Wp) * C + c0;
-      V8 d = load_bf16x8(base + ((size_t)(yy + 1) * Wp + (x + 1)) * C);
+      const T* base = dapad + ((size_t)n * Hp * Wp) * C + c0;
+      V8 d = ld8(base + ((size_t)(yy + 1) * Wp + (x + 1)) * C);
       const bool top = (yy == lo), bot = (yy == H - 1 - lo), lef = (x == lo), rig = (x == W - 1 - lo);
       if (top | bot | lef | rig) {               // border pixels also receive the gradient of their pad copies
         int ry[3], rx[3], ny = 1, nx = 1;
@@ -152,13 +132,13 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
         for (int a = 0; a < ny; ++a)
           for (int b = 0; b < nx; ++b) {
             if (a == 0 && b == 0) continue;
-            const V8 t = load_bf16x8(base + ((size_t)ry[a] * Wp + rx[b]) * C);
+            const V8 t = ld8(base + ((size_t)ry[a] * Wp + rx[b]) * C);
 #pragma unroll
             for (int j = 0; j < 8; ++j) d.f[j] += t.f[j];
           }
       }
       const size_t o = (((size_t)n * H + yy) * W + x) * C + c0;
-      const V8 yv = load_bf16x8(y + o);
+      const V8 yv = ld8(y + o);
       V8 g;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -169,7 +149,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
         acc1[j] += g.f[j];
         acc2[j] += g.f[j] * xhat;
       }
-      store_bf16x8(g_out + o, g);
+      st8(g_out + o, g);
     }
   }
 #pragma unroll
@@ -182,9 +162,10 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
 // lives in 16 registers like in the forward kernel instead of four shared-memory arrays (32 LDS per 8 elements made
 // v1 issue bound at 0.23 of HBM peak), and the second sum is accumulated as sum(g * y); every thread converts its
 // partial to sum(g * xhat) = invstd * (sum(g*y) - mean * sum(g)) once, before the block reduction.
+template <typename T>
 __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_v2_kernel(
-    const __nv_bfloat16* __restrict__ dapad, const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats,
-    const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ g_out,
+    const T* __restrict__ dapad, const T* __restrict__ y, const float* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ g_out,
     float* __restrict__ sums, int N, int H, int W, int C, int pad_mode, float inv_count, float eps) {
   extern __shared__ float s_mem[];     // [2][C] block partial sums
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_mem[i] = 0.f;
@@ -213,8 +194,8 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_v2_kernel(
       const int x = (int)(pix % (unsigned)W); pix /= (unsigned)W;
       const int yy = (int)(pix % (unsigned)H);
       const int n = (int)(pix / (unsigned)H);
-      const __nv_bfloat16* base = dapad + ((size_t)n * Hp * Wp) * C + c0;
-      V8 d = load_bf16x8(base + ((size_t)(yy + 1) * Wp + (x + 1)) * C);
+      const T* base = dapad + ((size_t)n * Hp * Wp) * C + c0;
+      V8 d = ld8(base + ((size_t)(yy + 1) * Wp + (x + 1)) * C);
       const bool top = (yy == lo), bot = (yy == H - 1 - lo), lef = (x == lo), rig = (x == W - 1 - lo);
       if (top | bot | lef | rig) {
         int ry[3], rx[3], ny = 1, nx = 1;
@@ -226,13 +207,13 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_v2_kernel(
         for (int p = 0; p < ny; ++p)
           for (int q = 0; q < nx; ++q) {
             if (p == 0 && q == 0) continue;
-            const V8 t = load_bf16x8(base + ((size_t)ry[p] * Wp + rx[q]) * C);
+            const V8 t = ld8(base + ((size_t)ry[p] * Wp + rx[q]) * C);
 #pragma unroll
             for (int j = 0; j < 8; ++j) d.f[j] += t.f[j];
           }
       }
       const size_t o = (((size_t)n * H + yy) * W + x) * C + c0;
-      const V8 yv = load_bf16x8(y + o);
+      const V8 yv = ld8(y + o);
       V8 g;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -241,7 +222,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_v2_kernel(
         acc1[j] += g.f[j];
         acc2[j] = fmaf(g.f[j], yv.f[j], acc2[j]);
       }
-      store_bf16x8(g_out + o, g);
+      st8(g_out + o, g);
     }
   }
 #pragma unroll
@@ -257,9 +238,10 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_v2_kernel(
 }
 
 // One thread = 8 channels of one pixel of one IMAGE; loops over its S planes.
+template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
-    const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats,
-    const float* __restrict__ gamma, const float* __restrict__ sums, __nv_bfloat16* __restrict__ dy,
+    const T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ sums, T* __restrict__ dy,
     float* __restrict__ dshared, float* __restrict__ dplane_bias, int B, int S, int H, int W, int C, float inv_count,
     float eps) {
   extern __shared__ float s_pb[];      // [S][C] per-plane bias gradient partials
@@ -297,14 +279,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     for (int j = 0; j < 8; ++j) d.f[j] = 0.f;
     if (active) {
       const size_t o = (((size_t)(b * S + s) * H * W) + pix) * C + c0;
-      const V8 gv = load_bf16x8(g + o), yv = load_bf16x8(y + o);
+      const V8 gv = ld8(g + o), yv = ld8(y + o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xhat = (yv.f[j] - mean[j]) * invstd[j];
         d.f[j] = coef[j] * (gv.f[j] - mg[j] - xhat * mgx[j]);
         ds[j] += d.f[j];
       }
-      store_bf16x8(dy + o, d);
+      st8(dy + o, d);
     }
     if (want_pb) {
       // lanes with equal (lane % cg) own the same channels (blockDim and cg are powers of two)
@@ -331,8 +313,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
 }
 
 // MPI head backward: g_mpi fp32 [.,4], mpi fp32 [.,4] (activated), sign int8 -> dz bf16 [.,16] (channels 4..15 zero)
+template <typename T>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float4* __restrict__ g_mpi, const float4* __restrict__ mpi,
-                                                       const int8_t* __restrict__ sign, __nv_bfloat16* __restrict__ dz,
+                                                       const int8_t* __restrict__ sign, T* __restrict__ dz,
                                                        float* __restrict__ dbias, size_t npix, int use_alpha) {
   __shared__ float s_db[4];
   if (threadIdx.x < 4) s_db[threadIdx.x] = 0.f;
@@ -343,12 +326,14 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float4* __restrict_
     float d0 = gg.x * o.x * (1.f - o.x), d1 = gg.y * o.y * (1.f - o.y), d2 = gg.z * o.z * (1.f - o.z);
     float d3 = use_alpha ? gg.w * o.w * (1.f - o.w) : gg.w * (float)sign[i];
     acc[0] += d0; acc[1] += d1; acc[2] += d2; acc[3] += d3;
-    uint4 lo, hi = make_uint4(0, 0, 0, 0);
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&lo);
-    h[0] = __floats2bfloat162_rn(d0, d1); h[1] = __floats2bfloat162_rn(d2, d3);
-    h[2] = __floats2bfloat162_rn(0.f, 0.f); h[3] = h[2];
-    uint4* dst = reinterpret_cast<uint4*>(dz + i * 16);
-    dst[0] = lo; dst[1] = hi;
+    V8 v0, v1;
+    v0.f[0] = d0; v0.f[1] = d1; v0.f[2] = d2; v0.f[3] = d3;
+#pragma unroll
+    for (int j = 4; j < 8; ++j) v0.f[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v1.f[j] = 0.f;
+    st8(dz + i * 16, v0);
+    st8(dz + i * 16 + 8, v1);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -367,47 +352,48 @@ static int grid_for(size_t total, int cap = 148 * 16) {
 }
 
 void launch_bn_act_pad_fwd(const void* y, const float* stats, const float* gamma, const float* beta, void* out, int N,
-                           int H, int W, int C, int pad_mode, float inv_count, float eps, cudaStream_t stream) {
+                           int H, int W, int C, int pad_mode, float inv_count, float eps, int es, cudaStream_t stream) {
   const size_t total = (size_t)N * (H + 2) * (W + 2) * (C / 8);
-  bn_act_pad_fwd_kernel<<<grid_for(total, 148 * 32), 256, 0, stream>>>(
-      (const __nv_bfloat16*)y, stats, gamma, beta, (__nv_bfloat16*)out, N, H, W, C, pad_mode, inv_count, eps);
+  MINE_DISPATCH_ES(es, T, (bn_act_pad_fwd_kernel<T><<<grid_for(total, 148 * 32), 256, 0, stream>>>(
+      (const T*)y, stats, gamma, beta, (T*)out, N, H, W, C, pad_mode, inv_count, eps)));
 }
 
 void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* stats, const float* gamma,
                               const float* beta, void* g_out, float* sums, int N, int H, int W, int C, int pad_mode,
-                              float inv_count, float eps, cudaStream_t stream) {
+                              float inv_count, float eps, int es, cudaStream_t stream) {
   const size_t total = (size_t)N * H * W * (C / 8);
   int blocks = grid_for(total, 148 * 8);
-  static const bool v2 = getenv("MINE_B200_BN_REDUCE") && getenv("MINE_B200_BN_REDUCE")[0] == 'v';
-  if (v2) {
-    bn_act_bwd_reduce_v2_kernel<<<blocks, 256, 2 * C * sizeof(float), stream>>>(
-        (const __nv_bfloat16*)dapad, (const __nv_bfloat16*)y, stats, gamma, beta, (__nv_bfloat16*)g_out, sums, N, H, W, C,
-        pad_mode, inv_count, eps);
+  static const bool v1 = getenv("MINE_B200_BN_REDUCE") && getenv("MINE_B200_BN_REDUCE")[0] == 'o';   // "old"
+  if (!v1) {
+    MINE_DISPATCH_ES(es, T, (bn_act_bwd_reduce_v2_kernel<T><<<blocks, 256, 2 * C * sizeof(float), stream>>>(
+        (const T*)dapad, (const T*)y, stats, gamma, beta, (T*)g_out, sums, N, H, W, C, pad_mode, inv_count, eps)));
     return;
   }
   // the grid-stride must be a multiple of the channel-group count so every thread keeps its channels
-  bn_act_bwd_reduce_kernel<<<blocks, 256, 6 * C * sizeof(float), stream>>>(
-      (const __nv_bfloat16*)dapad, (const __nv_bfloat16*)y, stats, gamma, beta, (__nv_bfloat16*)g_out, sums, N, H, W, C,
-      pad_mode, inv_count, eps);
+  MINE_DISPATCH_ES(es, T, (bn_act_bwd_reduce_kernel<T><<<blocks, 256, 6 * C * sizeof(float), stream>>>(
+      (const T*)dapad, (const T*)y, stats, gamma, beta, (T*)g_out, sums, N, H, W, C, pad_mode, inv_count, eps)));
 }
 
 void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const float* gamma, const float* sums,
                          void* dy, float* dshared, float* dplane_bias, int B, int S, int H, int W, int C,
-                         float inv_count, float eps, cudaStream_t stream) {
+                         float inv_count, float eps, int es, cudaStream_t stream) {
   const size_t per_img = (size_t)H * W * (C / 8);
   dim3 grid((unsigned)((per_img + 255) / 256), B);
   const size_t smem = dplane_bias ? (size_t)S * C * sizeof(float) : 0;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr = true; }
-  bn_bwd_apply_kernel<<<grid, 256, smem, stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y, stats, gamma, sums,
-                                                   (__nv_bfloat16*)dy, dshared, dplane_bias, B, S, H, W, C, inv_count,
-                                                   eps);
+  if (!attr) {
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    attr = true;
+  }
+  MINE_DISPATCH_ES(es, T, (bn_bwd_apply_kernel<T><<<grid, 256, smem, stream>>>(
+      (const T*)g, (const T*)y, stats, gamma, sums, (T*)dy, dshared, dplane_bias, B, S, H, W, C, inv_count, eps)));
 }
 
 void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, void* dz, float* dbias, size_t npix,
-                     int use_alpha, cudaStream_t stream) {
-  head_bwd_kernel<<<grid_for(npix, 148 * 8), 256, 0, stream>>>((const float4*)g_mpi, (const float4*)mpi, sign,
-                                                               (__nv_bfloat16*)dz, dbias, npix, use_alpha);
+                     int use_alpha, int es, cudaStream_t stream) {
+  MINE_DISPATCH_ES(es, T, (head_bwd_kernel<T><<<grid_for(npix, 148 * 8), 256, 0, stream>>>(
+      (const float4*)g_mpi, (const float4*)mpi, sign, (T*)dz, dbias, npix, use_alpha)));
 }
 
 }  // namespace mine

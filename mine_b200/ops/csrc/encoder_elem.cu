@@ -15,33 +15,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "act_types.cuh"
 #include "kernels.h"
 
 namespace mine {
 
 namespace {
-
-struct V8 {
-  float f[8];
-};
-__device__ __forceinline__ V8 ld8(const __nv_bfloat16* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-  V8 r;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    r.f[2 * i] = t.x; r.f[2 * i + 1] = t.y;
-  }
-  return r;
-}
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const V8& v) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v.f[2 * i], v.f[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
 
 // grid-stride over `total` 8-channel vectors with a stride that preserves (index mod cg)
 struct Walk {
@@ -61,9 +40,10 @@ __device__ __forceinline__ Walk make_walk(unsigned total, int C) {
   return w;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) bn_res_act_fwd_kernel(
-    const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
-    const float* __restrict__ beta, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out,
+    const T* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ out,
     unsigned total, int C, float slope, float inv_count, float eps) {
   const Walk w = make_walk(total, C);
   if (!w.active) return;
@@ -106,9 +86,10 @@ __device__ __forceinline__ void publish_sums(float* s_sum, float* __restrict__ s
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) bn_res_act_bwd_reduce_kernel(
-    const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ y,
-    const float* __restrict__ stats, __nv_bfloat16* __restrict__ g_out, float* __restrict__ sums, unsigned total, int C,
+    const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ y,
+    const float* __restrict__ stats, T* __restrict__ g_out, float* __restrict__ sums, unsigned total, int C,
     float slope, float inv_count, float eps) {
   extern __shared__ float s_sum[];       // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
@@ -144,7 +125,8 @@ __global__ void __launch_bounds__(256) bn_res_act_bwd_reduce_kernel(
   publish_sums(s_sum, sums, C, w.c0, w.active, acc1, acc2);
 }
 
-__global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ sums,
+template <typename T>
+__global__ void __launch_bounds__(256) channel_stats_kernel(const T* __restrict__ y, float* __restrict__ sums,
                                                             unsigned total, int C) {
   extern __shared__ float s_sum[];       // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
@@ -189,20 +171,19 @@ int blocks_for(size_t total, int C, int cap) {
 }  // namespace
 
 void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
-                           void* out, size_t npix, int C, float slope, float inv_count, float eps, cudaStream_t stream) {
+                           void* out, size_t npix, int C, float slope, float inv_count, float eps, int es,
+                           cudaStream_t stream) {
   const size_t total = npix * (size_t)(C / 8);
-  bn_res_act_fwd_kernel<<<blocks_for(total, C, 148 * 16), 256, 0, stream>>>(
-      (const __nv_bfloat16*)y, stats, gamma, beta, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (unsigned)total, C,
-      slope, inv_count, eps);
+  MINE_DISPATCH_ES(es, T, (bn_res_act_fwd_kernel<T><<<blocks_for(total, C, 148 * 16), 256, 0, stream>>>(
+      (const T*)y, stats, gamma, beta, (const T*)res, (T*)out, (unsigned)total, C, slope, inv_count, eps)));
 }
 
 void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void* y, const float* stats, void* g_out,
-                                  float* sums, size_t npix, int C, float slope, float inv_count, float eps,
+                                  float* sums, size_t npix, int C, float slope, float inv_count, float eps, int es,
                                   cudaStream_t stream) {
   const size_t total = npix * (size_t)(C / 8);
-  bn_res_act_bwd_reduce_kernel<<<blocks_for(total, C, 148 * 8), 256, 2 * C * sizeof(float), stream>>>(
-      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)y, stats, (__nv_bfloat16*)g_out, sums,
-      (unsigned)total, C, slope, inv_count, eps);
+  MINE_DISPATCH_ES(es, T, (bn_res_act_bwd_reduce_kernel<T><<<blocks_for(total, C, 148 * 8), 256, 2 * C * sizeof(float), stream>>>(
+      (const T*)dout, (const T*)out, (const T*)y, stats, (T*)g_out, sums, (unsigned)total, C, slope, inv_count, eps)));
 }
 
 void launch_bn_update_running(const float* stats, float* running_mean, float* running_var, long long* num_batches, int C,
@@ -212,10 +193,10 @@ void launch_bn_update_running(const float* stats, float* running_mean, float* ru
                                                                1.f / count, unbias, momentum);
 }
 
-void launch_channel_stats(const void* y, float* sums, size_t npix, int C, cudaStream_t stream) {
+void launch_channel_stats(const void* y, float* sums, size_t npix, int C, int es, cudaStream_t stream) {
   const size_t total = npix * (size_t)(C / 8);
-  channel_stats_kernel<<<blocks_for(total, C, 148 * 8), 256, 2 * C * sizeof(float), stream>>>(
-      (const __nv_bfloat16*)y, sums, (unsigned)total, C);
+  MINE_DISPATCH_ES(es, T, (channel_stats_kernel<T><<<blocks_for(total, C, 148 * 8), 256, 2 * C * sizeof(float), stream>>>(
+      (const T*)y, sums, (unsigned)total, C)));
 }
 
 }  // namespace mine

@@ -46,22 +46,22 @@ namespace mine {
 // ---- decoder_elem.cu (NHWC bf16) ---------------------------------------------------------------
 // pad_mode: 0 = reflection, 1 = replication (1 pixel); stats = [2, C] global (sum, sum of squares)
 void launch_bn_act_pad_fwd(const void* y, const float* stats, const float* gamma, const float* beta, void* out, int N,
-                           int H, int W, int C, int pad_mode, float inv_count, float eps, cudaStream_t stream);
+                           int H, int W, int C, int pad_mode, float inv_count, float eps, int es, cudaStream_t stream);
 void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* stats, const float* gamma,
                               const float* beta, void* g_out, float* sums, int N, int H, int W, int C, int pad_mode,
-                              float inv_count, float eps, cudaStream_t stream);
+                              float inv_count, float eps, int es, cudaStream_t stream);
 void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const float* gamma, const float* sums,
                          void* dy, float* dshared, float* dplane_bias, int B, int S, int H, int W, int C,
-                         float inv_count, float eps, cudaStream_t stream);
+                         float inv_count, float eps, int es, cudaStream_t stream);
 void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, void* dz, float* dbias, size_t npix,
-                     int use_alpha, cudaStream_t stream);
+                     int use_alpha, int es, cudaStream_t stream);
 }  // namespace mine
 
 namespace mine {
 // ---- conv_splitk.cu (split-K implicit GEMM for layers with few output tiles; fp32 partial sums + finalize) -------
 const char* launch_conv_splitk(const void* x, int N, int Hi, int Wi, int Ci, const void* wpack, int w_rows, int T,
                                const int* tap_y, const int* tap_x, int in_stride, float* out32, int Hg, int Wg, int Co,
-                               int TH, int TW, int ksplit, cudaStream_t stream);
+                               int TH, int TW, int ksplit, int es, cudaStream_t stream);
 void launch_splitk_finalize(const float* acc, void* y, float* stats, size_t npix, int C, cudaStream_t stream);
 }  // namespace mine
 
@@ -84,11 +84,12 @@ const char* launch_head_conv_direct(const void* apad, const float* wpk, const fl
 namespace mine {
 // ---- encoder_elem.cu (unpadded NHWC bf16, C a power of two in [16, 2048]) -------------------------------
 void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
-                           void* out, size_t npix, int C, float slope, float inv_count, float eps, cudaStream_t stream);
+                           void* out, size_t npix, int C, float slope, float inv_count, float eps, int es,
+                           cudaStream_t stream);
 void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void* y, const float* stats, void* g_out,
-                                  float* sums, size_t npix, int C, float slope, float inv_count, float eps,
+                                  float* sums, size_t npix, int C, float slope, float inv_count, float eps, int es,
                                   cudaStream_t stream);
-void launch_channel_stats(const void* y, float* sums, size_t npix, int C, cudaStream_t stream);
+void launch_channel_stats(const void* y, float* sums, size_t npix, int C, int es, cudaStream_t stream);
 void launch_bn_update_running(const float* stats, float* running_mean, float* running_var, long long* num_batches, int C,
                               float count, float momentum, cudaStream_t stream);
 }  // namespace mine

@@ -7,7 +7,14 @@ from mine_b200.ops import conv_engine as E
 from mine_b200.ops import cuda as K
 
 ap = argparse.ArgumentParser(); ap.add_argument("--only", default=None); ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16"])
+ap.add_argument("--out", default=None)
 args = ap.parse_args()
+E.set_precision(args.precision)
+ACT = E.ACT_DTYPE
+ES = 4 if args.precision == "tf32" else 2
+# compute roofline denominator: measured bf16 cuBLAS burst; TF32 tensor peak is nominally half of it
+PEAK_SCALE = 0.5 if args.precision == "tf32" else 1.0
 peaks = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
 dev = torch.device("cuda")
 flush = torch.zeros(64 * 1024 * 1024, device=dev)
@@ -32,8 +39,9 @@ rows = []
 
 def report(name, ms, bytes_, flops):
     gbs, tf = bytes_ / ms / 1e6, flops / ms / 1e9
-    rows.append((name, ms, gbs, gbs / peaks["hbm_gbs"], tf, tf / peaks["bf16_tflops"]))
-    print("%-34s %8.3f ms  %8.1f GB/s (%.2f of measured HBM)  %7.1f TFLOP/s (%.3f of measured bf16)" % rows[-1], flush=True)
+    rows.append((name, ms, gbs, gbs / peaks["hbm_gbs"], tf, tf / (peaks["bf16_tflops"] * PEAK_SCALE)))
+    print("%-34s %8.3f ms  %8.1f GB/s (%.2f of measured HBM)  %7.1f TFLOP/s (%.3f of measured bf16%s)" %
+          (rows[-1] + ("/2 = tf32" if PEAK_SCALE != 1.0 else "",)), flush=True)
 
 
 def want(name):
@@ -45,13 +53,13 @@ layers = [  # name, h (low-res for up), w, Ci, Co, up
     ("same_2_0", 32, 48, 128, 64, False), ("up_2_1", 32, 48, 64, 64, True), ("same_1_0", 64, 96, 64, 32, False),
     ("up_1_1", 64, 96, 32, 32, True), ("same_0_0", 128, 192, 32, 16, False), ("up_0_1", 128, 192, 16, 16, True)]
 for name, h, w, ci, co, up in layers:
-    xp = torch.randn(N, h + 2, w + 2, ci, device=dev).to(torch.bfloat16)
+    xp = torch.randn(N, h + 2, w + 2, ci, device=dev).to(ACT)
     wt = torch.randn(co, ci, 3, 3, device=dev) * 0.05
     stats = torch.zeros(2, co, device=dev)
     ho, wo = (2 * h, 2 * w) if up else (h, w)
-    dy = torch.randn(N, ho, wo, co, device=dev).to(torch.bfloat16)
+    dy = torch.randn(N, ho, wo, co, device=dev).to(ACT)
     fl = 2.0 * N * h * w * ci * co * (16 if up else 9)
-    by_f = xp.numel() * 2 + N * ho * wo * co * 2
+    by_f = xp.numel() * ES + N * ho * wo * co * ES
     if want("fprop_" + name):
         f = (lambda: E.conv_up_raw(xp, wt, stats=stats)) if up else (lambda: E.conv_same_raw(xp, wt, stats=stats))
         report("fprop_" + name, timeit(f), by_f, fl)
@@ -65,22 +73,22 @@ for name, h, w, ci, co, up in layers:
 # heads
 for s_, (h, w, c) in enumerate([(256, 384, 16), (128, 192, 32), (64, 96, 64), (32, 48, 128)]):
     if want("head_%d" % s_):
-        xp = torch.randn(N, h + 2, w + 2, c, device=dev).to(torch.bfloat16)
+        xp = torch.randn(N, h + 2, w + 2, c, device=dev).to(ACT)
         wt, b = torch.randn(4, c, 3, 3, device=dev) * 0.05, torch.zeros(4, device=dev)
-        report("head_%d" % s_, timeit(lambda: E.conv_same_raw(xp, wt, chan_bias=b, head=True)), xp.numel() * 2 + N * h * w * 17,
+        report("head_%d" % s_, timeit(lambda: E.conv_same_raw(xp, wt, chan_bias=b, head=True)), xp.numel() * ES + N * h * w * 17,
                2.0 * N * h * w * c * 4 * 9)
         del xp
 # elementwise companions on the largest activation
 if want("bn_act_pad_fwd"):
-    y = torch.randn(N, 256, 384, 16, device=dev).to(torch.bfloat16)
+    y = torch.randn(N, 256, 384, 16, device=dev).to(ACT)
     st = torch.stack([y.float().sum((0, 1, 2)), (y.float() ** 2).sum((0, 1, 2))]).contiguous()
     g, b = torch.ones(16, device=dev), torch.zeros(16, device=dev)
     cnt = float(N * 256 * 384)
-    report("bn_act_pad_fwd", timeit(lambda: E.ext().bn_act_pad_fwd(y, st, g, b, 0, cnt, 1e-5)), y.numel() * 4, 0)
-    dap = torch.randn(N, 258, 386, 16, device=dev).to(torch.bfloat16)
-    report("bn_act_bwd_reduce", timeit(lambda: E.ext().bn_act_bwd_reduce(dap, y, st, g, b, 0, cnt, 1e-5)), y.numel() * 6, 0)
+    report("bn_act_pad_fwd", timeit(lambda: E.ext().bn_act_pad_fwd(y, st, g, b, 0, cnt, 1e-5)), y.numel() * 2 * ES, 0)
+    dap = torch.randn(N, 258, 386, 16, device=dev).to(ACT)
+    report("bn_act_bwd_reduce", timeit(lambda: E.ext().bn_act_bwd_reduce(dap, y, st, g, b, 0, cnt, 1e-5)), y.numel() * 3 * ES, 0)
     gg, sums = E.ext().bn_act_bwd_reduce(dap, y, st, g, b, 0, cnt, 1e-5)
-    report("bn_bwd_apply", timeit(lambda: E.ext().bn_bwd_apply(gg, y, st, g, sums, 32, False, False, cnt, 1e-5)), y.numel() * 6, 0)
+    report("bn_bwd_apply", timeit(lambda: E.ext().bn_bwd_apply(gg, y, st, g, sums, 32, False, False, cnt, 1e-5)), y.numel() * 3 * ES, 0)
 # render
 if want("render"):
     from mine_b200 import geometry as geo
@@ -100,4 +108,4 @@ if want("ssim"):
     a, b = torch.rand(2, 3, 256, 384, device=dev), torch.rand(2, 3, 256, 384, device=dev)
     report("ssim_fwd(+partials) 2x3x256x384", timeit(lambda: K._ext.ssim_fwd(a, b, True)), a.numel() * 4 * 5, 0)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump([dict(zip(["kernel", "ms", "GBps", "frac_hbm", "TFLOPs", "frac_bf16"], r)) for r in rows], open("gpurun_out/kernel_bench.json", "w"), indent=1)
+json.dump([dict(zip(["kernel", "ms", "GBps", "frac_hbm", "TFLOPs", "frac_bf16"], r)) for r in rows], open(args.out or "gpurun_out/kernel_bench_%s.json" % args.precision, "w"), indent=1)

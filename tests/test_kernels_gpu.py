@@ -224,7 +224,10 @@ def test_cuda_graph_step_matches_eager(monkeypatch):
     le = te.train_step(items)          # ONE step from identical weights (a second Adam step moves every weight
     lg = tg.train_step(items)          # by ~lr regardless of its gradient, so later gradients are not comparable)
     assert tg._graph is not None
-    assert abs(le["loss"].item() - lg["loss"].item()) <= 2e-2 * abs(le["loss"].item())
+    rel_loss = abs(le["loss"].item() - lg["loss"].item()) / abs(le["loss"].item())
     # Adam turns fp noise on near-zero gradients into +-lr updates, so compare the gradients of the last step
     cos = torch.nn.functional.cosine_similarity(te.arena.grad, tg.arena.grad, dim=0).item()
-    assert cos > 0.99, cos
+    print("graph vs eager: relative loss difference %.3e, gradient cosine %.6f" % (rel_loss, cos))
+    # default precision (tf32): only the order of the fp32 atomics differs between the two runs
+    assert rel_loss <= 2e-3, rel_loss
+    assert cos > 0.999, cos

@@ -1,14 +1,23 @@
-"""Opt-in kernel variants: the CUDA-core MPI head (``csrc/head_direct.cu``) vs the tcgen05 head and the PyTorch
-specification, and variant 2 of the BatchNorm backward reduction vs the default kernel.
-Opt-in (``MINE_B200_TEST_OPTIN=1``) until the kernel has been run on hardware."""
+"""Kernel variants behind environment switches, each against its alternative and the PyTorch specification: the
+CUDA-core MPI head (``csrc/head_direct.cu``, bf16 operands) vs the tcgen05 head, the two BatchNorm backward
+reductions (register-coefficient kernel = default, shared-memory-coefficient kernel = ``MINE_B200_BN_REDUCE=old``),
+the fused sparse-point loss and the fused running-statistic update (both default on CUDA)."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MINE_B200_TEST_OPTIN", "0") != "1",
-                                 reason="opt-in kernels (MINE_B200_TEST_OPTIN=1)")]
+pytestmark = [pytest.mark.gpu]
+
+
+@pytest.fixture(autouse=True)
+def _bf16_operands():
+    """These variants are compared at bf16 operand precision (the direct head only exists there)."""
+    from mine_b200.ops import conv_engine as E
+    old = E.PRECISION
+    E.set_precision("bf16")
+    yield
+    E.set_precision(old)
 
 
 @pytest.mark.parametrize("c,n,h,w,alpha", [(16, 3, 40, 72, False), (32, 2, 33, 50, False), (16, 2, 16, 32, True)])
@@ -36,6 +45,7 @@ _REDUCE_SNIPPET = r"""
 import sys, torch
 sys.path.insert(0, {repo!r})
 from mine_b200.ops import conv_engine as E
+E.set_precision("bf16")
 g = torch.Generator().manual_seed(1)
 out = {{}}
 for c, pad in ((16, 0), (64, 1), (256, 0)):
@@ -58,7 +68,7 @@ def test_bn_backward_reduce_variant2_matches_variant1(tmp_path):
     import sys
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for tag, env in (("v1", {}), ("v2", {"MINE_B200_BN_REDUCE": "v2"})):
+    for tag, env in (("v1", {"MINE_B200_BN_REDUCE": "old"}), ("v2", {"MINE_B200_BN_REDUCE": "v2"})):
         path = str(tmp_path / (tag + ".pt"))
         r = subprocess.run([sys.executable, "-c", _REDUCE_SNIPPET.format(repo=repo), path], env=dict(os.environ, **env),
                            capture_output=True, text=True, timeout=300)
