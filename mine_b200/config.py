@@ -11,8 +11,11 @@ written by either system is readable by the other) but make the schema explicit:
 * keys that the reference ships but never reads ("dead keys") are accepted so that
   upstream yaml files load unchanged (including ``params_dtu.yaml``'s ``model.decoder_type``,
   which crashes the reference - SURVEY 2.8 item 2);
-* ``mpi.is_bg_depth_inf`` is honoured (the reference reads a never-defined key instead,
-  SURVEY 2.8 item 1); the legacy spelling ``mpi.render_tgt_rgb_depth`` is accepted as an alias.
+* background-depth handling keeps the reference's EFFECTIVE behaviour: upstream reads the never-defined key
+  ``mpi.render_tgt_rgb_depth``, so ``mpi.is_bg_depth_inf`` (true in its DTU preset) never
+  takes effect and released checkpoints were trained with the normalised depth.  Here ``mpi.render_tgt_rgb_depth``
+  is a real (default false) key with exactly that meaning; ``mpi.is_bg_depth_inf`` loads and is ignored unless
+  ``engine.honor_bg_depth_inf`` is set (breaks parity with upstream-trained checkpoints).
 """
 from __future__ import annotations
 
@@ -59,7 +62,8 @@ SCHEMA: Dict[str, tuple] = {
     # mpi
     "mpi.disparity_start": (float, 1.0),
     "mpi.disparity_end": (float, 0.001),
-    "mpi.is_bg_depth_inf": (bool, False),
+    "mpi.is_bg_depth_inf": (bool, False),           # dead upstream (see module docstring)
+    "mpi.render_tgt_rgb_depth": (bool, False),      # the key upstream actually reads for "background at infinity"
     "mpi.num_bins_coarse": (int, 32),
     "mpi.num_bins_fine": (int, 0),
     "mpi.valid_mask_threshold": (float, 2),
@@ -84,6 +88,7 @@ SCHEMA: Dict[str, tuple] = {
     "engine.precision": (str, "tf32"),              # tf32: fp32 tensors + TF32 tensor-core convs (reference numerics) | bf16: fast mode
     "engine.compute_dtype": (str, "bf16"),          # deprecated alias, ignored (see engine.precision)
     "engine.cuda_graph": (bool, False),
+    "engine.honor_bg_depth_inf": (bool, False),     # make mpi.is_bg_depth_inf effective (NOT reference behaviour)
     "engine.comm": (str, "p2p"),                    # p2p (own kernels over NVLink) | nccl (baseline)
     "engine.resume": (bool, True),                  # restore step/epoch/scheduler/RNG if present
     "training.seed": (int, 0),
@@ -93,7 +98,7 @@ SCHEMA: Dict[str, tuple] = {
     "training.max_steps": (int, 0),                 # 0 = no cap (used by tests / smoke runs)
 }
 
-ALIASES = {"mpi.render_tgt_rgb_depth": "mpi.is_bg_depth_inf"}
+ALIASES = {}
 
 # Runtime blackboard entries the reference stores inside the same dict.
 RUNTIME_KEYS = {

@@ -148,4 +148,9 @@ def restore_model(model_path, backbone, decoder, optimizer=None, logger=None) ->
                 logger.info("[MODEL_RESTORE] missing keys in %s model: %s" % (key, set(res.unexpected_keys)))
     if optimizer is not None and "optimizer" in ckpt:
         optimizer.load_state_dict(optimizer_from_reference(ckpt["optimizer"]))
-    return dict(ckpt.get("meta", {}))
+    meta = dict(ckpt.get("meta", {}))
+    if meta:
+        # only a checkpoint that carries optimizer state is a resumable training state; weights-only files
+        # (``checkpoint_%012d.pth``, upstream releases) are fine-tuning starting points
+        meta["has_optimizer"] = "optimizer" in ckpt
+    return meta

@@ -52,11 +52,34 @@ def set_precision(precision: str) -> None:
         _ext.set_operand_size(4 if precision == "tf32" else 2)
 
 
-def use_emulator(flag: bool, dtype: torch.dtype = torch.bfloat16) -> None:
-    """Route the engine's kernel calls to the PyTorch specification in ``emu.py`` (any device, tests only)."""
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest TF32-representable fp32 (10 explicit mantissa bits, ties away from zero = ``cvt.rna.tf32.f32``).
+    ``kind::tf32`` MMAs ignore the 13 low mantissa bits, i.e. truncate; every tensor-core operand is therefore rounded
+    once where it is produced (kernels: ``st8_op`` / ``store_operand``; framework-side producers: this function)."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def to_operand(t: torch.Tensor) -> torch.Tensor:
+    """Cast a framework tensor to the engine's operand storage type (bf16, or fp32 rounded to TF32)."""
+    if ACT_DTYPE == torch.float32:
+        t = t.float()
+        if _emulated:
+            from . import emu
+            if not emu.TF32_OPERANDS:          # exact-fp32 specification mode (CPU tier)
+                return t
+        r = round_tf32(t.detach())
+        return t + (r - t.detach()) if t.requires_grad else r      # straight-through: rounding has unit derivative
+    return t.to(ACT_DTYPE)
+
+
+def use_emulator(flag: bool, dtype: torch.dtype = torch.bfloat16, tf32_operands: bool = False) -> None:
+    """Route the engine's kernel calls to the PyTorch specification in ``emu.py`` (any device, tests only).
+    ``tf32_operands``: fp32 operands are truncated / rounded exactly like the tf32 kernels do (GPU comparisons)."""
     global _emulated, ACT_DTYPE
     from . import emu
     _emulated = bool(flag)
+    emu.TF32_OPERANDS = bool(flag and tf32_operands and dtype == torch.float32)
     if flag:
         ACT_DTYPE = dtype
     else:
@@ -457,7 +480,7 @@ class ConvEngine:
         y40 = smap[:, None] + pbias.reshape(b, s, 1, 1, -1)                        # [B,S,h,w,C]
         y40 = y40.reshape(n, *smap.shape[1:]).permute(0, 3, 1, 2)
         a = F.elu(blk.bn(y40)).permute(0, 2, 3, 1)                                 # NHWC fp32
-        xpad = pad_nhwc(a.to(ACT_DTYPE), "replicate")                        # feeds the upsample conv
+        xpad = pad_nhwc(to_operand(a), "replicate")                          # feeds the upsample conv
 
         outputs: Dict[int, torch.Tensor] = {}
         for i in range(4, -1, -1):

@@ -42,6 +42,20 @@ __device__ __forceinline__ void st8(float* p, const V8& v) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(v.f[4], v.f[5], v.f[6], v.f[7]);
 }
 
+// Store of a tensor-core OPERAND (activation / gradient that a convolution will read): fp32 storage is rounded to the
+// nearest TF32 value (cvt.rna, what cuDNN / cuBLAS do when they load fp32 data for TF32 math), because kind::tf32
+// ignores the 13 low mantissa bits - truncation would bias every product towards zero.  bf16: plain store.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void st8_op(__nv_bfloat16* p, const V8& v) { st8(p, v); }
+__device__ __forceinline__ void st8_op(float* p, const V8& v) {
+  *reinterpret_cast<float4*>(p) = make_float4(round_tf32(v.f[0]), round_tf32(v.f[1]), round_tf32(v.f[2]), round_tf32(v.f[3]));
+  *reinterpret_cast<float4*>(p + 4) = make_float4(round_tf32(v.f[4]), round_tf32(v.f[5]), round_tf32(v.f[6]), round_tf32(v.f[7]));
+}
+
 // host-side dispatch on the element size (2: bf16, 4: fp32)
 #define MINE_DISPATCH_ES(es, T, ...)                 \
   do {                                               \

@@ -49,6 +49,19 @@ struct WgradParams {
   int es;                                // operand element size: 2 = bf16, 4 = fp32 storage / TF32 math
   // filled by the launcher
   int a_cb, b_cb, a_slabs, b_slabs, co_blocks, ci_blocks, NB, taps_per_chunk, tap_chunks, stages, tmem_cols;
+  // TF32 (fp32 storage): MN-major operands exist only as 128-byte rows (32 fp32) with the 32-byte-atom swizzle.  A
+  // 16-channel tensor has 64-byte pixels, so one operand row holds TWO adjacent pixels ("diag" modes): the accumulator
+  // then holds the (half_a, half_b) cross terms and the epilogue keeps the two diagonal blocks.
+  //   pair = 2     : K rows are pairs of adjacent GEMM pixels (same-resolution layers); both diagonal blocks belong to
+  //                  the same weight gradient.
+  //   phase_pair   : sub-pixel (upsample) form, Co = Ci = 16: an A row holds the px = 0 / px = 1 gradients of one GEMM
+  //                  pixel (adjacent in dy), a B row the low-res pixels x + b, x + b + 1; diagonal block h is the
+  //                  gradient of phase (py, px = h).  Groups become the two py phases.
+  int pair;                              // 1, or 2
+  int phase_pair;                        // 0 / 1
+  int rows;                              // K rows per pixel tile
+  int a_pairdim, b_pairdim;              // operand read through the overlapping {32 = 2 pixels x 16 ch, W - 1, H, N} map
+  int NBp;                               // accumulator columns per tap = NB * (diag ? 2 : 1)
 };
 
 struct WgradLaunch {

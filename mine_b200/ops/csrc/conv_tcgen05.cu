@@ -435,6 +435,21 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // wgrad_taps
 // ------------------------------------------------------------------------------------------------
+// Operand rows are K (pixels, or pixel pairs in TF32 pair mode), MN (channels) is contiguous: MN-major descriptors.
+//   bf16 : rows of a_cb / b_cb channels (32/64/128 bytes) with the matching 16-byte-atom swizzle; one instruction
+//          covers 16 K rows = two 8-row groups SBO apart.
+//   tf32 : rows are always 128 bytes (32 fp32) in the SWIZZLE_128B_BASE32B layout (the only MN-major layout of
+//          kind::tf32; TMA swizzle 128B_ATOM_32B); the swizzle atom is 4 K rows, one instruction covers 8 K rows =
+//          two atoms SBO = 512 bytes apart.
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                   const WgradParams p) {
@@ -450,12 +465,14 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int nb = rem % p.ci_blocks; rem /= p.ci_blocks;
   const int mb = rem % p.co_blocks; rem /= p.co_blocks;
   const int tc = rem % p.tap_chunks; rem /= p.tap_chunks;
-  const int g = rem;
+  const int g = rem;                                     // group (phase); in phase-pair mode the py phase
+  const int gt = p.phase_pair ? 2 * g : g;               // row of the tap / offset tables (phase-pair: the px = 0 group)
   const int t0 = tc * p.taps_per_chunk;
   const int ntaps = min(p.taps_per_chunk, p.T - t0);
 
-  const int a_row = p.a_cb * p.es, b_row = p.b_cb * p.es;    // bytes per pixel row in the A / B slabs
-  const uint32_t a_slab = (uint32_t)p.KP * a_row, b_slab = (uint32_t)p.KP * b_row;
+  const bool tf32 = p.es == 4;
+  const int a_row = tf32 ? 128 : p.a_cb * p.es, b_row = tf32 ? 128 : p.b_cb * p.es;   // bytes per K row
+  const uint32_t a_slab = (uint32_t)p.rows * a_row, b_slab = (uint32_t)p.rows * b_row;
   const uint32_t a_bytes = a_slab * p.a_slabs;
   const uint32_t b_tap_bytes = b_slab * p.b_slabs;
   const uint32_t stage_bytes = ((a_bytes + b_tap_bytes * p.taps_per_chunk + 1023u) / 1024u) * 1024u;
@@ -481,6 +498,7 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
+      const int b_cblocks = p.b_slabs / 2;               // channel blocks per parity of the B operand (diag modes, Ci >= 32)
       for (int i = 0; i < my_tiles; ++i) {
         const int tid = blockIdx.x + i * gridDim.x;
         const int n_img = tid / tiles_per_img, tt = tid - n_img * tiles_per_img;
@@ -490,45 +508,61 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         if (i >= p.stages) mbar_wait(&empty_bar[s], (round - 1) & 1);
         uint8_t* a_dst = smem_aligned + (size_t)s * stage_bytes;
         mbar_expect_tx(&full_bar[s], a_bytes + b_tap_bytes * ntaps);
-        const int dy_y = oy0 * p.dy_stride + p.dy_oy[g], dy_x = ox0 * p.dy_stride + p.dy_ox[g];
-        for (int sl = 0; sl < p.a_slabs; ++sl)
-          tma_load_4d(&map_dy, &full_bar[s], a_dst + sl * a_slab, (mb * p.a_slabs + sl) * p.a_cb, dy_x, dy_y, n_img);
+        const int dy_y = oy0 * p.dy_stride + p.dy_oy[gt], dy_x = ox0 * p.dy_stride + p.dy_ox[gt];
+        if (p.a_pairdim) {
+          tma_load_4d(&map_dy, &full_bar[s], a_dst, 0, dy_x, dy_y, n_img);
+        } else {
+          for (int sl = 0; sl < p.a_slabs; ++sl)
+            tma_load_4d(&map_dy, &full_bar[s], a_dst + sl * a_slab, (mb * p.a_slabs + sl) * p.a_cb, dy_x, dy_y, n_img);
+        }
         for (int t = 0; t < ntaps; ++t) {
           uint8_t* b_dst = a_dst + a_bytes + (size_t)t * b_tap_bytes;
-          const int iy = oy0 * p.x_stride + p.tap_y[g][t0 + t], ix = ox0 * p.x_stride + p.tap_x[g][t0 + t];
-          for (int sl = 0; sl < p.b_slabs; ++sl)
-            tma_load_4d(&map_x, &full_bar[s], b_dst + sl * b_slab, (nb * p.b_slabs + sl) * p.b_cb, ix, iy, n_img);
+          const int iy = oy0 * p.x_stride + p.tap_y[gt][t0 + t], ix = ox0 * p.x_stride + p.tap_x[gt][t0 + t];
+          if (p.b_pairdim) {
+            tma_load_4d(&map_x, &full_bar[s], b_dst, 0, ix, iy, n_img);
+          } else if (p.pair == 2 || p.phase_pair) {
+            // slab order (parity q, channel block): accumulator column = q * NB + channel
+            for (int sl = 0; sl < p.b_slabs; ++sl) {
+              const int q = sl / b_cblocks, cbk = sl - q * b_cblocks;
+              tma_load_4d(&map_x, &full_bar[s], b_dst + sl * b_slab, (nb * b_cblocks + cbk) * p.b_cb, ix + q * p.x_stride, iy, n_img);
+            }
+          } else {
+            for (int sl = 0; sl < p.b_slabs; ++sl)
+              tma_load_4d(&map_x, &full_bar[s], b_dst + sl * b_slab, (nb * p.b_slabs + sl) * p.b_cb, ix, iy, n_img);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t lta = layout_type_for(a_row), ltb = layout_type_for(b_row);
-      // A: when Co < 128 the missing MN blocks alias block 0 (LBO = 0): rows >= Co are copies and never stored
+      const uint32_t lta = tf32 ? 1u : layout_type_for(a_row), ltb = tf32 ? 1u : layout_type_for(b_row);
+      const int kpi = 32 / p.es;                         // K rows per instruction: 16 (bf16) or 8 (tf32)
+      const uint32_t sbo_a = tf32 ? 512u : 8u * a_row, sbo_b = tf32 ? 512u : 8u * b_row;
+      // A: M = 128 rows = MN blocks LBO apart.  One slab: LBO = 0 (blocks alias block 0, rows >= Co are copies and never
+      // stored).  Several slabs but fewer than the instruction needs (tf32, Co = 64): the blocks past Co read the bytes
+      // that follow (finite operand data); their accumulator rows are never stored either.
       const uint32_t a_lbo = (p.a_slabs > 1) ? a_slab : 0u;
-      // B: the tap tiles of a stage are consecutive [KP][b_cb] slabs, b_slab apart == the MN-block stride of the
-      // MN-major descriptor, so ONE instruction spans several taps: N = nblk * b_cb (<= 256).  A single thread
-      // issues every MMA, so few wide instructions instead of many 16-column ones is what keeps the tensor
-      // pipe busy for the 16/32-channel layers.
+      // B: the tap tiles of a stage are consecutive slabs, b_slab apart == the MN-block stride of the MN-major
+      // descriptor, so ONE instruction spans several taps: N = nblk * block width (<= 256).  A single thread issues every
+      // MMA, so few wide instructions instead of many narrow ones is what keeps the tensor pipe busy for the
+      // 16/32-channel layers.
+      const int bw = tf32 ? 32 : p.b_cb;                 // accumulator columns per MN block of B
       const int total_blocks = ntaps * p.b_slabs;
-      const int blk_per_mma = 256 / p.b_cb;
-      const bool tf32 = p.es == 4;
-      const int kpi = 32 / p.es;
-      const uint64_t da0 = make_smem_desc(0, a_lbo, 8u * a_row, lta);
-      const uint64_t db0 = make_smem_desc(0, b_slab, 8u * b_row, ltb);
+      const int blk_per_mma = 256 / bw;
+      const uint64_t da0 = make_smem_desc(0, a_lbo, sbo_a, lta);
+      const uint64_t db0 = make_smem_desc(0, b_slab, sbo_b, ltb);
       for (int i = 0; i < my_tiles; ++i) {
         const int s = i % p.stages, round = i / p.stages;
         mbar_wait(&full_bar[s], round & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
         const uint32_t b_addr = a_addr + a_bytes;
-        for (int k = 0; k < p.KP / kpi; ++k) {
-          // kpi K rows (pixels) per instruction: 16 bf16 = two 8-row groups SBO apart, 8 tf32 = one group
+        for (int k = 0; k < p.rows / kpi; ++k) {
           const uint64_t da = da0 + (uint64_t)((a_addr + k * kpi * a_row) >> 4);
           for (int b0 = 0; b0 < total_blocks; b0 += blk_per_mma) {
             const int nblk = min(blk_per_mma, total_blocks - b0);
             const uint64_t db = db0 + (uint64_t)((b_addr + b0 * b_slab + k * kpi * b_row) >> 4);
-            umma(tf32, tmem_base + b0 * p.b_cb, da, db, make_idesc(128, nblk * p.b_cb, 1, 1, tf32), (i > 0 || k > 0) ? 1u : 0u);
+            umma(tf32, tmem_base + b0 * bw, da, db, make_idesc(128, nblk * bw, 1, 1, tf32), (i > 0 || k > 0) ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[s]);
@@ -537,23 +571,51 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     }
   } else {
     const int q = warp & 3;
-    const int co = mb * 128 + q * 32 + lane;            // TMEM lane == output-channel row
+    const int m = q * 32 + lane;                           // TMEM lane == accumulator row
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     if (my_tiles > 0) {
-      for (int t = 0; t < ntaps; ++t) {
-        for (int c0 = 0; c0 < p.NB; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.NB + c0), v);
-          if (co >= p.Co) continue;
-          const int ci = nb * p.NB + c0;
-          if (ci >= p.Ci) continue;
-          float* dst = p.dw + (((size_t)(g * p.T + t0 + t) * p.Co + co) * p.Ci + ci);
+      if (p.pair == 2 || p.phase_pair) {
+        // rows: m = half * Co + co (Co == 16); columns of tap t: t * NBp + half' * NB + ci.  Only the diagonal
+        // (half == half') blocks are wanted: pixel-pair mode adds both into the same gradient, phase-pair mode stores
+        // block h as the gradient of phase (py, px = h).
+        const int par = m / p.Co, co = m - par * p.Co;
+        if (q == 0) {
+          for (int t = 0; t < ntaps; ++t) {
+            for (int pp = 0; pp < 2; ++pp) {
+              for (int c0 = 0; c0 < p.NB; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + (uint32_t)(t * p.NBp + pp * p.NB + c0), v);
+                const int ci = nb * p.NB + c0;
+                if (par != pp || ci >= p.Ci) continue;
+                const int gd = p.phase_pair ? 2 * g + pp : g;
+                float* dst = p.dw + (((size_t)(gd * p.T + t0 + t) * p.Co + co) * p.Ci + ci);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
-                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                         : "memory");
+                for (int j = 0; j < 16; j += 4) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                               "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                               : "memory");
+                }
+              }
+            }
+          }
+        }
+      } else {
+        const int co = mb * 128 + m;
+        for (int t = 0; t < ntaps; ++t) {
+          for (int c0 = 0; c0 < p.NB; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.NB + c0), v);
+            if (co >= p.Co) continue;
+            const int ci = nb * p.NB + c0;
+            if (ci >= p.Ci) continue;
+            float* dst = p.dw + (((size_t)(g * p.T + t0 + t) * p.Co + co) * p.Ci + ci);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+            }
           }
         }
       }
@@ -599,23 +661,50 @@ static CUtensorMapDataType dtype_for(int es) { return es == 4 ? CU_TENSOR_MAP_DA
 static std::map<MapKey, CUtensorMap> g_maps;
 static std::mutex g_maps_mu;
 
-// NHWC activation: dims {C, W, H, N}; box {cb, bw, bh, 1}; element stride es on W and H.
-static const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int cb, int bw, int bh, int es,
-                            int esz) {
-  MapKey key{ptr, C, W, H, N, cb, bw * es, bh * es, 1, es, es, 4, esz};
+// NHWC activation: dims {C, W, H, N}; box {cb, bw * esx, bh * esy, 1}; element strides esx / esy on W / H (the box then
+// holds bw x bh pixels).  mn32: SWIZZLE_128B with 32-byte atoms (MN-major kind::tf32 operands), else by row bytes.
+static const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int cb, int bw, int bh, int esx,
+                            int esy, int esz, bool mn32 = false) {
+  MapKey key{ptr, C, W, H, N, cb, bw * esx, bh * esy, mn32 ? 2 : 1, esx, esy, 4, esz};
   std::lock_guard<std::mutex> lock(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return nullptr; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * esz, (cuuint64_t)W * C * esz, (cuuint64_t)H * W * C * esz};
-  cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1};
-  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)(bw * esx), (cuuint32_t)(bh * esy), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)esx, (cuuint32_t)esy, 1};
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return "cuTensorMapEncodeTiled is not available from this driver";
   CUresult r = enc(out, dtype_for(esz), 4, const_cast<void*>(ptr), dims, strides, box,
-                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cb * esz),
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      mn32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle_for(cb * esz),
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (bad shape / stride / alignment)";
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = *out;
+  return nullptr;
+}
+
+// 16-channel fp32 NHWC activation read as 128-byte rows of TWO ADJACENT pixels (the "diag" modes of the TF32 weight
+// gradient): dims {32 (2 pixels x 16 channels, contiguous), W - 1 (row start: any pixel, stride ONE pixel - the rows of
+// this view overlap), H, N}; box {32, bw * esx, bh * esy, 1} with element strides esx / esy -> bw x bh rows.  A start
+// at the last pixel of a line is out of bounds (zero row), so a row never straddles two image lines.
+static const char* overlap32_map(CUtensorMap* out, const void* ptr, int W, int H, int N, int bw, int bh, int esx, int esy) {
+  MapKey key{ptr, 32, W, H, N, 32, bw * esx, bh * esy, 3, esx, esy, 4, 4};
+  std::lock_guard<std::mutex> lock(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return nullptr; }
+  if (W < 2) return "pair map: tensor too narrow";
+  cuuint64_t dims[4] = {32, (cuuint64_t)(W - 1), (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {64, (cuuint64_t)W * 64, (cuuint64_t)H * W * 64};
+  cuuint32_t box[4] = {32, (cuuint32_t)(bw * esx), (cuuint32_t)(bh * esy), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)esx, (cuuint32_t)esy, 1};
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return "cuTensorMapEncodeTiled is not available from this driver";
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the pair map (bad shape / stride / alignment)";
   if (g_maps.size() > 4096) g_maps.clear();
   g_maps[key] = *out;
   return nullptr;
@@ -653,7 +742,11 @@ __device__ __forceinline__ bool phase_has(int p, int a, int k) {      // does 3-
   return p == 0 ? (a == 0 ? k == 0 : k >= 1) : (a == 0 ? k <= 1 : k == 2);
 }
 __device__ __forceinline__ void store_operand(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
-__device__ __forceinline__ void store_operand(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_operand(float* p, float v) {   // round to nearest TF32 (the MMA would truncate)
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  *p = __uint_as_float(r);
+}
 template <typename T>
 __global__ void pack_weights_kernel(const float* __restrict__ w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co,
                                     int Ci, int mode, int rows_pad, T* __restrict__ out, int total) {
@@ -734,7 +827,7 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   if (smem < smem_floor) smem = smem_floor;
   if (smem > 200u * 1024u) smem = 200u * 1024u;
   CUtensorMap mx, mw;
-  const char* e = nhwc_map(&mx, L.x, p.Ci, L.Wi, L.Hi, p.N, p.KB, p.TW, p.TH, p.in_stride, p.es);
+  const char* e = nhwc_map(&mx, L.x, p.Ci, L.Wi, L.Hi, p.N, p.KB, p.TW, p.TH, p.in_stride, p.in_stride, p.es);
   if (e) return e;
   e = weight_map(&mw, L.w, p.Ci, L.w_rows, p.G * p.T, p.KB, p.BN, p.es);
   if (e) return e;
@@ -757,54 +850,95 @@ const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
   WgradParams p = L.p;
   if (p.TH * p.TW != p.KP || p.KP % 16 || p.KP < 32 || p.KP > 256) return "wgrad pixel tile must be 32..256 pixels";
   if (p.es != 2 && p.es != 4) return "operand element size must be 2 (bf16) or 4 (fp32/tf32)";
-  // operand slabs: channel block = min(C, 128 bytes worth) with the matching swizzle
-  const int cbmax = 128 / p.es;
-  p.a_cb = p.Co < cbmax ? p.Co : cbmax;
-  p.b_cb = p.Ci < cbmax ? p.Ci : cbmax;
-  if (p.a_cb * p.es != 32 && p.a_cb * p.es != 64 && p.a_cb * p.es != 128) return "Co must span 32/64 bytes or a multiple of 128 bytes";
-  if (p.b_cb * p.es != 32 && p.b_cb * p.es != 64 && p.b_cb * p.es != 128) return "Ci must span 32/64 bytes or a multiple of 128 bytes";
-  if (p.Co % p.a_cb || p.Ci % p.b_cb) return "channels must be a multiple of the slab width";
-  // M = 128 rows = 128 / a_cb MN blocks LBO apart: all real when Co >= 128; one slab aliased by LBO = 0 when Co == a_cb;
-  // otherwise (fp32, Co = 64) the blocks past Co read the bytes that follow (finite operand data) and their
-  // accumulator rows are never stored
-  p.a_slabs = (p.Co < 128 ? p.Co : 128) / p.a_cb;
-  p.co_blocks = (p.Co + 127) / 128;
+  if (p.x_stride < 1) p.x_stride = 1;
+  const bool tf32 = p.es == 4;
+  p.pair = 1; p.phase_pair = 0; p.a_pairdim = p.b_pairdim = 0;
   p.NB = p.Ci < 128 ? p.Ci : 128;                        // N per accumulator
-  p.b_slabs = p.NB / p.b_cb;
   if (p.Ci % p.NB) return "Ci must be <= 128 or a multiple of 128";
   p.ci_blocks = p.Ci / p.NB;
-  p.taps_per_chunk = 512 / p.NB;
+  if (!tf32) {
+    // operand slabs: channel block = min(C, 64) with the matching swizzle
+    p.a_cb = p.Co < 64 ? p.Co : 64;
+    p.b_cb = p.Ci < 64 ? p.Ci : 64;
+    if (p.a_cb != 16 && p.a_cb != 32 && p.a_cb != 64) return "Co must be 16/32/multiple of 64";
+    if (p.b_cb != 16 && p.b_cb != 32 && p.b_cb != 64) return "Ci must be 16/32/multiple of 64";
+    if (p.Co % p.a_cb || p.Ci % p.b_cb) return "channels must be a multiple of the slab width";
+    p.a_slabs = p.Co >= 128 ? 2 : 1;                     // M = 128 rows: 2 real slabs, or 1 slab aliased by LBO = 0
+    p.co_blocks = (p.Co + 127) / 128;
+    p.b_slabs = p.NB / p.b_cb;
+  } else if (p.Co == 16 || p.Ci == 16) {
+    // diag modes (see WgradParams): operand rows hold two adjacent pixels
+    if (p.Co != 16) return "TF32 diag modes expect the 16-channel tensor on the gradient (dy) side";
+    if (p.Ci != 16 && p.Ci % 32) return "Ci must be 16 or a multiple of 32";
+    p.a_cb = 16; p.a_slabs = 1; p.a_pairdim = 1; p.co_blocks = 1;
+    if (p.dy_stride == 2) {
+      if (p.G != 4 || p.x_stride != 1) return "TF32 phase-pair mode needs the four sub-pixel groups";
+      for (int g2 = 0; g2 < 2; ++g2) {          // group tables must be the canonical (py, px) ones: px only shifts x by one
+        if (p.dy_ox[2 * g2] != 0 || p.dy_ox[2 * g2 + 1] != 1 || p.dy_oy[2 * g2] != p.dy_oy[2 * g2 + 1]) return "phase-pair: unexpected group offsets";
+        for (int t = 0; t < p.T; ++t)
+          if (p.tap_x[2 * g2 + 1][t] != p.tap_x[2 * g2][t] + 1 || p.tap_y[2 * g2 + 1][t] != p.tap_y[2 * g2][t]) return "phase-pair: unexpected tap table";
+      }
+      p.phase_pair = 1;
+      if (p.Ci == 16) { p.b_cb = 16; p.b_slabs = 1; p.b_pairdim = 1; }
+      else { p.b_cb = 32; p.b_slabs = 2 * (p.NB / 32); }
+    } else {
+      if (p.dy_stride != 1 || p.x_stride != 1) return "TF32 pixel-pair mode needs unit strides";
+      if (p.TW % 2) return "TF32 pixel-pair mode needs an even tile width";
+      p.pair = 2;
+      if (p.Ci == 16) { p.b_cb = 16; p.b_slabs = 1; p.b_pairdim = 1; }
+      else { p.b_cb = 32; p.b_slabs = 2 * (p.NB / 32); }
+    }
+  } else {
+    if (p.Co % 32 || p.Ci % 32) return "TF32 weight gradient: channels must be 16 or a multiple of 32";
+    p.a_cb = p.b_cb = 32;
+    p.a_slabs = (p.Co < 128 ? p.Co : 128) / 32;
+    p.co_blocks = (p.Co + 127) / 128;
+    p.b_slabs = p.NB / 32;
+  }
+  p.NBp = p.NB * ((p.pair == 2 || p.phase_pair) ? 2 : 1);
+  p.rows = p.KP / p.pair;
+  if (p.rows % (32 / p.es)) return "pixel tile too small for the K step";
+  const uint32_t a_rowb = tf32 ? 128u : (uint32_t)p.a_cb * p.es, b_rowb = tf32 ? 128u : (uint32_t)p.b_cb * p.es;
+  p.taps_per_chunk = 512 / p.NBp;
   if (p.taps_per_chunk > p.T) p.taps_per_chunk = p.T;
   // keep the stage under ~96 KB (>= 2 stages in flight)
   for (;;) {
-    const uint32_t sb = (uint32_t)p.KP * p.a_cb * p.es * p.a_slabs + (uint32_t)p.KP * p.b_cb * p.es * p.b_slabs * p.taps_per_chunk;
+    const uint32_t sb = (uint32_t)p.rows * a_rowb * p.a_slabs + (uint32_t)p.rows * b_rowb * p.b_slabs * p.taps_per_chunk;
     if (sb <= 96 * 1024 || p.taps_per_chunk == 1) break;
     p.taps_per_chunk = (p.taps_per_chunk + 1) / 2;
   }
   p.tap_chunks = (p.T + p.taps_per_chunk - 1) / p.taps_per_chunk;
-  p.tmem_cols = next_pow2_cols(p.taps_per_chunk * p.NB);
+  p.tmem_cols = next_pow2_cols(p.taps_per_chunk * p.NBp);
   p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
   p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
   const uint32_t stage_bytes =
-      (((uint32_t)p.KP * p.a_cb * p.es * p.a_slabs + (uint32_t)p.KP * p.b_cb * p.es * p.b_slabs * p.taps_per_chunk + 1023u) / 1024u) * 1024u;
+      (((uint32_t)p.rows * a_rowb * p.a_slabs + (uint32_t)p.rows * b_rowb * p.b_slabs * p.taps_per_chunk + 1023u) / 1024u) * 1024u;
   int stages = (int)(192u * 1024u / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  CUtensorMap mdy, mx;
-  const char* e = nhwc_map(&mdy, L.dy, p.Co, L.dyW, L.dyH, p.N, p.a_cb, p.TW, p.TH, p.dy_stride, p.es);
-  if (e) return e;
-  if (p.x_stride < 1) p.x_stride = 1;
+  if (smem > 200u * 1024u) return "wgrad stage does not fit in shared memory";
+  if (p.TW * p.dy_stride > 256 || p.TH * p.dy_stride > 256) return "strided wgrad tile exceeds the TMA box limit";
   if (p.TW * p.x_stride > 256 || p.TH * p.x_stride > 256) return "strided wgrad tile exceeds the TMA box limit";
-  e = nhwc_map(&mx, L.x, p.Ci, L.xW, L.xH, p.N, p.b_cb, p.TW, p.TH, p.x_stride, p.es);
+  CUtensorMap mdy, mx;
+  const char* e;
+  if (p.phase_pair) e = overlap32_map(&mdy, L.dy, L.dyW, L.dyH, p.N, p.TW, p.TH, 2, 2);          // rows start at pixel 2 * ox
+  else if (p.a_pairdim) e = overlap32_map(&mdy, L.dy, L.dyW, L.dyH, p.N, p.TW / 2, p.TH, 2, 1);   // rows start at pixel 2 * j
+  else e = nhwc_map(&mdy, L.dy, p.Co, L.dyW, L.dyH, p.N, p.a_cb, p.TW, p.TH, p.dy_stride, p.dy_stride, p.es, tf32);
+  if (e) return e;
+  if (p.phase_pair && p.b_pairdim) e = overlap32_map(&mx, L.x, L.xW, L.xH, p.N, p.TW, p.TH, 1, 1);  // rows x + b, x + b + 1
+  else if (p.phase_pair) e = nhwc_map(&mx, L.x, p.Ci, L.xW, L.xH, p.N, p.b_cb, p.TW, p.TH, 1, 1, p.es, true);
+  else if (p.b_pairdim) e = overlap32_map(&mx, L.x, L.xW, L.xH, p.N, p.TW / 2, p.TH, 2, 1);
+  else if (p.pair == 2) e = nhwc_map(&mx, L.x, p.Ci, L.xW, L.xH, p.N, p.b_cb, p.TW / 2, p.TH, 2 * p.x_stride, p.x_stride, p.es, true);
+  else e = nhwc_map(&mx, L.x, p.Ci, L.xW, L.xH, p.N, p.b_cb, p.TW, p.TH, p.x_stride, p.x_stride, p.es, tf32);
   if (e) return e;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(wgrad_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  const int combos = p.G * p.tap_chunks * p.co_blocks * p.ci_blocks;
+  const int combos = (p.phase_pair ? p.G / 2 : p.G) * p.tap_chunks * p.co_blocks * p.ci_blocks;
   const int total_tiles = p.tiles_x * p.tiles_y * p.N;
   int splits = (148 * 2 + combos - 1) / combos;
   if (splits > total_tiles) splits = total_tiles;

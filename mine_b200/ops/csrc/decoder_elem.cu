@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) bn_act_pad_fwd_kernel(
       const float u = v.f[j] * k.a[j] + k.b[j];
       v.f[j] = u > 0.f ? u : (__expf(u) - 1.f);
     }
-    st8(out + (((size_t)n * Hp + py) * Wp + px) * C + c0, v);
+    st8_op(out + (((size_t)n * Hp + py) * Wp + px) * C + c0, v);
   }
 }
 
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
         d.f[j] = coef[j] * (gv.f[j] - mg[j] - xhat * mgx[j]);
         ds[j] += d.f[j];
       }
-      st8(dy + o, d);
+      st8_op(dy + o, d);
     }
     if (want_pb) {
       // lanes with equal (lane % cg) own the same channels (blockDim and cg are powers of two)
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float4* __restrict_
     for (int j = 4; j < 8; ++j) v0.f[j] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v1.f[j] = 0.f;
-    st8(dz + i * 16, v0);
+    st8_op(dz + i * 16, v0);
     st8(dz + i * 16 + 8, v1);
   }
 #pragma unroll

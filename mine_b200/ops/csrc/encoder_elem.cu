@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) bn_res_act_fwd_kernel(
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v.f[j] = v.f[j] > 0.f ? v.f[j] : slope * v.f[j];
-    st8(out + o, v);
+    st8_op(out + o, v);
   }
 }
 

@@ -19,6 +19,24 @@ import torch
 import torch.nn.functional as F
 
 ACT_DTYPE = torch.bfloat16          # ``conv_engine.use_emulator(True, torch.float32)`` switches to fp32 for tight tests
+# ``True``: fp32 operands behave like the tf32 kernels - the MMA reads only the 10 high mantissa bits (truncation) and
+# every operand PRODUCER rounds to the nearest TF32 value (``cvt.rna``).  ``False`` (default): exact fp32, the
+# device-independent contract the CPU tier tests the orchestration against.
+TF32_OPERANDS = False
+
+
+def _trunc(x: torch.Tensor) -> torch.Tensor:
+    """What a kind::tf32 MMA sees of an fp32 operand."""
+    if TF32_OPERANDS and x.dtype == torch.float32:
+        return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    return x
+
+
+def _round_op(x: torch.Tensor) -> torch.Tensor:
+    """Operand store of a producer kernel (``st8_op`` / ``store_operand``)."""
+    if TF32_OPERANDS and x.dtype == torch.float32:
+        return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return x
 
 
 def _gather(x: torch.Tensor, iy: torch.Tensor, ix: torch.Tensor) -> torch.Tensor:
@@ -35,7 +53,7 @@ def conv_taps(x, wpack, out, Hg, Wg, G, T, tap_y, tap_x, in_stride, Co, out_sy, 
     ox*in_stride + tap_x[g,t], :] @ wpack[g*T + t, :Co, :]^T`` (+ epilogue terms), for oy < Hg, ox < Wg."""
     n = x.shape[0]
     dev = x.device
-    xf, wf = x.float(), wpack.float()
+    xf, wf = _trunc(x.float()), _trunc(wpack.float())
     oy, ox = torch.arange(Hg, device=dev), torch.arange(Wg, device=dev)
     planes = max(int(planes_per_image), 1)
     for g in range(G):
@@ -72,7 +90,7 @@ def wgrad_taps(dy, x, dw, Hg, Wg, G, T, tap_y, tap_x, dy_stride, dy_oy, dy_ox, T
     """``dw[g*T + t, co, ci] += sum_{n, oy < Hg, ox < Wg} dy[n, oy*dy_stride + dy_oy[g], ox*dy_stride + dy_ox[g], co] *
     x[n, oy*x_stride + tap_y[g,t], ox*x_stride + tap_x[g,t], ci]`` (zero outside either tensor)."""
     dev = x.device
-    dyf, xf = dy.float(), x.float()
+    dyf, xf = _trunc(dy.float()), _trunc(x.float())
     oy, ox = torch.arange(Hg, device=dev), torch.arange(Wg, device=dev)
     for g in range(G):
         dyg = _gather(dyf, oy * dy_stride + dy_oy[g], ox * dy_stride + dy_ox[g])
@@ -108,7 +126,7 @@ def pack_weights(w: torch.Tensor, mode: int) -> torch.Tensor:
     rows_pad = (rows + 15) // 16 * 16
     out = torch.zeros((len(mats), rows_pad, mats[0].shape[1]), dtype=ACT_DTYPE, device=w.device)
     for i, m in enumerate(mats):
-        out[i, :rows] = m.to(ACT_DTYPE)
+        out[i, :rows] = _round_op(m.to(ACT_DTYPE))
     return out
 
 
@@ -135,7 +153,7 @@ def bn_act_pad_fwd(y, stats, gamma, beta, pad_mode, count, eps):
     _, _, a, b = _bn_coef(stats.float(), gamma.float(), beta.float(), count, eps)
     u = F.elu(y.float() * a + b)
     sy, sx = _pad_src(y.shape[1], pad_mode, y.device), _pad_src(y.shape[2], pad_mode, y.device)
-    return u[:, sy][:, :, sx].to(y.dtype).contiguous()
+    return _round_op(u[:, sy][:, :, sx].to(y.dtype).contiguous())
 
 
 def bn_act_bwd_reduce(dapad, y, stats, gamma, beta, pad_mode, count, eps):
@@ -162,7 +180,7 @@ def bn_bwd_apply(g, y, stats, gamma, sums, planes_per_image, want_shared, want_p
     dy = gamma.float() * invstd * (g.float() - sums[0] / count - xhat * (sums[1] / count))
     dshared = dy.reshape(n // s, s, h, w, c).sum(dim=1) if want_shared else None
     dpb = dy.sum(dim=(1, 2)) if want_plane_bias else None
-    return [dy.to(y.dtype), dshared, dpb]
+    return [_round_op(dy.to(y.dtype)), dshared, dpb]
 
 
 def head_bwd(g_mpi, mpi, sign, use_alpha):
@@ -172,7 +190,7 @@ def head_bwd(g_mpi, mpi, sign, use_alpha):
     if not use_alpha:
         d = torch.cat([d[:, :3], gm[:, 3:] * sign.reshape(-1, 1).float()], dim=1)
     dz = torch.zeros((*sign.shape, 16), dtype=ACT_DTYPE, device=mpi.device)
-    dz[..., :4] = d.reshape(*sign.shape, 4).to(ACT_DTYPE)
+    dz[..., :4] = _round_op(d.reshape(*sign.shape, 4).to(ACT_DTYPE))
     return [dz, d.sum(dim=0)]
 
 
@@ -186,7 +204,7 @@ def bn_res_act_fwd(y, stats, gamma, beta, residual, slope, count, eps):
     if residual is not None:
         u = u + residual.float()
     u = torch.where(u > 0, u, u * slope)
-    return u.to(y.dtype)
+    return _round_op(u.to(y.dtype))
 
 
 def bn_res_act_bwd_reduce(dout, out, y, stats, gamma, beta, slope, count, eps):

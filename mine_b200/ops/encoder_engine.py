@@ -48,13 +48,13 @@ def _out_size(n: int, k: int, stride: int) -> int:
 def _pack_fprop(w: torch.Tensor) -> torch.Tensor:
     """[Co,Ci,k,k] -> [k*k, Co, Ci] in the operand dtype."""
     co, ci, k, _ = w.shape
-    return w.detach().permute(2, 3, 0, 1).reshape(k * k, co, ci).to(E.ACT_DTYPE).contiguous()
+    return E.to_operand(w.detach().permute(2, 3, 0, 1).reshape(k * k, co, ci)).contiguous()
 
 
 def _pack_dgrad(w: torch.Tensor) -> torch.Tensor:
     """[Co,Ci,k,k] -> [k*k, Ci, Co]."""
     co, ci, k, _ = w.shape
-    return w.detach().permute(2, 3, 1, 0).reshape(k * k, ci, co).to(E.ACT_DTYPE).contiguous()
+    return E.to_operand(w.detach().permute(2, 3, 1, 0).reshape(k * k, ci, co)).contiguous()
 
 
 # per-axis decomposition of the stride-2 3x3 data gradient: dx[2q + p] = sum_a dy[q + OFF[p][a]] * W[K[p][a]]
@@ -307,9 +307,9 @@ class StemConv(torch.autograd.Function):
         ho, wo = _out_size(h, 7, 2), _out_size(w_, 7, 2)
         cols = F.unfold(x_nchw.float(), 7, padding=3, stride=2)                       # [N, 147, Ho*Wo], (c, ky, kx) order
         a = torch.zeros((n, ho, wo, STEM_K), dtype=E.ACT_DTYPE, device=x_nchw.device)
-        a[..., :147] = cols.transpose(1, 2).reshape(n, ho, wo, 147).to(E.ACT_DTYPE)
+        a[..., :147] = E.to_operand(cols.transpose(1, 2).reshape(n, ho, wo, 147))
         wp = torch.zeros((1, co, STEM_K), dtype=E.ACT_DTYPE, device=w.device)
-        wp[0, :, :147] = w.detach().reshape(co, 147).to(E.ACT_DTYPE)
+        wp[0, :, :147] = E.to_operand(w.detach().reshape(co, 147))
         stats = torch.zeros((2, co), dtype=torch.float32, device=w.device) if want_stats else None
         y = torch.empty((n, ho, wo, co), dtype=E.ACT_DTYPE, device=w.device)
         th, tw = pick_tile(ho, wo)
@@ -350,7 +350,7 @@ class SharedConv(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dmap):
         xpad, w = ctx.saved_tensors
-        dy = dmap.to(E.ACT_DTYPE).contiguous()
+        dy = E.to_operand(dmap).contiguous()
         dw = E.wgrad_same_raw(dy, xpad).to(w.dtype) if ctx.needs_input_grad[1] else None
         dx = E.dgrad_same_raw(dy, w) if ctx.needs_input_grad[0] else None
         return dx, dw
@@ -369,7 +369,7 @@ def _upsample_nhwc(x: torch.Tensor, size) -> torch.Tensor:
 def receptive_field_extension(dec, top_nchw: torch.Tensor, reducer=None) -> torch.Tensor:
     """``DepthDecoder.receptive_field_extension`` (reference ``depth_decoder.py:55-61,96-101``) on the engine:
     pool -> 1x1 -> pool -> 3x3 -> up -> 3x3 -> up -> 1x1, every conv followed by BN + LeakyReLU(0.1)."""
-    top = top_nchw.permute(0, 2, 3, 1).to(E.ACT_DTYPE).contiguous()
+    top = E.to_operand(top_nchw.permute(0, 2, 3, 1)).contiguous()
 
     def layer(x, blk):
         y, stats = Conv.apply(x, blk[0].weight, 1, blk[1].training)
@@ -382,7 +382,7 @@ def receptive_field_extension(dec, top_nchw: torch.Tensor, reducer=None) -> torc
 
 def shared_skip_map(feat_nchw: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """``conv3x3(reflect_pad(feat))`` as the fp32 NHWC map the plane-conv epilogue consumes."""
-    x = F.pad(feat_nchw.float(), (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1).to(E.ACT_DTYPE).contiguous()
+    x = E.to_operand(F.pad(feat_nchw.float(), (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1)).contiguous()
     return SharedConv.apply(x, w)
 
 
@@ -422,7 +422,7 @@ class EncoderEngine:
                        enabled=img.is_cuda and E.ACT_DTYPE == torch.bfloat16)
             with torch.autocast(**amp):
                 y = F.conv2d(x.contiguous(memory_format=torch.channels_last), e.conv1.weight, None, 2, 3)
-            y, stats = y.permute(0, 2, 3, 1).to(E.ACT_DTYPE).contiguous(), torch.empty(0, device=img.device)
+            y, stats = E.to_operand(y.permute(0, 2, 3, 1)).contiguous(), torch.empty(0, device=img.device)
         else:                                                      # stem as one im2col GEMM tap on the engine
             y, stats = StemConv.apply(x, e.conv1.weight, e.bn1.training)
         c1 = BNAct.apply(y, stats, e.bn1.weight, e.bn1.bias, None, True, e.bn1, reducer)

@@ -57,6 +57,15 @@ class PixelGrid:
         self.meshgrid = geo.pixel_grid(h, w, device=device)
 
 
+def bg_depth_inf(config: Mapping) -> bool:
+    """Background-at-infinity switch with the reference's effective semantics (``synthesis_task.py:265,273,427,466``
+    read ``mpi.render_tgt_rgb_depth``, which no upstream config defines): ``mpi.is_bg_depth_inf`` only counts when
+    ``engine.honor_bg_depth_inf`` is set."""
+    if bool(cfg_get(config, "mpi.render_tgt_rgb_depth", False)):
+        return True
+    return bool(cfg_get(config, "engine.honor_bg_depth_inf", False)) and bool(cfg_get(config, "mpi.is_bg_depth_inf", False))
+
+
 def _get_disparity_list(config: Mapping, B: int, device=None, generator=None) -> torch.Tensor:
     return S.disparity_planes(config, B, device=device, generator=generator)
 
@@ -151,8 +160,13 @@ class SynthesisTask:
         self._gen = None
         self._graph, self._graph_out, self._static = None, None, None
         self._want_graph = bool(cfg_get(config, "engine.cuda_graph", False)) and not is_val
-        if self.resume_meta and cfg_get(config, "engine.resume", True):
+        # Resume (step / epoch / scheduler / RNG) only from a full training state, i.e. a checkpoint that also holds the
+        # optimizer (``checkpoint_latest.pth``).  A weights-only ``training.pretrained_checkpoint_path`` is a
+        # fine-tuning start exactly as upstream: weights loaded, counters and learning rate fresh.
+        if self.resume_meta and self.resume_meta.get("has_optimizer", False) and cfg_get(config, "engine.resume", True):
             self._apply_resume(self.resume_meta)
+        elif self.resume_meta:
+            self.resume_meta = {}
 
     # ------------------------------------------------------------------------------------------
     # data
@@ -210,7 +224,7 @@ class SynthesisTask:
         return {"mpi_all_src_list": mpis, "disparity_all_src": disparity}
 
     def _bg_inf(self) -> bool:
-        return bool(cfg_get(self.config, "mpi.is_bg_depth_inf", False))
+        return bg_depth_inf(self.config)
 
     # ------------------------------------------------------------------------------------------
     # rendering
@@ -478,7 +492,9 @@ class SynthesisTask:
         self.epoch_step = int(meta.get("epoch_step", 0))
         if self.lr_scheduler is not None and meta.get("lr_scheduler"):
             self.lr_scheduler.load_state_dict(meta["lr_scheduler"])
-        if meta.get("rng") is not None:
+        # the saved generator state is rank 0's: restoring it everywhere would make all replicas draw identical
+        # disparity samples from then on, so the other ranks keep their own (seeded per rank) streams
+        if meta.get("rng") is not None and int(self.config.get("global_rank", 0)) == 0:
             try:
                 set_rng_state(meta["rng"])
             except Exception:      # RNG layouts differ across devices/torch versions: not fatal

@@ -1,4 +1,16 @@
-"""Worker for tests/test_multigpu.py (launched by torch.distributed.run, one rank per GPU)."""
+"""Worker for tests/test_multigpu.py (launched by torch.distributed.run, one rank per GPU).
+
+Sections (all results go into one JSON line printed by rank 0):
+  1. small SUM kernels vs NCCL (odd sizes, repeated calls, bit-identical across ranks)
+  2. in-place mean on the symmetric arena vs NCCL, P2P and multimem paths
+  3. timings of the gradient-sized all-reduce and the statistic exchange vs NCCL
+  4. IN-STEP audit: a full training step at the bench shape in which EVERY collective our communicator executes
+     (BatchNorm statistic sums on the compute stream, gradient-bucket means launched from autograd hooks on the side
+     stream) is checked against the NCCL result of the same input, for the P2P and the multimem path
+  5. data-parallel equivalence: gradients of the N-rank step (own communicator) vs the NCCL communicator, vs a
+     second NCCL run (control: how far two valid runs are apart), and vs ONE process stepping on the N x batch
+  6. soak: 200 CUDA-graph replays with the own communicator; parameters must stay bit-identical across ranks
+"""
 import json
 import os
 import sys
@@ -8,13 +20,16 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
+QUICK = os.environ.get("MINE_B200_MG_QUICK", "0") == "1"          # skip timings (sanitizer runs)
+
 
 def main():
     from mine_b200.parallel import bootstrap
+    from mine_b200.parallel.comm import Communicator
     from mine_b200.parallel.p2p import P2PComm
     ctx = bootstrap.init_distributed()
     dev, rank, world = ctx.device, ctx.rank, ctx.world_size
-    res = {}
+    res = {"world": world}
     comm = P2PComm(dev)
     res["multicast"] = bool(comm._small["mc"])
     # 1. small one-shot SUM, repeated (flag reuse / epoch bugs), odd sizes
@@ -52,12 +67,8 @@ def main():
             torch.cuda.synchronize()
             okb &= bool(torch.allclose(arena, ref, rtol=1e-5, atol=1e-6))
         res["mean_ok_multimem" if use_mm else "mean_ok_p2p"] = okb
-    # 3. timing of the gradient-sized all-reduce (152 MB) vs NCCL
-    big = 38 * 1024 * 1024
-    comm2 = P2PComm(dev)
-    a2 = comm2.alloc_symmetric(big)
-    nccl_buf = torch.zeros(big, device=dev)
 
+    # 3. timing of the gradient-sized all-reduce (152 MB) vs NCCL
     def timeit(fn, iters=10):
         for _ in range(3):
             fn()
@@ -70,42 +81,159 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
-    comm2.use_multimem = False
-    res["ms_152MB_p2p"] = timeit(lambda: comm2.allreduce_mean_(a2))
-    if res["multicast"]:
-        comm2.use_multimem = True
-        res["ms_152MB_multimem"] = timeit(lambda: comm2.allreduce_mean_(a2))
-    res["ms_152MB_nccl"] = timeit(lambda: (dist.all_reduce(nccl_buf), nccl_buf.mul_(1.0 / world)))
-    for n_small in (256, 4097):
-        small = torch.zeros(n_small, device=dev)
-        comm2.use_ll = True
-        res["us_small%d_ll" % n_small] = 1e3 * timeit(lambda: comm2.allreduce_sum_(small), 50)
-        comm2.use_ll = False
-        res["us_small%d_oneshot" % n_small] = 1e3 * timeit(lambda: comm2.allreduce_sum_(small), 50)
-        comm2.use_ll = True
-        res["us_small%d_nccl" % n_small] = 1e3 * timeit(lambda: dist.all_reduce(small), 50)
-    # 4. two-rank training step: own comm == NCCL comm (same weights, same data)
+    if not QUICK:
+        big = 38 * 1024 * 1024
+        comm2 = P2PComm(dev)
+        a2 = comm2.alloc_symmetric(big)
+        nccl_buf = torch.zeros(big, device=dev)
+        comm2.use_multimem = False
+        res["ms_152MB_p2p"] = timeit(lambda: comm2.allreduce_mean_(a2))
+        if res["multicast"]:
+            comm2.use_multimem = True
+            res["ms_152MB_multimem"] = timeit(lambda: comm2.allreduce_mean_(a2))
+        res["ms_152MB_nccl"] = timeit(lambda: (dist.all_reduce(nccl_buf), nccl_buf.mul_(1.0 / world)))
+        for n_small in (256, 4097):
+            small = torch.zeros(n_small, device=dev)
+            comm2.use_ll = True
+            res["us_small%d_ll" % n_small] = 1e3 * timeit(lambda: comm2.allreduce_sum_(small), 50)
+            comm2.use_ll = False
+            res["us_small%d_oneshot" % n_small] = 1e3 * timeit(lambda: comm2.allreduce_sum_(small), 50)
+            comm2.use_ll = True
+            res["us_small%d_nccl" % n_small] = 1e3 * timeit(lambda: dist.all_reduce(small), 50)
+        del comm2, a2, nccl_buf
+
+    # ---- whole-step checks -----------------------------------------------------------------------------------
     from mine_b200 import config as C
     from mine_b200.data.synthetic import synthetic_batch
+    from mine_b200.models.norm import set_stat_reducer
     from mine_b200.task import SynthesisTask
-    # 256x256: the receptive-field block then normalises over >= 16 values per channel also at 8 ranks
-    base = {"data.img_w": 256, "data.img_h": 256, "mpi.num_bins_coarse": 4, "data.visible_point_count": 32,
-            "model.imagenet_pretrained": False, "mpi.fix_disparity": True, "data.per_gpu_batch_size": 1,
-            "lr.backbone_lr": 0.0, "lr.decoder_lr": 0.0}
-    grads = {}
-    for kind in ("p2p", "nccl"):
+    small_shape = os.environ.get("MINE_B200_MG_SMALL", "0") == "1"
+    H, W, S, B = (128, 192, 8, 2) if small_shape else (256, 384, 32, 2)
+    base = {"data.img_w": W, "data.img_h": H, "mpi.num_bins_coarse": S, "data.visible_point_count": 256,
+            "model.imagenet_pretrained": False, "mpi.fix_disparity": True, "data.per_gpu_batch_size": B,
+            "lr.backbone_lr": 0.0, "lr.decoder_lr": 0.0, "engine.precision": os.environ.get("MINE_B200_MG_PRECISION", "tf32")}
+    res["step_shape"] = {"H": H, "W": W, "planes": S, "per_gpu_batch": B, "precision": base["engine.precision"]}
+    items_all = synthetic_batch(world * B, H, W, 256, seed=0)
+    mine = tuple({k: v[rank * B:(rank + 1) * B] for k, v in d.items()} for d in items_all)
+
+    class AuditComm(Communicator):
+        """Runs every collective through the own kernels AND through NCCL on a copy of the input; records the
+        worst absolute deviation relative to the largest NCCL result element."""
+        name = "audit(p2p)"
+
+        def __init__(self, inner):
+            self.inner, self.world_size, self.rank = inner, inner.world_size, inner.rank
+            self.graph_safe = False
+            self.sum_err, self.mean_err, self.calls_sum, self.calls_mean = [], [], 0, 0
+
+        def alloc_symmetric(self, numel):
+            return self.inner.alloc_symmetric(numel)
+
+        def allreduce_sum_(self, t):
+            ref = t.clone()
+            dist.all_reduce(ref)
+            out = self.inner.allreduce_sum_(t)
+            self.sum_err.append(torch.stack([(out - ref).abs().max(), ref.abs().max()]))
+            self.calls_sum += 1
+            return out
+
+        def allreduce_mean_(self, t, stream=None):
+            s = stream if stream is not None else torch.cuda.current_stream()
+            with torch.cuda.stream(s):
+                ref = t.clone()
+                dist.all_reduce(ref)
+                ref.mul_(1.0 / self.world_size)
+            out = self.inner.allreduce_mean_(t, stream=stream)
+            with torch.cuda.stream(s):
+                self.mean_err.append(torch.stack([(t - ref).abs().max(), ref.abs().max()]))
+            self.calls_mean += 1
+            return out
+
+        def barrier(self):
+            self.inner.barrier()
+
+    def build(kind, comm_obj=None):
         cfg = C.config_for_dataset("llff", dict(base, **{"engine.comm": kind}))
         cfg.update({"device": dev, "global_rank": rank})
         torch.manual_seed(0)
-        task = SynthesisTask(cfg, None)
-        items = synthetic_batch(world, 256, 256, 32, seed=0)
-        mine = tuple({k: v[rank:rank + 1] for k, v in d.items()} for d in items)
+        return SynthesisTask(cfg, None, comm=comm_obj)
+
+    grads = {}
+    for tag, use_mm in (("p2p", False), ("multimem", True)):
+        if use_mm and not res["multicast"]:
+            continue
+        inner = P2PComm(dev)
+        inner.use_multimem = use_mm
+        audit = AuditComm(inner)
+        task = build("p2p", audit)
+        losses = task.train_step(mine)
+        torch.cuda.synchronize()
+        se = torch.stack(audit.sum_err).cpu() if audit.sum_err else torch.zeros(1, 2)
+        me = torch.stack(audit.mean_err).cpu() if audit.mean_err else torch.zeros(1, 2)
+        res["audit_%s" % tag] = {
+            "stat_collectives": audit.calls_sum, "grad_buckets": audit.calls_mean,
+            "stat_max_rel_err": float((se[:, 0] / se[:, 1].clamp_min(1e-30)).max()),
+            "grad_max_rel_err": float((me[:, 0] / me[:, 1].clamp_min(1e-30)).max()),
+            "grad_max_abs_err": float(me[:, 0].max()), "loss": float(losses["loss"])}
+        gathered = [torch.empty_like(task.arena.grad) for _ in range(world)] if world <= 8 else None
+        dist.all_gather(gathered, task.arena.grad)
+        res["audit_%s" % tag]["grads_identical_across_ranks"] = all(torch.equal(gathered[0], g_) for g_ in gathered)
+        del gathered
+        grads[tag] = task.arena.grad.clone()
+        task.grad_sync.close()
+        del task, audit, inner
+        torch.cuda.empty_cache()
+    for tag in ("nccl", "nccl_repeat"):
+        task = build("nccl")
+        res["comm_nccl"] = task.comm.name
         task.train_step(mine)
         torch.cuda.synchronize()
-        grads[kind] = task.arena.grad.clone()
-        res["comm_" + kind] = task.comm.name
-    cos = torch.nn.functional.cosine_similarity(grads["p2p"], grads["nccl"], dim=0).item()
-    res["step_grad_cos"] = cos
+        grads[tag] = task.arena.grad.clone()
+        task.grad_sync.close()
+        del task
+        torch.cuda.empty_cache()
+    cos = lambda a, b: torch.nn.functional.cosine_similarity(grads[a].double(), grads[b].double(), dim=0).item()
+    res["cos_p2p_vs_nccl"] = cos("p2p", "nccl")
+    res["cos_nccl_vs_nccl_repeat"] = cos("nccl", "nccl_repeat")
+    if "multimem" in grads:
+        res["cos_multimem_vs_nccl"] = cos("multimem", "nccl")
+    # one process, N x batch (rank 0 computes; every rank builds the task because construction broadcasts)
+    single = build("p2p", Communicator())
+    if rank == 0:
+        out1 = single.train_step(tuple({k: v for k, v in d.items()} for d in items_all))
+        torch.cuda.synchronize()
+        g1 = single.arena.grad.double()
+        res["loss_single_process"] = float(out1["loss"])
+        res["cos_p2p_vs_single_process"] = torch.nn.functional.cosine_similarity(grads["p2p"].double(), g1, dim=0).item()
+        res["cos_nccl_vs_single_process"] = torch.nn.functional.cosine_similarity(grads["nccl"].double(), g1, dim=0).item()
+        res["relerr_p2p_vs_single_process"] = float((grads["p2p"].double() - g1).norm() / g1.norm())
+    del single
+    torch.cuda.empty_cache()
+    dist.barrier()
+
+    # 6. soak: graph replays with the own communicator (default path for this world size)
+    cfg = C.config_for_dataset("llff", dict(base, **{"engine.comm": "p2p", "engine.cuda_graph": True,
+                                                     "lr.backbone_lr": 1e-4, "lr.decoder_lr": 1e-4,
+                                                     "mpi.fix_disparity": False}))
+    cfg.update({"device": dev, "global_rank": rank})
+    torch.manual_seed(0)
+    task = SynthesisTask(cfg, None)
+    pool = []
+    for i in range(4):
+        it = synthetic_batch(world * B, H, W, 256, seed=10 + i)
+        pool.append(tuple({k: v[rank * B:(rank + 1) * B].to(dev) for k, v in d.items()} for d in it))
+    n_replays = int(os.environ.get("MINE_B200_MG_REPLAYS", "200"))
+    for i in range(n_replays):
+        out = task.train_step(pool[i % 4])
+    torch.cuda.synchronize()
+    res["soak"] = {"replays": n_replays, "graph": task._graph is not None, "comm": task.comm.name,
+                   "multimem": bool(getattr(task.comm, "use_multimem", False)), "final_loss": float(out["loss"])}
+    chk = task.arena.data.view(torch.int32).to(torch.int64).sum().reshape(1)
+    gathered = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(gathered, chk)
+    res["soak"]["params_bit_identical_across_ranks"] = all(int(g_) == int(gathered[0]) for g_ in gathered)
+    res["soak"]["params_finite"] = bool(torch.isfinite(task.arena.data).all())
+    res["comm_p2p"] = task.comm.name
     if rank == 0:
         print("RESULT " + json.dumps(res), flush=True)
     dist.barrier()

@@ -30,7 +30,10 @@ def test_config_merge_and_unknown_keys(tmp_path):
         C.config_for_dataset("llff", {"mpi.no_such_key": 1})
     dtu = C.config_for_dataset("dtu")                       # crashes upstream (model.decoder_type not in defaults)
     assert dtu["training.gpus"] == [1, 2, 3, 4, 5, 6, 7] and dtu["mpi.is_bg_depth_inf"] is True
-    assert C.get({"mpi.is_bg_depth_inf": True}, "mpi.render_tgt_rgb_depth") is True     # legacy alias
+    # reference-effective semantics: the DTU preset's flag is dead upstream (it reads mpi.render_tgt_rgb_depth)
+    from mine_b200.task import bg_depth_inf
+    assert bg_depth_inf(dtu) is False and bg_depth_inf({"mpi.render_tgt_rgb_depth": True}) is True
+    assert bg_depth_inf({"mpi.is_bg_depth_inf": True, "engine.honor_bg_depth_inf": True}) is True
     p = tmp_path / "params.yaml"
     C.dump_config(cfg, str(p))
     back = C.load_dumped_config(str(p), '{"data.per_gpu_batch_size": 1}')
@@ -82,7 +85,7 @@ def test_task_public_surface_and_shapes():
     assert set(vis) == {"src_disparity_syn", "tgt_disparity_syn", "tgt_imgs_syn", "tgt_mask_syn", "src_imgs_syn"}
 
 
-@pytest.mark.parametrize("extra", [{"mpi.num_bins_fine": 2}, {"mpi.use_alpha": True}, {"mpi.is_bg_depth_inf": True},
+@pytest.mark.parametrize("extra", [{"mpi.num_bins_fine": 2}, {"mpi.use_alpha": True}, {"mpi.render_tgt_rgb_depth": True},
                                    {"mpi.fix_disparity": True, "training.src_rgb_blending": False},
                                    {"loss.smoothness_lambda_v1": 0.5, "loss.smoothness_lambda_v2": 0.01}])
 def test_task_variants_train_one_step(extra):

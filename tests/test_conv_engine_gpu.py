@@ -99,7 +99,7 @@ def test_conv_up_fprop(n, h, w, ci, co):
     xp = F.pad(x, (1, 1, 1, 1), mode="replicate")
     y = E.conv_up_raw(_act(xp), wt)
     assert tuple(y.shape) == (n, 2 * h, 2 * w, co)
-    assert _rel(_nchw(y), ref) < _tol(1.5e-2, 2e-4)
+    assert _rel(_nchw(y), ref) < _tol(1.5e-2, 1e-3)     # phase weights are tap sums: not TF32-representable
 
 
 @pytest.mark.parametrize("n,h,w,ci,co", SHAPES)
@@ -134,7 +134,7 @@ def test_dgrad_and_wgrad_up(n, h, w, ci, co):
             out[:, :, py::2, px::2] = acc
     out.backward(dy)
     dx = E.dgrad_up_raw(_act(dy), wt.detach())
-    assert _rel(_nchw(dx), xp.grad) < _tol(1.5e-2, 2e-4)
+    assert _rel(_nchw(dx), xp.grad) < _tol(1.5e-2, 1e-3)
     dw = E.wgrad_up_raw(_act(dy), _act(xp.detach()))
     assert _rel(dw, wt.grad) < _tol(1e-2, 2e-4)
 
@@ -272,11 +272,11 @@ def test_kernels_match_emulator_contract():
         y = E.conv_up_raw(xlo, wt, plane_bias=pb, shared_map=sm, planes=2, stats=stats)
         return y, stats, E.dgrad_up_raw(dy, wt), E.wgrad_up_raw(dy, xlo)
     real = run()
-    E.use_emulator(True, E.ACT_DTYPE)
+    E.use_emulator(True, E.ACT_DTYPE, tf32_operands=True)
     try:
         spec = run()
     finally:
         E.use_emulator(False)
-    assert _rel(real[0], spec[0]) < _tol(1e-2, 2e-4) and _rel(real[2], spec[2]) < _tol(1e-2, 2e-4)
+    assert _rel(real[0], spec[0]) < _tol(1e-2, 1e-3) and _rel(real[2], spec[2]) < _tol(1e-2, 1e-3)
     assert torch.allclose(real[1], spec[1], rtol=2e-3, atol=1.0)
     assert _rel2(real[3], spec[3]) < _tol(2e-3, 2e-4)

@@ -22,6 +22,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mine_b200 import config as cfglib  # noqa: E402
 from mine_b200 import geometry as geo  # noqa: E402
 from mine_b200.ops import api as ops  # noqa: E402
+from mine_b200.task import bg_depth_inf  # noqa: E402
 from mine_b200.utils.misc import disparity_normalization_vis  # noqa: E402
 from mine_b200.utils.video_io import img_tensor_to_np, write_img_to_disk, write_video  # noqa: E402,F401
 
@@ -91,7 +92,7 @@ class VideoGenerator:
         packed = ops.pack_mpi(endpoints["mpi_all_src_list"][0])
         src_out = ops.render_src(packed, self.disparity_all_src, self.K_inv, self.img,
                                  bool(self.config.get("mpi.use_alpha", False)),
-                                 bool(cfglib.get(self.config, "mpi.is_bg_depth_inf", False)), blend=True)
+                                 bg_depth_inf(self.config), blend=True)
         self.mpi_packed = src_out["mpi"].contiguous()            # source-blended colours + sigma
         view = ops.unpack_mpi(self.mpi_packed)
         self.mpi_all_rgb_src, self.mpi_all_sigma_src = view[:, :, 0:3], view[:, :, 3:]
