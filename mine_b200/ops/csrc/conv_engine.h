@@ -30,6 +30,10 @@ struct ConvParams {
   int es;                                // operand element size: 2 = bf16 (kind::f16), 4 = fp32 storage (kind::tf32)
   // filled by the launcher
   int stages, tmem_cols, ipb;
+  // halo kernel (conv_halo.cu): every tap offset lies in a 3x3 window -> tap (g, t) = window origin + (rel_y, rel_x)
+  int halo_y0, halo_x0;
+  int8_t rel_y[4][16], rel_x[4][16];
+  int box_stride, w_tile_bytes, w_bytes;
 };
 
 struct ConvLaunch {
@@ -71,6 +75,8 @@ struct WgradLaunch {
 };
 
 const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream);
+// conv_halo.cu: returns true when the layer was eligible and has been launched (err set on launch failure)
+bool try_launch_conv_halo(const ConvLaunch& L, cudaStream_t stream, const char** err);
 void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co, int Ci, int mode,
                          int rows_pad, void* out, int es, cudaStream_t stream);
 const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream);

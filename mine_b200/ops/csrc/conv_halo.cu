@@ -1,0 +1,360 @@
+// Halo variant of the tcgen05 implicit-GEMM convolution for the narrow, high-resolution layers of the MPI decoder
+// (16..64 channels at full / half resolution: same-resolution 3x3 convs, the fused x2-upsample conv in its sub-pixel
+// form, the MPI heads, and the 3x3 data gradients).
+//
+// conv_taps_kernel (conv_tcgen05.cu) issues one TMA box per (tile, tap, k-block) plus the matching weight box: nine
+// activation re-loads of 32..128-byte rows and nine weight re-loads per 128-pixel tile.  For the narrow layers that
+// TMA row traffic - not HBM, not the tensor pipe - sets the time (profiles/ncu_head_0.txt: DRAM 7 %, tensor 3 %).
+// Here, per tile:
+//   * activations: THREE boxes of (TH + 2) x TW pixels (one per horizontal tap offset).  A vertical tap offset dy is
+//     a shift of dy * TW rows inside a box; with TW a multiple of 8 that shift is a whole number of 8-row swizzle
+//     atoms, so the K-major UMMA descriptor of tap (dy, dx) is just  box[dx] + dy * TW * row_bytes  - nine MMAs read
+//     three loads (2.4x - 2.7x fewer rows through the TMA unit);
+//   * weights: ALL taps / k-blocks of the layer stay resident in shared memory for the lifetime of the CTA (loaded once);
+//   * the sub-pixel (upsample) form keeps the four phase accumulators of a low-resolution tile in TMEM together, so
+//     one halo feeds 16 MMAs and the epilogue writes the 2x2 output pixels of every input pixel.
+// Pipeline / roles as in conv_taps_kernel: warp 0 TMA producer, warp 1 single-thread MMA issue (kind::f16 or
+// kind::tf32), warps 2..5 epilogue (tcgen05.ld, bias / shared map / BatchNorm partial sums / head activation),
+// persistent CTAs, TMEM accumulators double buffered across tiles.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "conv_common.cuh"
+#include "conv_engine.h"
+
+namespace mine {
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// MMA-issue loop of one CTA (single thread).  s_tab[(g * T + t) * kblocks + kb] = {A offset inside a halo set, B tile
+// address}, both in 16-byte descriptor units and constant for the lifetime of the CTA.
+template <bool TF32, int KS>
+__device__ __forceinline__ void halo_issue_loop(const ConvParams& p, const uint2* s_tab, uint8_t* ring, uint32_t set_bytes,
+                                                uint32_t tmem_base, uint64_t* full_bar, uint64_t* empty_bar,
+                                                uint64_t* accum_full, uint64_t* accum_empty, int total_work) {
+  const int row_bytes = p.KB * p.es;
+  const uint32_t idesc = make_idesc(128, p.BN, 0, 0, TF32);
+  const uint64_t desc0 = make_smem_desc(0, 16, 8u * row_bytes, layout_type_for(row_bytes));
+  const uint32_t lo0 = (uint32_t)desc0, hi = (uint32_t)(desc0 >> 32);
+  const int G = p.G, T = p.T, KBK = p.kblocks, BN = p.BN;
+  int s = 0, j = 0;
+  uint32_t par = 0;
+  for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
+    const int as = j & 1;
+    if (j >= 2) mbar_wait(&accum_empty[as], ((j >> 1) - 1) & 1);
+    tc_fence_after();
+    for (int kb = 0; kb < KBK; ++kb) {
+      mbar_wait(&full_bar[s], par);
+      tc_fence_after();
+      const uint32_t slot_lo = lo0 + (smem_u32(ring + (size_t)s * set_bytes) >> 4);
+      const uint2* tab = s_tab + kb;
+      uint32_t d_tmem = tmem_base + (uint32_t)(as * G * BN);
+      for (int g = 0; g < G; ++g, d_tmem += BN) {
+        uint32_t acc = kb ? 1u : 0u;
+        for (int t = 0; t < T; ++t, tab += KBK) {
+          const uint2 e = *tab;
+          const uint32_t a_lo = slot_lo + e.x, b_lo = lo0 + e.y;
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            umma_lohi<TF32>(d_tmem, a_lo + 2u * k, b_lo + 2u * k, hi, idesc, acc);
+            acc = 1u;
+          }
+        }
+      }
+      umma_commit(&empty_bar[s]);
+      if (++s == p.stages) { s = 0; par ^= 1u; }
+    }
+    umma_commit(&accum_full[as]);
+  }
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                 const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_full[2];
+  __shared__ __align__(8) uint64_t accum_empty[2];
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_stats[2][64];
+  __shared__ uint2 s_tab[4 * 16 * 4];                  // per (group, tap, k-block): {A offset, B tile address} >> 4
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int total_work = tiles * p.N;                  // w -> (tile, image); the G groups share one halo
+  const int row_bytes = p.KB * p.es;
+  const uint32_t box_bytes = (uint32_t)(p.TH + 2) * p.TW * row_bytes;
+  const uint32_t set_bytes = 3u * p.box_stride;
+  uint8_t* smem_aligned = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_smem = smem_aligned;                      // [G*T][kblocks] tiles of BN x KB, w_tile_bytes apart
+  uint8_t* ring = smem_aligned + p.w_bytes;            // stages x {3 boxes}
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&accum_full[s], 1); mbar_init(&accum_empty[s], 4); }
+    mbar_init(&w_bar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) (&s_stats[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < p.G * p.T * p.kblocks; i += blockDim.x) {
+    const int gt = i / p.kblocks, g = gt / p.T, t = gt - g * p.T;
+    const uint32_t a_off = (uint32_t)p.rel_x[g][t] * p.box_stride + (uint32_t)p.rel_y[g][t] * (uint32_t)(p.TW * row_bytes);
+    s_tab[i] = make_uint2(a_off >> 4, (smem_u32(w_smem) + (uint32_t)i * p.w_tile_bytes) >> 4);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: every (group, tap, k-block) tile once per CTA
+      const int gt_n = p.G * p.T;
+      mbar_expect_tx(&w_bar, (uint32_t)gt_n * p.kblocks * (uint32_t)p.BN * row_bytes);
+      for (int gt = 0; gt < gt_n; ++gt)
+        for (int kb = 0; kb < p.kblocks; ++kb)
+          tma_load_3d(&map_w, &w_bar, w_smem + (size_t)(gt * p.kblocks + kb) * p.w_tile_bytes, kb * p.KB, 0, gt);
+      int s = 0;
+      uint32_t par = 0;
+      bool ring_full = false;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tile = w % tiles, n_img = w / tiles;
+        const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+        const int iy = tile_y * p.TH + p.halo_y0, ix = tile_x * p.TW + p.halo_x0;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          if (ring_full) mbar_wait(&empty_bar[s], par ^ 1u);
+          mbar_expect_tx(&full_bar[s], 3u * box_bytes);
+          uint8_t* slot = ring + (size_t)s * set_bytes;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+            tma_load_4d(&map_x, &full_bar[s], slot + dx * p.box_stride, kb * p.KB, ix + dx, iy, n_img);
+          if (++s == p.stages) { s = 0; par ^= 1u; ring_full = true; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(&w_bar, 0);
+      const int ks = row_bytes / 32;
+#define HALO_ISSUE(TF, KS_) halo_issue_loop<TF, KS_>(p, s_tab, ring, set_bytes, tmem_base, full_bar, empty_bar, accum_full, accum_empty, total_work)
+      if (p.es == 4) { if (ks == 4) HALO_ISSUE(true, 4); else if (ks == 2) HALO_ISSUE(true, 2); else HALO_ISSUE(true, 1); }
+      else { if (ks == 4) HALO_ISSUE(false, 4); else if (ks == 2) HALO_ISSUE(false, 2); else HALO_ISSUE(false, 1); }
+#undef HALO_ISSUE
+    }
+  } else {
+    // ---------------- epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) ----------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ty = r / p.TW, tx = r - ty * p.TW;
+    const bool reg_stats = p.stats != nullptr;           // BN <= 32 (launcher): sums stay in registers across tiles
+    float ra1[16], ra2[16], rb1[16], rb2[16];
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) ra1[jj] = ra2[jj] = rb1[jj] = rb2[jj] = 0.f;
+    int j = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
+      const int tile = w % tiles, n_img = w / tiles;
+      const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+      const int oy = tile_y * p.TH + ty, ox = tile_x * p.TW + tx;
+      const bool valid = (oy < p.Hg) && (ox < p.Wg);
+      const int as = j & 1;
+      mbar_wait(&accum_full[as], (j >> 1) & 1);
+      tc_fence_after();
+      const float* pbias = p.plane_bias ? p.plane_bias + (size_t)n_img * p.Co : nullptr;
+      for (int g = 0; g < p.G; ++g) {
+        const int out_y = oy * p.out_sy + p.out_oy[g], out_x = ox * p.out_sx + p.out_ox[g];
+        const size_t out_pix = ((size_t)n_img * p.Ho + out_y) * p.Wo + out_x;
+        const uint32_t t_acc = tmem_base + (uint32_t)((as * p.G + g) * p.BN) + ((uint32_t)(q * 32) << 16);
+        const float* smap = nullptr;
+        if (p.shared_map && valid)
+          smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          // two 16-column loads in flight before the wait
+          uint32_t v[32];
+          const bool two = c0 + 16 < p.BN;
+          tmem_ld16_nowait(t_acc + (uint32_t)c0, v);
+          if (two) tmem_ld16_nowait(t_acc + (uint32_t)(c0 + 16), v + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = c0 + 16 * h;
+            if (h == 1 && !two) break;
+            if (cc >= p.Co) break;
+            float f[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(v[16 * h + jj]);
+            if (p.chan_bias) {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) if (cc + jj < p.Co) f[jj] += p.chan_bias[cc + jj];
+            }
+            if (pbias) {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) if (cc + jj < p.Co) f[jj] += pbias[cc + jj];
+            }
+            if (smap) {
+#pragma unroll
+              for (int jj = 0; jj < 16; jj += 4) {
+                const float4 m = *reinterpret_cast<const float4*>(smap + cc + jj);
+                f[jj] += m.x; f[jj + 1] += m.y; f[jj + 2] += m.z; f[jj + 3] += m.w;
+              }
+            }
+            if (reg_stats) {
+              if (cc == 0) {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) { const float x = valid ? f[jj] : 0.f; ra1[jj] += x; ra2[jj] += x * x; }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) { const float x = valid ? f[jj] : 0.f; rb1[jj] += x; rb2[jj] += x * x; }
+              }
+            }
+            if (valid) {
+              if (p.act == 1) {                     // MPI head: 4 real channels -> packed fp32 MPI (+ sign of sigma)
+                float4 o;
+                o.x = 1.f / (1.f + __expf(-f[0])); o.y = 1.f / (1.f + __expf(-f[1])); o.z = 1.f / (1.f + __expf(-f[2]));
+                o.w = p.head_alpha ? 1.f / (1.f + __expf(-f[3])) : fabsf(f[3]) + 1e-4f;
+                reinterpret_cast<float4*>(p.out)[out_pix] = o;
+                if (p.raw_out) reinterpret_cast<int8_t*>(p.raw_out)[out_pix] = f[3] >= 0.f ? (int8_t)1 : (int8_t)-1;
+              } else if (p.out_fp32) {
+                float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + cc;
+#pragma unroll
+                for (int jj = 0; jj < 16; jj += 4)
+                  *reinterpret_cast<float4*>(dst + jj) = make_float4(f[jj], f[jj + 1], f[jj + 2], f[jj + 3]);
+              } else {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + cc;
+                uint4 o0, o1;
+                __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+                __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  h0[jj] = __floats2bfloat162_rn(f[2 * jj], f[2 * jj + 1]);
+                  h1[jj] = __floats2bfloat162_rn(f[8 + 2 * jj], f[8 + 2 * jj + 1]);
+                }
+                *reinterpret_cast<uint4*>(dst) = o0;
+                *reinterpret_cast<uint4*>(dst + 8) = o1;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // this warp has finished reading the accumulators of the tile: hand them back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&accum_empty[as]);
+    }
+    if (reg_stats) {
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const float a1 = warp_sum32(ra1[jj]), a2 = warp_sum32(ra2[jj]);
+        const float b1 = warp_sum32(rb1[jj]), b2 = warp_sum32(rb2[jj]);
+        if (lane == 0) {
+          atomicAdd(&s_stats[0][jj], a1); atomicAdd(&s_stats[1][jj], a2);
+          if (p.BN > 16) { atomicAdd(&s_stats[0][16 + jj], b1); atomicAdd(&s_stats[1][16 + jj], b2); }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // epilogue warps only
+      const int e = threadIdx.x - 64;                        // 0..127
+      if (e < p.Co) {
+        atomicAdd(p.stats + e, s_stats[0][e]);
+        atomicAdd(p.stats + p.Co + e, s_stats[1][e]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+bool try_launch_conv_halo(const ConvLaunch& L, cudaStream_t stream, const char** err) {
+  *err = nullptr;
+  static const bool enabled = !(getenv("MINE_B200_HALO") && getenv("MINE_B200_HALO")[0] == '0');
+  if (!enabled) return false;
+  ConvParams p = L.p;
+  if (p.CB < 1) p.CB = 1;
+  if (p.in_stride != 1 || p.CB != 1 || p.accumulate) return false;
+  if (p.es != 2 && p.es != 4) return false;
+  if (p.BN % 16 || p.BN < 16 || p.BN > 64) return false;
+  if (p.stats && p.BN > 32) return false;                              // BatchNorm sums live in registers: <= 32 channels
+  if (p.KB * p.es != 32 && p.KB * p.es != 64 && p.KB * p.es != 128) return false;
+  if (p.Ci % p.KB) return false;
+  p.kblocks = p.Ci / p.KB;
+  if (p.kblocks > 4) return false;
+  if (2 * p.G * p.BN > 512) return false;                              // double-buffered accumulators of all groups
+  // all tap offsets inside one 3x3 window
+  int y0 = 1 << 20, x0 = 1 << 20, y1 = -(1 << 20), x1 = -(1 << 20);
+  for (int g = 0; g < p.G; ++g)
+    for (int t = 0; t < p.T; ++t) {
+      y0 = min(y0, (int)p.tap_y[g][t]); y1 = max(y1, (int)p.tap_y[g][t]);
+      x0 = min(x0, (int)p.tap_x[g][t]); x1 = max(x1, (int)p.tap_x[g][t]);
+    }
+  if (y1 - y0 > 2 || x1 - x0 > 2) return false;
+  p.halo_y0 = y0; p.halo_x0 = x0;
+  for (int g = 0; g < p.G; ++g)
+    for (int t = 0; t < p.T; ++t) { p.rel_y[g][t] = (int8_t)(p.tap_y[g][t] - y0); p.rel_x[g][t] = (int8_t)(p.tap_x[g][t] - x0); }
+  // tile: TW a multiple of 8 so that a vertical tap shift is a whole number of swizzle atoms
+  const int row_bytes = p.KB * p.es;
+  const double u8 = (double)p.Hg * p.Wg / ((double)((p.Hg + 15) / 16 * 16) * ((p.Wg + 7) / 8 * 8));
+  const double u16 = (double)p.Hg * p.Wg / ((double)((p.Hg + 7) / 8 * 8) * ((p.Wg + 15) / 16 * 16));
+  if (u8 >= u16) { p.TW = 8; p.TH = 16; } else { p.TW = 16; p.TH = 8; }
+  p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
+  p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
+  const uint32_t box_bytes = (uint32_t)(p.TH + 2) * p.TW * row_bytes;
+  p.box_stride = (int)((box_bytes + 1023u) / 1024u * 1024u);
+  p.w_tile_bytes = (int)(((uint32_t)p.BN * row_bytes + 1023u) / 1024u * 1024u);
+  p.w_bytes = p.G * p.T * p.kblocks * p.w_tile_bytes;
+  if (p.w_bytes > 112 * 1024) return false;
+  const uint32_t set_bytes = 3u * p.box_stride;
+  p.tmem_cols = next_pow2_cols(2 * p.G * p.BN);
+  // prefer two resident CTAs per SM (the epilogue of one overlaps the loads / MMAs of the other) when >= 2 ring stages
+  // still fit in half of the shared memory; otherwise one CTA with a deeper ring
+  int ctas_per_sm = 1;
+  int stages = (int)((107u * 1024u - 1024u - (uint32_t)p.w_bytes) / set_bytes);
+  if ((uint32_t)p.w_bytes + 3u * 1024u < 107u * 1024u && stages >= 2 && 2 * p.tmem_cols <= 512) {
+    ctas_per_sm = 2;
+  } else {
+    stages = (int)((200u * 1024u - 2048u - (uint32_t)p.w_bytes) / set_bytes);
+  }
+  if (stages > 4) stages = 4;
+  if (stages < 2) return false;
+  p.stages = stages;
+  size_t smem = (size_t)p.w_bytes + (size_t)stages * set_bytes + 1024;
+  const size_t smem_floor = (220u * 1024u) / (ctas_per_sm + 1) + 1024;   // one more CTA must NOT fit
+  if (smem < smem_floor) smem = smem_floor;
+  if (smem > 200u * 1024u) smem = 200u * 1024u;
+  CUtensorMap mx, mw;
+  const char* e = nhwc_map(&mx, L.x, p.Ci, L.Wi, L.Hi, p.N, p.KB, p.TW, p.TH + 2, 1, 1, p.es);
+  if (e) { *err = e; return true; }
+  e = weight_map(&mw, L.w, p.Ci, L.w_rows, p.G * p.T, p.KB, p.BN, p.es);
+  if (e) { *err = e; return true; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const int total_work = p.tiles_x * p.tiles_y * p.N;
+  int grid_x = sm_count() * ctas_per_sm;
+  if (grid_x > total_work) grid_x = total_work;
+  conv_halo_kernel<<<grid_x, kConvThreads, smem, stream>>>(mx, mw, p);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) *err = cudaGetErrorString(ce);
+  return true;
+}
+
+}  // namespace mine

@@ -35,139 +35,58 @@
 #include <mutex>
 #include <tuple>
 
+#include "conv_common.cuh"
 #include "conv_engine.h"
 
 namespace mine {
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
-          "r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-          "r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// one K step = 32 bytes of the reduction dimension: 16 bf16 (kind::f16) or 8 fp32 containers read as TF32 (kind::tf32)
-__device__ __forceinline__ void umma(bool tf32, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                     uint32_t accumulate) {
-  if (tf32) umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
-  else umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell).
-//   K-major  : rows (M/N index) are `row_bytes` (=swizzle span) apart, 8-row groups SBO apart.
-//   MN-major : K rows are `row_bytes` apart, 8-K-row groups SBO apart, 64/32/16-element MN blocks LBO apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-  d |= (uint64_t)(layout_type & 7) << 61;
-  return d;
-}
-__device__ __forceinline__ uint32_t layout_type_for(int swizzle_bytes) {
-  return swizzle_bytes == 128 ? 2u : (swizzle_bytes == 64 ? 4u : 6u);     // SWIZZLE_128B / 64B / 32B
-}
-// Instruction descriptor: fp32 accumulation (c_format 1), operand format 1 = bf16 (kind::f16) or 2 = tf32 (kind::tf32).
-__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, bool tf32 = false) {
-  const uint32_t fmt = tf32 ? 2u : 1u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ float warp_sum32(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-constexpr int kConvThreads = 192;     // warp0: TMA producer, warp1: TMEM alloc + MMA issue, warps 2..5: epilogue
-constexpr int kMaxStages = 8;
 
 // ------------------------------------------------------------------------------------------------
 // conv_taps: fprop / phase-upsample fprop / dgrad
 // ------------------------------------------------------------------------------------------------
+// MMA-issue loop (one thread per CTA).  The issuing thread is a latency-bound scalar instruction stream: for narrow
+// layers (N = 16..64) its per-instruction bookkeeping - not the tensor pipe - paces the kernel (ncu source view of round
+// 2: ~80 SASS instructions per tap), so the loop is specialised on the operand kind and the K steps per row and works
+// on the low descriptor words only.
+template <bool TF32, int KS>
+__device__ __forceinline__ void taps_issue_loop(const ConvParams& p, uint8_t* smem_aligned, uint32_t stage_bytes,
+                                                uint32_t sub_bytes, uint32_t a_bytes, uint32_t tmem_base,
+                                                uint64_t* full_bar, uint64_t* empty_bar, uint64_t* accum_full,
+                                                uint64_t* accum_empty, int total_work, int iters) {
+  const int row_bytes = p.KB * p.es;
+  const uint32_t idesc = make_idesc(128, p.BN, 0, 0, TF32);
+  const uint64_t desc0 = make_smem_desc(0, 16, 8u * row_bytes, layout_type_for(row_bytes));
+  const uint32_t lo0 = (uint32_t)desc0, hi = (uint32_t)(desc0 >> 32);
+  const uint32_t sub16 = sub_bytes >> 4, ab16 = a_bytes >> 4;
+  const int ipb = p.ipb, stages = p.stages;
+  int s = 0, j = 0;
+  uint32_t par = 0;
+  for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
+    const int as = j & 1;
+    if (j >= 2) mbar_wait(&accum_empty[as], ((j >> 1) - 1) & 1);     // epilogue drained this accumulator
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+    uint32_t first = 0;                              // 0 for the very first MMA of the tile (overwrite)
+    for (int remaining = iters; remaining > 0;) {
+      const int n_in = remaining < ipb ? remaining : ipb;
+      mbar_wait(&full_bar[s], par);
+      tc_fence_after();
+      uint32_t a_lo = lo0 + (smem_u32(smem_aligned + (size_t)s * stage_bytes) >> 4);
+      for (int u = 0; u < n_in; ++u, a_lo += sub16) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          umma_lohi<TF32>(d_tmem, a_lo + 2u * k, a_lo + ab16 + 2u * k, hi, idesc, first);
+          first = 1u;
+        }
+      }
+      umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
+      remaining -= n_in;
+      if (++s == stages) { s = 0; par ^= 1u; }
+    }
+    umma_commit(&accum_full[as]);           // accumulator of this tile complete
+  }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const ConvParams p) {
@@ -250,38 +169,11 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const bool tf32 = p.es == 4;
-      const uint32_t idesc = make_idesc(128, p.BN, 0, 0, tf32);
-      const uint32_t lt = layout_type_for(row_bytes);
-      const uint32_t sbo = 8u * row_bytes;
-      const uint64_t desc0 = make_smem_desc(0, 16, sbo, lt);
-      const int ksteps = row_bytes / 32;
-      int s = 0, j = 0;
-      uint32_t par = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
-        const int as = j & 1;
-        if (j >= 2) mbar_wait(&accum_empty[as], ((j >> 1) - 1) & 1);     // epilogue drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
-        uint32_t first = 0;                              // 0 for the very first MMA of the tile (overwrite)
-        for (int remaining = iters; remaining > 0;) {
-          const int n_in = remaining < p.ipb ? remaining : p.ipb;
-          mbar_wait(&full_bar[s], par);
-          tc_fence_after();
-          uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
-          for (int u = 0; u < n_in; ++u, a_addr += sub_bytes) {
-            const uint64_t da = desc0 + (uint64_t)(a_addr >> 4), db = desc0 + (uint64_t)((a_addr + a_bytes) >> 4);
-            for (int k = 0; k < ksteps; ++k) {
-              umma(tf32, d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
-              first = 1u;
-            }
-          }
-          umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
-          remaining -= n_in;
-          if (++s == p.stages) { s = 0; par ^= 1u; }
-        }
-        umma_commit(&accum_full[as]);           // accumulator of this tile complete
-      }
+      const int ks = row_bytes / 32;
+#define TAPS_ISSUE(TF, KS_) taps_issue_loop<TF, KS_>(p, smem_aligned, stage_bytes, sub_bytes, a_bytes, tmem_base, full_bar, empty_bar, accum_full, accum_empty, total_work, iters)
+      if (p.es == 4) { if (ks == 4) TAPS_ISSUE(true, 4); else if (ks == 2) TAPS_ISSUE(true, 2); else TAPS_ISSUE(true, 1); }
+      else { if (ks == 4) TAPS_ISSUE(false, 4); else if (ks == 2) TAPS_ISSUE(false, 2); else TAPS_ISSUE(false, 1); }
+#undef TAPS_ISSUE
     }
   } else {
     // ---------------- epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) ----------------
@@ -551,19 +443,29 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       const int blk_per_mma = 256 / bw;
       const uint64_t da0 = make_smem_desc(0, a_lbo, sbo_a, lta);
       const uint64_t db0 = make_smem_desc(0, b_slab, sbo_b, ltb);
+      // descriptors as (low word, high word): per MMA the issuing thread does two 32-bit adds (see taps_issue_loop)
+      const uint32_t a_lo0 = (uint32_t)da0, a_hi = (uint32_t)(da0 >> 32), b_lo0 = (uint32_t)db0, b_hi = (uint32_t)(db0 >> 32);
+      const uint32_t a_step = (uint32_t)(kpi * a_row) >> 4, b_step = (uint32_t)(kpi * b_row) >> 4, slab16 = b_slab >> 4;
+      const int ksteps = p.rows / kpi;
+      const uint32_t idesc_full = make_idesc(128, min(blk_per_mma, total_blocks) * bw, 1, 1, tf32);
+      const int tail_blocks = total_blocks % blk_per_mma;
+      const uint32_t idesc_tail = make_idesc(128, (tail_blocks ? tail_blocks : 1) * bw, 1, 1, tf32);
       for (int i = 0; i < my_tiles; ++i) {
         const int s = i % p.stages, round = i / p.stages;
         mbar_wait(&full_bar[s], round & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem_aligned + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        for (int k = 0; k < p.rows / kpi; ++k) {
-          const uint64_t da = da0 + (uint64_t)((a_addr + k * kpi * a_row) >> 4);
-          for (int b0 = 0; b0 < total_blocks; b0 += blk_per_mma) {
-            const int nblk = min(blk_per_mma, total_blocks - b0);
-            const uint64_t db = db0 + (uint64_t)((b_addr + b0 * b_slab + k * kpi * b_row) >> 4);
-            umma(tf32, tmem_base + b0 * bw, da, db, make_idesc(128, nblk * bw, 1, 1, tf32), (i > 0 || k > 0) ? 1u : 0u);
+        uint32_t a_lo = a_lo0 + (a_addr >> 4);
+        uint32_t b_lo_k = b_lo0 + ((a_addr + a_bytes) >> 4);
+        uint32_t acc = i > 0 ? 1u : 0u;
+        for (int k = 0; k < ksteps; ++k, a_lo += a_step, b_lo_k += b_step) {
+          uint32_t b_lo = b_lo_k, d = tmem_base;
+          for (int b0 = 0; b0 < total_blocks; b0 += blk_per_mma, b_lo += blk_per_mma * slab16, d += blk_per_mma * bw) {
+            const uint32_t idesc = (total_blocks - b0 >= blk_per_mma) ? idesc_full : idesc_tail;
+            if (tf32) umma_lohi2<true>(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+            else umma_lohi2<false>(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
           }
+          acc = 1u;
         }
         umma_commit(&empty_bar[s]);
       }
@@ -663,8 +565,8 @@ static std::mutex g_maps_mu;
 
 // NHWC activation: dims {C, W, H, N}; box {cb, bw * esx, bh * esy, 1}; element strides esx / esy on W / H (the box then
 // holds bw x bh pixels).  mn32: SWIZZLE_128B with 32-byte atoms (MN-major kind::tf32 operands), else by row bytes.
-static const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int cb, int bw, int bh, int esx,
-                            int esy, int esz, bool mn32 = false) {
+const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int cb, int bw, int bh, int esx,
+                     int esy, int esz, bool mn32) {
   MapKey key{ptr, C, W, H, N, cb, bw * esx, bh * esy, mn32 ? 2 : 1, esx, esy, 4, esz};
   std::lock_guard<std::mutex> lock(g_maps_mu);
   auto it = g_maps.find(key);
@@ -711,7 +613,7 @@ static const char* overlap32_map(CUtensorMap* out, const void* ptr, int W, int H
 }
 
 // packed weights: dims {Ci, Co_pad, GT}; box {kb, bn, 1}
-static const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop, int GT, int kb, int bn, int esz) {
+const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop, int GT, int kb, int bn, int esz) {
   MapKey key{ptr, Ci, Cop, GT, 0, kb, bn, 1, 0, 1, 1, 3, esz};
   std::lock_guard<std::mutex> lock(g_maps_mu);
   auto it = g_maps.find(key);
@@ -730,7 +632,12 @@ static const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop
   return nullptr;
 }
 
-static int next_pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+int next_pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+  return n;
+}
 
 // ---- weight packing: fp32 [Co,Ci,3,3] (any strides) -> bf16 GEMM operand packs, one launch --------------
 // mode 0: fprop 3x3        out[ky*3+kx][co][ci]
@@ -787,6 +694,10 @@ void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int
 }
 
 const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
+  {   // narrow high-resolution layers: halo kernel (three activation boxes per tile, resident weights)
+    const char* herr = nullptr;
+    if (try_launch_conv_halo(L, stream, &herr)) return herr;
+  }
   ConvParams p = L.p;
   if (p.TH * p.TW != 128) return "tile must cover 128 pixels";
   if (p.es != 2 && p.es != 4) return "operand element size must be 2 (bf16) or 4 (fp32/tf32)";

@@ -21,6 +21,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 QUICK = os.environ.get("MINE_B200_MG_QUICK", "0") == "1"          # skip timings (sanitizer runs)
+DAMP = float(os.environ.get("MINE_B200_MG_DAMP", "0.1"))          # residual-branch BN gain of the test network (0: off)
 
 
 def main():
@@ -112,7 +113,8 @@ def main():
     base = {"data.img_w": W, "data.img_h": H, "mpi.num_bins_coarse": S, "data.visible_point_count": 256,
             "model.imagenet_pretrained": False, "mpi.fix_disparity": True, "data.per_gpu_batch_size": B,
             "lr.backbone_lr": 0.0, "lr.decoder_lr": 0.0, "engine.precision": os.environ.get("MINE_B200_MG_PRECISION", "tf32")}
-    res["step_shape"] = {"H": H, "W": W, "planes": S, "per_gpu_batch": B, "precision": base["engine.precision"]}
+    res["step_shape"] = {"H": H, "W": W, "planes": S, "per_gpu_batch": B, "precision": base["engine.precision"],
+                         "residual_bn_gain": DAMP}
     items_all = synthetic_batch(world * B, H, W, 256, seed=0)
     mine = tuple({k: v[rank * B:(rank + 1) * B] for k, v in d.items()} for d in items_all)
 
@@ -152,11 +154,22 @@ def main():
         def barrier(self):
             self.inner.barrier()
 
-    def build(kind, comm_obj=None):
-        cfg = C.config_for_dataset("llff", dict(base, **{"engine.comm": kind}))
+    def build(kind, comm_obj=None, **over):
+        cfg = C.config_for_dataset("llff", dict(base, **{"engine.comm": kind}, **over))
         cfg.update({"device": dev, "global_rank": rank})
         torch.manual_seed(0)
-        return SynthesisTask(cfg, None, comm=comm_obj)
+        task = SynthesisTask(cfg, None, comm=comm_obj)
+        # Conditioning of the TEST network: at plain random init the gradient of this 60-layer BatchNorm network is
+        # chaotic - a 1e-7 relative perturbation of the input image moves it by 3 %, 1e-6 by 84 % (fp32, CPU,
+        # scripts/conditioning_probe.py) - so no two valid executions agree to 1e-3.  Damping the residual branches
+        # (gain of the last BatchNorm of every ResNet block, "zero-init residual" style) makes the comparison
+        # meaningful; every arm gets the same weights.
+        if DAMP > 0:
+            with torch.no_grad():
+                for li in range(1, 5):
+                    for blk in getattr(task.backbone.encoder, "layer%d" % li):
+                        (blk.bn3 if hasattr(blk, "bn3") else blk.bn2).weight.fill_(DAMP)
+        return task
 
     grads = {}
     for tag, use_mm in (("p2p", False), ("multimem", True)):
@@ -197,18 +210,59 @@ def main():
     res["cos_nccl_vs_nccl_repeat"] = cos("nccl", "nccl_repeat")
     if "multimem" in grads:
         res["cos_multimem_vs_nccl"] = cos("multimem", "nccl")
-    # one process, N x batch (rank 0 computes; every rank builds the task because construction broadcasts)
-    single = build("p2p", Communicator())
+    # one process, N x batch (rank 0 computes; every rank builds the task because construction broadcasts).
+    # (a) with the kernels: TF32 rounding makes a random-init network's gradient a noisy quantity (two identical NCCL
+    #     runs already differ, see the control above), so this number is reported, not asserted;
+    # (b) EXACT arithmetic: the same orchestration through the fp32 kernel specification (ops/emu.py) with true-fp32
+    #     library convolutions - what is left is summation order at fp32 epsilon, so data-parallel semantics
+    #     (cross-replica BatchNorm counts, loss / gradient scaling, bucket reduction) must reproduce the
+    #     single-process gradient of the N x batch almost exactly.
+    def single_process_grad(**over):
+        single = build("p2p", Communicator(), **over)
+        out = None
+        if rank == 0:
+            o = single.train_step(tuple({k: v for k, v in d.items()} for d in items_all))
+            torch.cuda.synchronize()
+            out = (single.arena.grad.double().clone(), float(o["loss"]))
+        del single
+        torch.cuda.empty_cache()
+        dist.barrier()
+        return out
+    ref1 = single_process_grad()
     if rank == 0:
-        out1 = single.train_step(tuple({k: v for k, v in d.items()} for d in items_all))
-        torch.cuda.synchronize()
-        g1 = single.arena.grad.double()
-        res["loss_single_process"] = float(out1["loss"])
-        res["cos_p2p_vs_single_process"] = torch.nn.functional.cosine_similarity(grads["p2p"].double(), g1, dim=0).item()
-        res["cos_nccl_vs_single_process"] = torch.nn.functional.cosine_similarity(grads["nccl"].double(), g1, dim=0).item()
-        res["relerr_p2p_vs_single_process"] = float((grads["p2p"].double() - g1).norm() / g1.norm())
-    del single
-    torch.cuda.empty_cache()
+        g1, res["loss_single_process"] = ref1
+        cosd = lambda a, b: torch.nn.functional.cosine_similarity(a.double(), b.double(), dim=0).item()
+        res["kernels_cos_p2p_vs_single_process"] = cosd(grads["p2p"], g1)
+        res["kernels_cos_nccl_vs_single_process"] = cosd(grads["nccl"], g1)
+    from mine_b200.ops import conv_engine as E
+    prev_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    E.use_emulator(True, torch.float32)
+    exact_over = {"mpi.num_bins_coarse": 8}          # the semantics under test do not depend on the plane count
+    res["exact_shape"] = {"H": H, "W": W, "planes": 8, "per_gpu_batch": B}
+    try:
+        exact = {}
+        for tag, use_mm in (("p2p", False), ("multimem", True)):
+            if use_mm and not res["multicast"]:
+                continue
+            task = build("p2p", **exact_over)
+            task.comm.use_multimem = use_mm
+            task.train_step(mine)
+            torch.cuda.synchronize()
+            exact[tag] = task.arena.grad.clone()
+            task.grad_sync.close()
+            del task
+            torch.cuda.empty_cache()
+        ref2 = single_process_grad(**exact_over)
+        if rank == 0:
+            g2, _ = ref2
+            for tag, g_ in exact.items():
+                res["exact_cos_%s_vs_single_process" % tag] = cosd(g_, g2)
+                res["exact_relerr_%s_vs_single_process" % tag] = float((g_.double() - g2).norm() / g2.norm())
+    finally:
+        E.use_emulator(False)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
     dist.barrier()
 
     # 6. soak: graph replays with the own communicator (default path for this world size)

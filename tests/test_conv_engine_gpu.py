@@ -153,7 +153,7 @@ def test_bn_act_pad_fwd_bwd(pad_mode, n, h, w, c):
     bn = F.batch_norm(yr, None, None, g_r, b_r, training=True, eps=1e-5)
     ref = F.pad(F.elu(bn), (1, 1, 1, 1), mode="reflect" if pad_mode == 0 else "replicate")
     apad = ext.bn_act_pad_fwd(_act(y), stats, gamma, beta, pad_mode, count, 1e-5)
-    assert _rel(_nchw(apad), ref) < _tol(1e-2, 1e-4)
+    assert _rel(_nchw(apad), ref) < _tol(1e-2, 6e-4)        # the stored activation is rounded to TF32 (2^-11)
     dap = _bf(_rand(ref.shape, 3))
     ref.backward(dap)
     g, sums = ext.bn_act_bwd_reduce(_act(dap), _act(y), stats, gamma, beta,
