@@ -31,6 +31,27 @@ inline const float* opt_f32(const c10::optional<at::Tensor>& t, const char* name
   return t->data_ptr<float>();
 }
 
+// Fused statistic exchange (ll_exchange.cuh): peer receive buffers of the P2P communicator + its device counters.
+struct FusedX {
+  mine::LLExchange x{};
+  bool on = false;
+};
+FusedX make_fused(const std::vector<int64_t>& ll_ptrs, int64_t rank, int64_t cap, const c10::optional<at::Tensor>& epoch,
+                  const c10::optional<at::Tensor>& ticket, int64_t n) {
+  FusedX f;
+  if (ll_ptrs.size() < 2) return f;
+  TORCH_CHECK(ll_ptrs.size() <= 16, "at most 16 peers");
+  TORCH_CHECK(epoch.has_value() && ticket.has_value() && epoch->is_cuda() && ticket->is_cuda() &&
+                  epoch->scalar_type() == at::kInt && ticket->scalar_type() == at::kInt, "epoch / ticket: CUDA int32 tensors");
+  TORCH_CHECK(n <= cap, "statistic vector larger than the exchange slot");
+  for (size_t i = 0; i < ll_ptrs.size(); ++i) f.x.ptr[i] = reinterpret_cast<void*>(ll_ptrs[i]);
+  f.x.rank = (int)rank; f.x.world = (int)ll_ptrs.size(); f.x.cap = (int)cap;
+  f.x.epoch = reinterpret_cast<uint32_t*>(epoch->data_ptr<int>());
+  f.x.ticket = reinterpret_cast<uint32_t*>(ticket->data_ptr<int>());
+  f.on = true;
+  return f;
+}
+
 void conv_taps(const at::Tensor& x, const at::Tensor& wpack, at::Tensor out, int64_t Hg, int64_t Wg, int64_t G, int64_t T,
                std::vector<int64_t> tap_y, std::vector<int64_t> tap_x, int64_t in_stride, int64_t Co, int64_t out_sy,
                int64_t out_sx, std::vector<int64_t> out_oy, std::vector<int64_t> out_ox, bool accumulate,
@@ -141,18 +162,30 @@ void wgrad_taps(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_
   TORCH_CHECK(err == nullptr, "wgrad_taps: ", err ? err : "");
 }
 
-at::Tensor bn_act_pad_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
-                          int64_t pad_mode, double count, double eps) {
+// `stats` are this rank's sums; with a fused exchange (ll_ptrs of >= 2 ranks) the kernel reduces them across GPUs in its
+// prologue and the reduced vector comes back as the second result (`count` is then the GLOBAL element count).
+std::vector<at::Tensor> bn_act_pad_fwd_x(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma,
+                                         const at::Tensor& beta, int64_t pad_mode, double count, double eps,
+                                         std::vector<int64_t> ll_ptrs, int64_t rank, int64_t cap,
+                                         const c10::optional<at::Tensor>& epoch, const c10::optional<at::Tensor>& ticket) {
   check_act_nhwc(y, "y");
   c10::cuda::CUDAGuard guard(y.device());
   const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
   TORCH_CHECK((C & (C - 1)) == 0 && C >= 16, "channels must be a power of two >= 16");
   TORCH_CHECK((int64_t)N * (H + 2) * (W + 2) * (C / 8) < (1ll << 31), "tensor too large for 32-bit indexing");
+  TORCH_CHECK(opt_f32(stats, "stats") && stats.numel() == 2 * C, "stats must be fp32 [2, C]");
   at::Tensor out = at::empty({N, H + 2, W + 2, C}, y.options());
+  FusedX f = make_fused(ll_ptrs, rank, cap, epoch, ticket, 2 * C);
+  at::Tensor red = f.on ? at::empty_like(stats) : stats;
   mine::launch_bn_act_pad_fwd(y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(),
                               out.data_ptr(), N, H, W, C, (int)pad_mode, (float)(1.0 / count), (float)eps, esize(y),
-                              cur_stream());
-  return out;
+                              f.on ? &f.x : nullptr, f.on ? red.data_ptr<float>() : nullptr, cur_stream());
+  return {out, red};
+}
+
+at::Tensor bn_act_pad_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
+                          int64_t pad_mode, double count, double eps) {
+  return bn_act_pad_fwd_x(y, stats, gamma, beta, pad_mode, count, eps, {}, 0, 0, c10::nullopt, c10::nullopt)[0];
 }
 
 std::vector<at::Tensor> bn_act_bwd_reduce(const at::Tensor& dapad, const at::Tensor& y, const at::Tensor& stats,
@@ -172,21 +205,31 @@ std::vector<at::Tensor> bn_act_bwd_reduce(const at::Tensor& dapad, const at::Ten
   return {g, sums};
 }
 
-std::vector<at::Tensor> bn_bwd_apply(const at::Tensor& g, const at::Tensor& y, const at::Tensor& stats,
-                                     const at::Tensor& gamma, const at::Tensor& sums, int64_t planes_per_image,
-                                     bool want_shared, bool want_plane_bias, double count, double eps) {
+std::vector<at::Tensor> bn_bwd_apply_x(const at::Tensor& g, const at::Tensor& y, const at::Tensor& stats,
+                                       const at::Tensor& gamma, const at::Tensor& sums, int64_t planes_per_image,
+                                       bool want_shared, bool want_plane_bias, double count, double eps,
+                                       std::vector<int64_t> ll_ptrs, int64_t rank, int64_t cap,
+                                       const c10::optional<at::Tensor>& epoch, const c10::optional<at::Tensor>& ticket) {
   check_act_nhwc(g, "g"); check_act_nhwc(y, "y"); check_same_type(g, y, "bn_bwd_apply");
   c10::cuda::CUDAGuard guard(y.device());
   const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
   const int S = planes_per_image, B = N / S;
+  FusedX f = make_fused(ll_ptrs, rank, cap, epoch, ticket, 2 * C);
   at::Tensor dy = at::empty_like(y);
   at::Tensor dshared = want_shared ? at::empty({B, H, W, C}, stats.options()) : at::Tensor();
   at::Tensor dpb = want_plane_bias ? at::zeros({N, C}, stats.options()) : at::Tensor();
   mine::launch_bn_bwd_apply(g.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(),
                             sums.data_ptr<float>(), dy.data_ptr(), want_shared ? dshared.data_ptr<float>() : nullptr,
                             want_plane_bias ? dpb.data_ptr<float>() : nullptr, B, S, H, W, C, (float)(1.0 / count),
-                            (float)eps, esize(y), cur_stream());
+                            (float)eps, esize(y), f.on ? &f.x : nullptr, cur_stream());
   return {dy, dshared, dpb};
+}
+
+std::vector<at::Tensor> bn_bwd_apply(const at::Tensor& g, const at::Tensor& y, const at::Tensor& stats,
+                                     const at::Tensor& gamma, const at::Tensor& sums, int64_t planes_per_image,
+                                     bool want_shared, bool want_plane_bias, double count, double eps) {
+  return bn_bwd_apply_x(g, y, stats, gamma, sums, planes_per_image, want_shared, want_plane_bias, count, eps, {}, 0, 0,
+                        c10::nullopt, c10::nullopt);
 }
 
 std::vector<at::Tensor> head_bwd(const at::Tensor& g_mpi, const at::Tensor& mpi, const at::Tensor& sign, bool use_alpha) {
@@ -227,8 +270,10 @@ inline void check_channels(const at::Tensor& y) {
   TORCH_CHECK(y.numel() / 8 < (1ll << 31), "tensor too large for 32-bit indexing");
 }
 
-at::Tensor bn_res_act_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
-                          const c10::optional<at::Tensor>& residual, double slope, double count, double eps) {
+std::vector<at::Tensor> bn_res_act_fwd_x(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma,
+                                         const at::Tensor& beta, const c10::optional<at::Tensor>& residual, double slope,
+                                         double count, double eps, std::vector<int64_t> ll_ptrs, int64_t rank, int64_t cap,
+                                         const c10::optional<at::Tensor>& epoch, const c10::optional<at::Tensor>& ticket) {
   check_act_nhwc(y, "y"); check_channels(y);
   TORCH_CHECK(stats.numel() == 2 * y.size(3) && opt_f32(stats, "stats") && opt_f32(gamma, "gamma") && opt_f32(beta, "beta"),
               "stats/gamma/beta");
@@ -240,10 +285,18 @@ at::Tensor bn_res_act_fwd(const at::Tensor& y, const at::Tensor& stats, const at
   }
   c10::cuda::CUDAGuard guard(y.device());
   at::Tensor out = at::empty_like(y);
+  FusedX f = make_fused(ll_ptrs, rank, cap, epoch, ticket, 2 * y.size(3));
+  at::Tensor red = f.on ? at::empty_like(stats) : stats;
   mine::launch_bn_res_act_fwd(y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(), res,
                               out.data_ptr(), (size_t)(y.numel() / y.size(3)), (int)y.size(3), (float)slope,
-                              (float)(1.0 / count), (float)eps, esize(y), cur_stream());
-  return out;
+                              (float)(1.0 / count), (float)eps, esize(y), f.on ? &f.x : nullptr,
+                              f.on ? red.data_ptr<float>() : nullptr, cur_stream());
+  return {out, red};
+}
+
+at::Tensor bn_res_act_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
+                          const c10::optional<at::Tensor>& residual, double slope, double count, double eps) {
+  return bn_res_act_fwd_x(y, stats, gamma, beta, residual, slope, count, eps, {}, 0, 0, c10::nullopt, c10::nullopt)[0];
 }
 
 std::vector<at::Tensor> bn_res_act_bwd_reduce(const at::Tensor& dout, const at::Tensor& out, const at::Tensor& y,
@@ -332,6 +385,9 @@ void register_conv(pybind11::module_& m) {
   m.def("wgrad_taps", &wgrad_taps);
   m.def("pack_weights", &pack_weights);
   m.def("bn_act_pad_fwd", &bn_act_pad_fwd);
+  m.def("bn_act_pad_fwd_x", &bn_act_pad_fwd_x);
+  m.def("bn_bwd_apply_x", &bn_bwd_apply_x);
+  m.def("bn_res_act_fwd_x", &bn_res_act_fwd_x);
   m.def("bn_act_bwd_reduce", &bn_act_bwd_reduce);
   m.def("bn_bwd_apply", &bn_bwd_apply);
   m.def("head_bwd", &head_bwd);

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "act_types.cuh"
+#include "ll_exchange.cuh"
 #include "kernels.h"
 
 namespace mine {
@@ -52,7 +53,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_act_pad_fwd_kernel(
     const T* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, T* __restrict__ out, int N, int H, int W, int C, int pad_mode,
-    float inv_count, float eps) {
+    float inv_count, float eps, const LLExchange x, float* __restrict__ red_out) {
+  extern __shared__ float s_red[];               // [2C] cross-GPU reduced statistics (only when x.world > 1)
+  if (x.world > 1) { ll_exchange_sum(stats, s_red, 2 * C, x, red_out); stats = s_red; }
   const int cg = C >> 3;                         // power of two (C in {16,...,256})
   const int cg_shift = 31 - __clz(cg);
   const int Hp = H + 2, Wp = W + 2;
@@ -243,9 +246,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ sums, T* __restrict__ dy,
     float* __restrict__ dshared, float* __restrict__ dplane_bias, int B, int S, int H, int W, int C, float inv_count,
-    float eps) {
-  extern __shared__ float s_pb[];      // [S][C] per-plane bias gradient partials
+    float eps, const LLExchange x) {
+  extern __shared__ float s_pb[];      // [S][C] per-plane bias gradient partials (if wanted), then [2C] reduced sums
   const bool want_pb = dplane_bias != nullptr;
+  if (x.world > 1) {                   // cross-GPU SUM of the two BatchNorm backward reductions, fused into this kernel
+    float* s_red = s_pb + (want_pb ? S * C : 0);
+    ll_exchange_sum(sums, s_red, 2 * C, x, nullptr);
+    sums = s_red;
+  }
   if (want_pb) {
     for (int i = threadIdx.x; i < S * C; i += blockDim.x) s_pb[i] = 0.f;
     __syncthreads();
@@ -352,10 +360,14 @@ static int grid_for(size_t total, int cap = 148 * 16) {
 }
 
 void launch_bn_act_pad_fwd(const void* y, const float* stats, const float* gamma, const float* beta, void* out, int N,
-                           int H, int W, int C, int pad_mode, float inv_count, float eps, int es, cudaStream_t stream) {
+                           int H, int W, int C, int pad_mode, float inv_count, float eps, int es, const LLExchange* x,
+                           float* red_out, cudaStream_t stream) {
   const size_t total = (size_t)N * (H + 2) * (W + 2) * (C / 8);
-  MINE_DISPATCH_ES(es, T, (bn_act_pad_fwd_kernel<T><<<grid_for(total, 148 * 32), 256, 0, stream>>>(
-      (const T*)y, stats, gamma, beta, (T*)out, N, H, W, C, pad_mode, inv_count, eps)));
+  LLExchange xx{};
+  if (x) xx = *x;
+  const size_t smem = xx.world > 1 ? 2 * (size_t)C * sizeof(float) : 0;
+  MINE_DISPATCH_ES(es, T, (bn_act_pad_fwd_kernel<T><<<grid_for(total, 148 * 32), 256, smem, stream>>>(
+      (const T*)y, stats, gamma, beta, (T*)out, N, H, W, C, pad_mode, inv_count, eps, xx, red_out)));
 }
 
 void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* stats, const float* gamma,
@@ -376,10 +388,12 @@ void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* sta
 
 void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const float* gamma, const float* sums,
                          void* dy, float* dshared, float* dplane_bias, int B, int S, int H, int W, int C,
-                         float inv_count, float eps, int es, cudaStream_t stream) {
+                         float inv_count, float eps, int es, const LLExchange* x, cudaStream_t stream) {
   const size_t per_img = (size_t)H * W * (C / 8);
   dim3 grid((unsigned)((per_img + 255) / 256), B);
-  const size_t smem = dplane_bias ? (size_t)S * C * sizeof(float) : 0;
+  LLExchange xx{};
+  if (x) xx = *x;
+  const size_t smem = (dplane_bias ? (size_t)S * C * sizeof(float) : 0) + (xx.world > 1 ? 2 * (size_t)C * sizeof(float) : 0);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(bn_bwd_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
@@ -387,7 +401,7 @@ void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const
     attr = true;
   }
   MINE_DISPATCH_ES(es, T, (bn_bwd_apply_kernel<T><<<grid, 256, smem, stream>>>(
-      (const T*)g, (const T*)y, stats, gamma, sums, (T*)dy, dshared, dplane_bias, B, S, H, W, C, inv_count, eps)));
+      (const T*)g, (const T*)y, stats, gamma, sums, (T*)dy, dshared, dplane_bias, B, S, H, W, C, inv_count, eps, xx)));
 }
 
 void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, void* dz, float* dbias, size_t npix,

@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "act_types.cuh"
+#include "ll_exchange.cuh"
 #include "kernels.h"
 
 namespace mine {
@@ -44,7 +45,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_res_act_fwd_kernel(
     const T* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, const T* __restrict__ res, T* __restrict__ out,
-    unsigned total, int C, float slope, float inv_count, float eps) {
+    unsigned total, int C, float slope, float inv_count, float eps, const LLExchange x, float* __restrict__ red_out) {
+  extern __shared__ float s_red[];       // [2C] cross-GPU reduced statistics (only when x.world > 1)
+  if (x.world > 1) { ll_exchange_sum(stats, s_red, 2 * C, x, red_out); stats = s_red; }
   const Walk w = make_walk(total, C);
   if (!w.active) return;
   float a[8], b[8];
@@ -172,10 +175,13 @@ int blocks_for(size_t total, int C, int cap) {
 
 void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
                            void* out, size_t npix, int C, float slope, float inv_count, float eps, int es,
-                           cudaStream_t stream) {
+                           const LLExchange* x, float* red_out, cudaStream_t stream) {
   const size_t total = npix * (size_t)(C / 8);
-  MINE_DISPATCH_ES(es, T, (bn_res_act_fwd_kernel<T><<<blocks_for(total, C, 148 * 16), 256, 0, stream>>>(
-      (const T*)y, stats, gamma, beta, (const T*)res, (T*)out, (unsigned)total, C, slope, inv_count, eps)));
+  LLExchange xx{};
+  if (x) xx = *x;
+  const size_t smem = xx.world > 1 ? 2 * (size_t)C * sizeof(float) : 0;
+  MINE_DISPATCH_ES(es, T, (bn_res_act_fwd_kernel<T><<<blocks_for(total, C, 148 * 16), 256, smem, stream>>>(
+      (const T*)y, stats, gamma, beta, (const T*)res, (T*)out, (unsigned)total, C, slope, inv_count, eps, xx, red_out)));
 }
 
 void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void* y, const float* stats, void* g_out,

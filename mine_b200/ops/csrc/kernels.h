@@ -43,16 +43,24 @@ void launch_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, 
 }  // namespace mine
 
 namespace mine {
+// cross-GPU statistic exchange fused into the consuming kernel (device side: ll_exchange.cuh); null pointer: none
+struct LLExchange {
+  void* ptr[16];          // per-rank receive buffers: [2 parities][world sources][cap] uint2 (symmetric allocation)
+  int rank, world, cap;   // world <= 1: exchange disabled
+  uint32_t* epoch;        // device counter shared with allreduce_small_ll_kernel
+  uint32_t* ticket;       // device counter (zero between kernels)
+};
 // ---- decoder_elem.cu (NHWC bf16) ---------------------------------------------------------------
 // pad_mode: 0 = reflection, 1 = replication (1 pixel); stats = [2, C] global (sum, sum of squares)
 void launch_bn_act_pad_fwd(const void* y, const float* stats, const float* gamma, const float* beta, void* out, int N,
-                           int H, int W, int C, int pad_mode, float inv_count, float eps, int es, cudaStream_t stream);
+                           int H, int W, int C, int pad_mode, float inv_count, float eps, int es, const LLExchange* x,
+                           float* red_out, cudaStream_t stream);
 void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* stats, const float* gamma,
                               const float* beta, void* g_out, float* sums, int N, int H, int W, int C, int pad_mode,
                               float inv_count, float eps, int es, cudaStream_t stream);
 void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const float* gamma, const float* sums,
                          void* dy, float* dshared, float* dplane_bias, int B, int S, int H, int W, int C,
-                         float inv_count, float eps, int es, cudaStream_t stream);
+                         float inv_count, float eps, int es, const LLExchange* x, cudaStream_t stream);
 void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, void* dz, float* dbias, size_t npix,
                      int use_alpha, int es, cudaStream_t stream);
 }  // namespace mine
@@ -85,7 +93,7 @@ namespace mine {
 // ---- encoder_elem.cu (unpadded NHWC bf16, C a power of two in [16, 2048]) -------------------------------
 void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
                            void* out, size_t npix, int C, float slope, float inv_count, float eps, int es,
-                           cudaStream_t stream);
+                           const LLExchange* x, float* red_out, cudaStream_t stream);
 void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void* y, const float* stats, void* g_out,
                                   float* sums, size_t npix, int C, float slope, float inv_count, float eps, int es,
                                   cudaStream_t stream);

@@ -214,18 +214,24 @@ class BNAct(torch.autograd.Function):
         slope = (RELU if relu else IDENTITY) if isinstance(relu, bool) else float(relu)
         training = bn is None or bn.training
         count = float(y.shape[0] * y.shape[1] * y.shape[2])
+        fx = None
         if training:
             if stats.numel() == 0:
                 stats = ext().channel_stats(y)
                 _count()
             if reducer is not None:
-                stats = reducer(stats.reshape(-1)).reshape(2, -1).contiguous()
                 count *= ctx_world(reducer)
+                fx = E.fused_exchange(reducer, stats.numel())
+                if fx is None:
+                    stats = reducer(stats.reshape(-1)).reshape(2, -1).contiguous()
         else:
             rm, rv = bn.running_mean.float(), bn.running_var.float()
             stats = torch.stack([rm * count, (rv + rm * rm) * count]).contiguous()
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        a = ext().bn_res_act_fwd(y, stats, g32, b32, residual, slope, count, BN_EPS)
+        if fx is not None:                   # statistic exchange inside the normalise kernel (csrc/ll_exchange.cuh)
+            a, stats = ext().bn_res_act_fwd_x(y, stats, g32, b32, residual, slope, count, BN_EPS, *fx)
+        else:
+            a = ext().bn_res_act_fwd(y, stats, g32, b32, residual, slope, count, BN_EPS)
         _count()
         if bn is not None and training:
             E.update_running_stats(bn, stats, count)
@@ -239,12 +245,16 @@ class BNAct(torch.autograd.Function):
         slope, count, reducer, has_res, training = ctx.cfg
         g, sums = ext().bn_res_act_bwd_reduce(da.contiguous(), a, y, stats, g32, b32, slope, count, BN_EPS)
         dgamma, dbeta = sums[1], sums[0]
+        fx = E.fused_exchange(reducer, sums.numel()) if training else None
         if not training:             # frozen statistics: BN is a per-channel affine map
             sums = torch.zeros_like(sums)
-        elif reducer is not None:    # the local sums are the parameter gradients; the reduction is in place
+        elif reducer is not None and fx is None:    # separate all-reduce, in place: keep the local sums (= gradients)
             dgamma, dbeta = sums[1].clone(), sums[0].clone()
             sums = reducer(sums.reshape(-1)).reshape(2, -1).contiguous()
-        dy = ext().bn_bwd_apply(g, y, stats, g32, sums, 1, False, False, count, BN_EPS)[0]
+        if fx is not None:
+            dy = ext().bn_bwd_apply_x(g, y, stats, g32, sums, 1, False, False, count, BN_EPS, *fx)[0]
+        else:
+            dy = ext().bn_bwd_apply(g, y, stats, g32, sums, 1, False, False, count, BN_EPS)[0]
         _count(2)
         return dy, None, dgamma.to(g32.dtype), dbeta.to(b32.dtype), (g if has_res else None), None, None, None
 
@@ -366,13 +376,16 @@ def _upsample_nhwc(x: torch.Tensor, size) -> torch.Tensor:
     return F.interpolate(x.permute(0, 3, 1, 2), size=tuple(size), mode="nearest").permute(0, 2, 3, 1).contiguous()
 
 
-def receptive_field_extension(dec, top_nchw: torch.Tensor, reducer=None) -> torch.Tensor:
+def receptive_field_extension(dec, top_nchw: torch.Tensor, reducer=None, library_conv: bool = False) -> torch.Tensor:
     """``DepthDecoder.receptive_field_extension`` (reference ``depth_decoder.py:55-61,96-101``) on the engine:
     pool -> 1x1 -> pool -> 3x3 -> up -> 3x3 -> up -> 1x1, every conv followed by BN + LeakyReLU(0.1)."""
     top = E.to_operand(top_nchw.permute(0, 2, 3, 1)).contiguous()
 
     def layer(x, blk):
-        y, stats = Conv.apply(x, blk[0].weight, 1, blk[1].training)
+        if library_conv:                           # "hybrid": library convolution, fused BN / LeakyReLU kernels
+            y, stats = ConvLib.apply(x, blk[0].weight, 1), torch.empty(0, device=x.device)
+        else:
+            y, stats = Conv.apply(x, blk[0].weight, 1, blk[1].training)
         return BNAct.apply(y, stats, blk[1].weight, blk[1].bias, None, LEAKY, blk[1], reducer)
     d1 = layer(_pool_nhwc(top), dec.conv_down1)
     d2 = layer(_pool_nhwc(d1), dec.conv_down2)

@@ -41,6 +41,7 @@ class P2PComm(Communicator):
         self._ll = self._alloc(2 * self.world_size * LL_CAP * 2, torch.int32)      # uint2 words
         self._ll["tensor"].zero_()
         self._epoch_ll = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=self.device)       # fused exchanges (ll_exchange.cuh)
         self._flags = self._alloc(FLAG_CHANNELS * 16, torch.int32)
         self._flags["tensor"].zero_()
         self._small["tensor"].zero_()
@@ -79,6 +80,14 @@ class P2PComm(Communicator):
         from ..ops import cuda as C
         C.LAUNCHES["count"] += 1
         return t
+
+    def fused_handle(self):
+        """Arguments of the ``*_x`` kernels that run the low-latency statistic exchange in their own prologue instead of a
+        separate all-reduce launch (``csrc/ll_exchange.cuh``): peer receive buffers, rank, slot capacity, the epoch
+        counter shared with :meth:`allreduce_sum_`, and the CTA ticket counter.  ``None``: not available."""
+        if not self.use_ll or os.environ.get("MINE_B200_FUSED_BN", "1") != "1":
+            return None
+        return (self._ll["ptrs"], self.rank, LL_CAP, self._epoch_ll, self._ticket)
 
     def allreduce_mean_(self, t: torch.Tensor, stream=None) -> torch.Tensor:
         a = self._arena

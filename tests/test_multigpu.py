@@ -25,6 +25,7 @@ def run_worker(n, env=None, timeout=1500):
 def check(res):
     n = res["world"]
     assert res["small_ok"] and res["mean_ok_p2p"]
+    assert res["fused_exchange_bit_identical"], res
     if res.get("multicast"):
         assert res["mean_ok_multimem"]
     assert res["comm_p2p"].startswith("p2p")
@@ -37,12 +38,10 @@ def check(res):
         assert a["stat_max_rel_err"] < 1e-5, (tag, a)
         assert a["grad_max_rel_err"] < 1e-5, (tag, a)
         assert a["grads_identical_across_ranks"], (tag, a)
-    # Whole-step gradients with the kernels (own communicator vs NCCL communicator, same weights and data): the audit
-    # above already shows every collective is equal, so what differs between two runs is atomics order amplified by a
-    # random-init network at TF32 granularity - two NCCL runs are just as far apart (control, reported); sanity only.
-    assert res["cos_p2p_vs_nccl"] > 0.9 and res["cos_nccl_vs_nccl_repeat"] > 0.9, res
-    if "cos_multimem_vs_nccl" in res:
-        assert res["cos_multimem_vs_nccl"] > 0.9, res
+    # Whole-step gradient cosines WITH the kernels (own vs NCCL communicator, vs a repeated NCCL run, vs one process)
+    # are reported but not asserted: TF32 rounding noise through this random-init network is O(1) on the gradient
+    # direction (two NCCL runs are as far apart as anything else; scripts/conditioning_probe.py), while the audit above
+    # proves the collectives themselves are exact.
     # data-parallel equivalence in exact arithmetic (fp32 specification kernels): N ranks == one process on N x batch
     assert res["exact_cos_p2p_vs_single_process"] > 0.9995, res
     if "exact_cos_multimem_vs_single_process" in res:
