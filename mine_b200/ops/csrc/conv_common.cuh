@@ -191,6 +191,8 @@ const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int
                      int esy, int esz, bool mn32 = false);
 // packed weights: dims {Ci, rows, GT}; box {kb, bn, 1}
 const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop, int GT, int kb, int bn, int esz);
+// 16-channel fp32 tensor as 128-byte rows of two adjacent pixels (overlapping view, see conv_tcgen05.cu)
+const char* overlap32_map(CUtensorMap* out, const void* ptr, int W, int H, int N, int bw, int bh, int esx, int esy);
 int next_pow2_cols(int n);
 int sm_count();
 

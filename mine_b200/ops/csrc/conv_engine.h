@@ -80,5 +80,7 @@ bool try_launch_conv_halo(const ConvLaunch& L, cudaStream_t stream, const char**
 void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co, int Ci, int mode,
                          int rows_pad, void* out, int es, cudaStream_t stream);
 const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream);
+// wgrad_halo.cu: returns true when the layer was eligible and has been launched (err set on launch failure)
+bool try_launch_wgrad_halo(const WgradLaunch& L, cudaStream_t stream, const char** err);
 
 }  // namespace mine

@@ -591,7 +591,7 @@ const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int
 // gradient): dims {32 (2 pixels x 16 channels, contiguous), W - 1 (row start: any pixel, stride ONE pixel - the rows of
 // this view overlap), H, N}; box {32, bw * esx, bh * esy, 1} with element strides esx / esy -> bw x bh rows.  A start
 // at the last pixel of a line is out of bounds (zero row), so a row never straddles two image lines.
-static const char* overlap32_map(CUtensorMap* out, const void* ptr, int W, int H, int N, int bw, int bh, int esx, int esy) {
+const char* overlap32_map(CUtensorMap* out, const void* ptr, int W, int H, int N, int bw, int bh, int esx, int esy) {
   MapKey key{ptr, 32, W, H, N, 32, bw * esx, bh * esy, 3, esx, esy, 4, 4};
   std::lock_guard<std::mutex> lock(g_maps_mu);
   auto it = g_maps.find(key);
@@ -758,6 +758,10 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
 }
 
 const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream) {
+  {   // narrow / high-resolution layers: tap-sharing kernel (one activation load per horizontal offset, wgrad_halo.cu)
+    const char* herr = nullptr;
+    if (try_launch_wgrad_halo(L, stream, &herr)) return herr;
+  }
   WgradParams p = L.p;
   if (p.TH * p.TW != p.KP || p.KP % 16 || p.KP < 32 || p.KP > 256) return "wgrad pixel tile must be 32..256 pixels";
   if (p.es != 2 && p.es != 4) return "operand element size must be 2 (bf16) or 4 (fp32/tf32)";
