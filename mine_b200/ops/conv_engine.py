@@ -348,8 +348,10 @@ class PlaneConvBNAct(torch.autograd.Function):
         _count(2)
         dcb = None
         if has_cb:
-            # dy summed over everything == 0 analytically for BN inputs; keep exact semantics anyway
-            dcb = torch.sum(dy, dim=(0, 1, 2), dtype=torch.float32)
+            # a bias in front of BatchNorm has an exactly-zero gradient (dy of a BatchNorm sums to zero over the batch);
+            # autograd on the reference produces rounding noise around 0 here - return the exact value instead of
+            # reducing a multi-hundred-MB tensor to get that noise
+            dcb = torch.zeros(dy.shape[3], dtype=torch.float32, device=dy.device)
         dw = (wgrad_up_raw if up else wgrad_same_raw)(dy, xpad).to(w.dtype)
         dx = None
         if ctx.needs_input_grad[0]:

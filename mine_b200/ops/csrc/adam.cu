@@ -68,4 +68,65 @@ void launch_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, 
   }
 }
 
+
+// ---- gradient gather: many autograd-owned gradient tensors -> their slices of the flat gradient arena --------------
+// The framework's AccumulateGrad node adds every incoming gradient into a pre-set ``.grad`` with one elementwise kernel
+// per parameter (~320 launches, 0.9 ms per step in round 2's CUPTI table).  With ``.grad = None`` it simply keeps the
+// incoming tensor; this kernel then moves a whole list of them into the arena at once (tensor / chunk tables in
+// kernel-parameter space, multi-tensor-apply style; a null source zero-fills its slice).
+constexpr int kMcTensors = 48, kMcBlocks = 448, kMcChunk = 32768;     // floats per chunk
+struct MultiCopyMeta {
+  const float* src[kMcTensors];
+  float* dst[kMcTensors];
+  int numel[kMcTensors];
+  uint8_t block_tensor[kMcBlocks];
+  uint16_t block_chunk[kMcBlocks];
+};
+
+__global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ MultiCopyMeta m) {
+  const int t = m.block_tensor[blockIdx.x];
+  const int c0 = (int)m.block_chunk[blockIdx.x] * kMcChunk;
+  const int n = min(kMcChunk, m.numel[t] - c0);
+  const float* __restrict__ src = m.src[t] ? m.src[t] + c0 : nullptr;
+  float* __restrict__ dst = m.dst[t] + c0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (!src || (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (vec) {
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = src ? reinterpret_cast<const float4*>(src)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(dst)[i] = v;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) dst[i] = src ? src[i] : 0.f;
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src ? src[i] : 0.f;
+  }
+}
+
+void launch_multi_copy(const float* const* srcs, float* const* dsts, const int64_t* numels, int count, cudaStream_t stream) {
+  MultiCopyMeta m;
+  int nt = 0, nb = 0;
+  auto flush = [&]() {
+    if (nb > 0) multi_copy_kernel<<<nb, 256, 0, stream>>>(m);
+    nt = 0; nb = 0;
+  };
+  for (int i = 0; i < count; ++i) {
+    int64_t done = 0;
+    while (done < numels[i]) {
+      if (nt == kMcTensors || nb == kMcBlocks) flush();
+      // at most 65535 chunks per table entry and as many blocks as still fit into this launch
+      const int64_t left = numels[i] - done;
+      int64_t chunks = (left + kMcChunk - 1) / kMcChunk;
+      if (chunks > kMcBlocks - nb) chunks = kMcBlocks - nb;
+      const int64_t take = chunks * kMcChunk < left ? chunks * kMcChunk : left;
+      m.src[nt] = srcs[i] ? srcs[i] + done : nullptr;
+      m.dst[nt] = dsts[i] + done;
+      m.numel[nt] = (int)take;
+      for (int c = 0; c < (int)chunks; ++c) { m.block_tensor[nb] = (uint8_t)nt; m.block_chunk[nb] = (uint16_t)c; ++nb; }
+      ++nt;
+      done += take;
+    }
+  }
+  flush();
+}
+
 }  // namespace mine

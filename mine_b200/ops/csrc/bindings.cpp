@@ -174,6 +174,30 @@ void fused_adam(at::Tensor p, const at::Tensor& g, at::Tensor m, at::Tensor v, c
                           cur_stream());
 }
 
+// gradient gather: srcs[i] (dense fp32 tensors in their parameter's memory order; undefined -> zero fill) into
+// flat[offsets[i] : offsets[i] + numels[i]]
+void gather_into_arena(at::Tensor flat, std::vector<c10::optional<at::Tensor>> srcs, std::vector<int64_t> offsets,
+                       std::vector<int64_t> numels) {
+  check_f32(flat, "flat");
+  TORCH_CHECK(srcs.size() == offsets.size() && srcs.size() == numels.size(), "list lengths differ");
+  c10::cuda::CUDAGuard guard(flat.device());
+  std::vector<const float*> sp(srcs.size());
+  std::vector<float*> dp(srcs.size());
+  for (size_t i = 0; i < srcs.size(); ++i) {
+    TORCH_CHECK(offsets[i] >= 0 && offsets[i] + numels[i] <= flat.numel(), "slice outside the arena");
+    dp[i] = flat.data_ptr<float>() + offsets[i];
+    if (srcs[i].has_value() && srcs[i]->defined()) {
+      const at::Tensor& t = *srcs[i];
+      TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.numel() == numels[i] && t.is_non_overlapping_and_dense(),
+                  "gradient ", i, " must be a dense CUDA fp32 tensor of its parameter's size");
+      sp[i] = t.data_ptr<float>();
+    } else {
+      sp[i] = nullptr;
+    }
+  }
+  mine::launch_multi_copy(sp.data(), dp.data(), numels.data(), (int)srcs.size(), cur_stream());
+}
+
 std::vector<at::Tensor> smooth_v2_fwd(const at::Tensor& img, const at::Tensor& disp, bool need_grad) {
   check_f32(img, "img"); check_f32(disp, "disp");
   TORCH_CHECK(img.dim() == 4 && img.size(1) == 3 && disp.dim() == 4 && disp.size(1) == 1, "img Bx3xHxW, disp Bx1xHxW");
@@ -241,6 +265,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sparse_point_fwd", &sparse_point_fwd);
   m.def("sparse_point_bwd", &sparse_point_bwd);
   m.def("fused_adam", &fused_adam);
+  m.def("gather_into_arena", &gather_into_arena);
   m.def("smooth_v2_fwd", &smooth_v2_fwd);
   m.def("smooth_v2_bwd", &smooth_v2_bwd);
   m.def("smooth_v1_fwd", &smooth_v1_fwd);

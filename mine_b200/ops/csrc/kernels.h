@@ -39,6 +39,8 @@ void launch_masked_l1_fwd(const float* a, const float* b, const float* mask, flo
 // hyper: device array {lr, step}
 void launch_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1,
                        float beta2, float eps, float weight_decay, cudaStream_t stream);
+// srcs[i] (null: zero fill) -> dsts[i], numels[i] floats each, a handful of multi-tensor launches
+void launch_multi_copy(const float* const* srcs, float* const* dsts, const int64_t* numels, int count, cudaStream_t stream);
 
 }  // namespace mine
 

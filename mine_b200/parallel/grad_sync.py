@@ -57,11 +57,61 @@ class FlatArena:
             return chunk.view(co, kh, kw, ci).permute(0, 3, 1, 2)
         return chunk.view(p.shape)
 
+    # ---- gradients -----------------------------------------------------------------------------------------------
+    # Two modes.  "accumulate" (CPU, and anything that calls backward() more than once per step): ``.grad`` of every
+    # parameter is a view of the gradient arena, autograd adds into it (one elementwise kernel per parameter).
+    # "gather" (CUDA default, ``MINE_B200_GRAD_GATHER=0`` disables): ``.grad`` is None during backward, so autograd's
+    # AccumulateGrad just keeps the incoming tensor (no kernel); :meth:`gather_grads` then moves whole parameter ranges
+    # into the arena with a few multi-tensor launches (``adam.cu::multi_copy_kernel``) and re-attaches the views.
+    def gather_mode(self) -> bool:
+        import os
+        return self.data.is_cuda and os.environ.get("MINE_B200_GRAD_GATHER", "1") == "1"
+
     def zero_grad(self) -> None:
+        if self.gather_mode():
+            for p in self.params:
+                p.grad = None
+            self._gathered = [False] * len(self.params)
+            return
         self.grad.zero_()
         for i, (p, o) in enumerate(zip(self.params, self.offsets)):   # re-attach if something set grads to None
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 p.grad = self.view_of(self.grad, i)
+
+    def gather_grads(self, first: int = 0, last: int = -1) -> None:
+        """Move the autograd-owned gradients of parameters ``first..last`` into their arena slices (zero where a
+        parameter received none) and point ``.grad`` at the arena again.  No-op outside gather mode."""
+        if not self.gather_mode():
+            return
+        if last < 0:
+            last = len(self.params) - 1
+        done = getattr(self, "_gathered", None)
+        if done is None:
+            done = self._gathered = [False] * len(self.params)
+        srcs, offs, nums, slow = [], [], [], []
+        base = self.grad.data_ptr()
+        for i in range(first, last + 1):
+            if done[i]:
+                continue
+            done[i] = True
+            p, o = self.params[i], self.offsets[i]
+            g = p.grad
+            if g is not None and g.data_ptr() == base + 4 * o:
+                continue                                       # already lives in the arena
+            if g is not None and (g.dtype != torch.float32 or g.stride() != p.stride() or not g.is_cuda):
+                slow.append((i, g))                            # unexpected layout: plain copy
+                continue
+            srcs.append(g)
+            offs.append(o)
+            nums.append(p.numel())
+        if srcs:
+            from ..ops import cuda as C
+            C._ext.gather_into_arena(self.grad, srcs, offs, nums)
+            C.LAUNCHES["count"] += max(1, len(srcs) // 40)
+        for i, g in slow:
+            self.view_of(self.grad, i).copy_(g)
+        for i in range(first, last + 1):
+            self.params[i].grad = self.view_of(self.grad, i)
 
     def slice_of(self, first: int, last: int):
         """Arena range covering params ``first..last`` inclusive."""
@@ -107,6 +157,7 @@ class GradSync:
     def _launch(self, b: dict) -> None:
         b["pending"] = 0
         b["done"] = True
+        self.arena.gather_grads(b["first"], b["last"])          # gather mode: this bucket's gradients into the arena
         view = self.arena.grad[b["lo"]:b["hi"]]
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream(view.device))
@@ -122,6 +173,7 @@ class GradSync:
     def finish(self) -> None:
         """Reduce whatever was not launched from hooks, then make the compute stream wait."""
         if not self.enabled:
+            self.arena.gather_grads()                           # single replica: everything at once
             return
         for b in self.buckets:
             if not b.get("done", False):

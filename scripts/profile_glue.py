@@ -19,21 +19,24 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], with_stack=True) as prof:
     t.train_step(items)
     torch.cuda.synchronize()
-agg = collections.defaultdict(lambda: [0, 0.0])
-for ev in prof.events():
-    if ev.device_type != torch.autograd.DeviceType.CPU or not ev.name.startswith("aten::"):
+rows = []
+for ka in prof.key_averages(group_by_stack_n=12):
+    if not ka.key.startswith("aten::"):
         continue
-    dt = getattr(ev, "self_device_time_total", 0) or 0
+    dt = getattr(ka, "self_device_time_total", 0) or 0
     if dt <= 0:
         continue
     site = "?"
-    for fr in (ev.stack or []):
-        if "/mine_b200/" in fr or "task.py" in fr:
-            site = fr.split("/mine_b200/")[-1][:60] if "/mine_b200/" in fr else fr[-60:]
+    for fr in (ka.stack or []):
+        if ("/mine_b200/" in fr or "/repo/task" in fr) and "profile_glue" not in fr:
+            site = fr.split("/mine_b200/")[-1][:70]
             break
-    agg[(ev.name, site)][0] += 1
-    agg[(ev.name, site)][1] += dt
+    rows.append((dt, ka.count, ka.key, site))
+agg = collections.defaultdict(lambda: [0, 0.0])
+for dt, c, k, site in rows:
+    agg[(k, site)][0] += c
+    agg[(k, site)][1] += dt
 tot = sum(v[1] for v in agg.values())
 print("ATen self device time per step: %.0f us in %d op calls" % (tot, sum(v[0] for v in agg.values())))
-for (name, site), (c, us) in sorted(agg.items(), key=lambda x: -x[1][1])[:70]:
+for (name, site), (c, us) in sorted(agg.items(), key=lambda x: -x[1][1])[:80]:
     print("%8.1f us %4d  %-34s %s" % (us, c, name, site))
