@@ -10,6 +10,12 @@
 // 128-byte rows, SWIZZLE_128B_BASE32B, pixel-pair / phase-pair rows for 16-channel tensors), the single-thread issue
 // loop, fp32 atomics into the packed gradient - is as in wgrad_taps_kernel.
 //
+// Operand roles are SWAPPED with respect to wgrad_taps_kernel: the activation tap-blocks form the M dimension (3 taps x
+// 32 channels = 96 of the 128 accumulator rows are useful) and the output gradient the N dimension (16..64 columns).
+// tcgen05.mma costs max(M,128) * N / 256 cycles, so the fixed-cost M side should be the wide one: with the gradient on
+// M (Co = 16..32 useful rows of 128) and 96 tap columns on N the narrow layers were tensor-pipe bound at ~50 % active
+// (profiles/ncu_r2_wgrad_*), 3x the math of this arrangement.
+//
 // The work of a layer is described by small tables built on the host (per chunk of <= 512 accumulator columns):
 //   loads[] : activation boxes of a pixel tile {horizontal offset, channel block}
 //   ops[]   : MMAs per K step {A slab, load, first line, number of line-blocks, accumulator column, diag half,
@@ -52,6 +58,7 @@ struct WHParams {
   int y0, x0;                           // window origin of the taps in x
   int diag;                             // 0 none, 1 parity-slab ops, 2 halves inside a block (16-channel pair rows)
   int half_dst_stride;                  // phase-pair: destination tap index of half h = dst + h * stride; else 0
+  int ncols;                            // accumulator columns per op = gradient channels (diag modes: 32 = 2 halves x 16)
   int NB;                               // input channels handled per CTA (<= 128), ci_blocks over blockIdx.z
   int stages, tmem_cols, nchunks, ci_blocks;
   float* dw;
@@ -77,7 +84,7 @@ __device__ __forceinline__ void wh_issue_loop(const WHParams& p, const uint4* s_
     for (int k = 0; k < ksteps; ++k, ka += a_step, kb += b_step) {
       for (int o = issuer; o < nops; o += n_issuers) {
         const uint4 c = s_opc[o];
-        umma_lohi2<TF32>(c.z, ka + c.x, a_hi, kb + c.y, b_hi, c.w, acc);
+        umma_lohi2<TF32>(c.z, kb + c.y, b_hi, ka + c.x, a_hi, c.w, acc);       // A = activation blocks, B = gradient
       }
       acc = 1u;
     }
@@ -129,7 +136,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       const WHOp& op = ck.ops[o];
       s_opc[o] = make_uint4((uint32_t)(op.a_idx * p.a_slabs) * (a_slab >> 4),
                             (a_bytes + (uint32_t)op.load * b_region + (uint32_t)op.ty0 * line_bytes_) >> 4,
-                            tmem_base + op.col, make_idesc(128, op.nblk * p.bw, 1, 1, tf32));
+                            tmem_base + op.col, make_idesc(128, p.ncols, 1, 1, tf32));
     }
   }
   __syncthreads();
@@ -137,7 +144,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const uint32_t lta = tf32 ? 1u : layout_type_for(p.a_row), ltb = tf32 ? 1u : layout_type_for(p.b_row);
   const int kpi = 32 / p.es;                             // K rows per instruction: 16 (bf16) or 8 (tf32)
   const uint32_t sbo_a = tf32 ? 512u : 8u * p.a_row, sbo_b = tf32 ? 512u : 8u * p.b_row;
-  const uint32_t a_lbo = (p.a_slabs > 1) ? a_slab : 0u;   // see wgrad_taps_kernel
+  const uint32_t a_lbo = a_slab;                          // gradient = N operand: column blocks one channel slab apart
   const uint64_t da0 = make_smem_desc(0, a_lbo, sbo_a, lta);
   const uint64_t db0 = make_smem_desc(0, (uint32_t)p.rpl * p.b_row, sbo_b, ltb);   // MN-block stride of B = one image line
   const uint32_t a_lo0 = (uint32_t)da0, a_hi = (uint32_t)(da0 >> 32), b_lo0 = (uint32_t)db0, b_hi = (uint32_t)(db0 >> 32);
@@ -189,31 +196,31 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     if (my_tiles > 0) {
-      const int par = p.diag ? m / p.Co : 0;               // diag modes: row = half * Co + co (Co == 16)
-      const int co = p.diag ? m - par * p.Co : m;
-      const bool row_ok = p.diag ? (m < 2 * p.Co) : (co < p.Co);
-      if (!p.diag || q == 0) {
-        for (int o = 0; o < ck.nops; ++o) {
-          const WHOp op = ck.ops[o];
-          const int cb_ci = p.b_kind ? 0 : ck.loads[op.load].cb * p.b_cb;       // first input channel of this op's block
-          for (int j = 0; j < op.nblk; ++j) {
-            for (int c0 = 0; c0 < p.bw; c0 += 16) {
-              uint32_t v[16];
-              tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(op.col + j * p.bw + c0), v);
-              if (!row_ok) continue;
-              int ci = nb * p.NB + cb_ci + c0, half = 0;
-              if (p.diag == 1) { if (op.half != par) continue; half = par; }
-              else if (p.diag == 2) { if ((c0 >> 4) != par) continue; half = par; ci = nb * p.NB + (c0 & 15); }
-              if (ci >= p.Ci) continue;
-              const int gt = op.dst[j] + half * p.half_dst_stride;
-              float* dst = p.dw + (((size_t)gt * p.Co + co) * p.Ci + ci);
+      // accumulator row m = (line-block j, channel c' of the block), columns = gradient channels (diag modes: 2 halves x
+      // 16).  Only the diagonal (activation half == gradient half) is kept in the diag modes.
+      const int j = m / p.bw, cp = m - j * p.bw;
+      for (int o = 0; o < ck.nops; ++o) {
+        const WHOp op = ck.ops[o];
+        int ci = nb * p.NB + (p.b_kind ? 0 : ck.loads[op.load].cb * p.b_cb) + cp, half = 0;
+        bool keep = j < op.nblk;
+        if (p.diag == 1) half = op.half;                                  // parity-slab op: activation half of the whole op
+        else if (p.diag == 2) { half = cp >> 4; ci = nb * p.NB + (cp & 15); }   // half inside the 2-pixel row
+        keep = keep && ci < p.Ci;
+        const int gt = keep ? op.dst[j] + half * p.half_dst_stride : 0;
+        // tcgen05.ld takes ONE column address per warp: in the diag modes both gradient halves are visited with uniform
+        // addresses and every lane keeps the one that matches its activation half
+        const int nhalf = p.diag == 2 ? 2 : 1, ncol = p.diag ? 16 : p.Co;
+        for (int hh = 0; hh < nhalf; ++hh) {
+          const int col0 = p.diag == 1 ? op.half * 16 : hh * 16 * (p.diag == 2);
+          const bool mine_half = p.diag != 2 || half == hh;
+          for (int c0 = 0; c0 < ncol; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(op.col + col0 + c0), v);
+            if (!keep || !mine_half) continue;
+            float* dst = p.dw + (((size_t)gt * p.Co + c0) * p.Ci + ci);
 #pragma unroll
-              for (int e = 0; e < 16; e += 4) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + e), "f"(__uint_as_float(v[e])),
-                             "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
-                             : "memory");
-              }
-            }
+            for (int e = 0; e < 16; ++e)
+              if (c0 + e < p.Co) atomicAdd(dst + (size_t)e * p.Ci, __uint_as_float(v[e]));
           }
         }
       }
@@ -319,6 +326,10 @@ bool try_launch_wgrad_halo(const WgradLaunch& L, cudaStream_t stream, const char
     p.a_oy[g] = phase_pair ? g : (up ? (g >> 1) : 0);
     p.a_ox[g] = phase_pair ? 0 : (up ? (g & 1) : 0);
   }
+  p.ncols = p.diag ? 32 : w.Co;
+  if (p.ncols % 16 || p.ncols > 256) return false;
+  const int max_blk = 128 / p.bw;                 // line-blocks per MMA (M = 128 rows)
+  if (max_blk < 1) return false;
   // ---- ops, then chunks of <= 512 accumulator columns ----
   struct RawOp { int a_idx, xoff, cb, ty0, nblk, half, dst[3]; };
   RawOp raw[48]; int nraw = 0;
@@ -349,11 +360,22 @@ bool try_launch_wgrad_halo(const WgradLaunch& L, cudaStream_t stream, const char
           o.dst[2] = 0;
         }
   }
+  // an MMA covers at most max_blk line-blocks (M = 128 rows): split longer ops
+  for (int i = 0; i < nraw; ++i) {
+    if (raw[i].nblk <= max_blk) continue;
+    if (nraw == 48) return false;
+    RawOp tail = raw[i];
+    tail.ty0 = raw[i].ty0 + max_blk; tail.nblk = raw[i].nblk - max_blk;
+    for (int j2 = 0; j2 < 3; ++j2) tail.dst[j2] = j2 + max_blk < 3 ? raw[i].dst[j2 + max_blk] : 0;
+    raw[i].nblk = max_blk;
+    for (int k2 = nraw; k2 > i + 1; --k2) raw[k2] = raw[k2 - 1];
+    raw[i + 1] = tail;
+    ++nraw;
+  }
   p.nchunks = 0;
   {
     // balanced chunks: as few as the 512 accumulator columns allow, the ops spread evenly over them
-    int total_cols = 0;
-    for (int i = 0; i < nraw; ++i) total_cols += raw[i].nblk * p.bw;
+    int total_cols = nraw * p.ncols;
     int want = (total_cols + 511) / 512;
     if ((nraw + want - 1) / want > 12) want = (nraw + 11) / 12;
     const int per_chunk = (nraw + want - 1) / want;
@@ -364,7 +386,7 @@ bool try_launch_wgrad_halo(const WgradLaunch& L, cudaStream_t stream, const char
       c.nl = 0; c.nops = 0; c.cols = 0;
       while (i < nraw && c.nops < per_chunk) {
         const RawOp& r = raw[i];
-        const int cols = r.nblk * p.bw;
+        const int cols = p.ncols;
         if (c.cols + cols > 512) break;
         int li = -1;
         for (int l = 0; l < c.nl; ++l) if (c.loads[l].x_off == r.xoff && c.loads[l].cb == r.cb) li = l;
@@ -384,12 +406,15 @@ bool try_launch_wgrad_halo(const WgradLaunch& L, cudaStream_t stream, const char
   p.tmem_cols = next_pow2_cols(max_cols);
   const size_t stage_bytes = (((size_t)p.rows * p.a_row * p.NA + (size_t)p.lines * p.rpl * p.b_row * max_nl + 1023) / 1024) * 1024;
   // two resident CTAs per SM (two sets of issuers / epilogue warps) when the accumulators and >= 2 stages allow it
-  int ctas = (2 * p.tmem_cols <= 512 && 2 * stage_bytes + 1024 <= 107 * 1024) ? 2 : 1;
-  int stages = (int)(((ctas == 2 ? 107u : 200u) * 1024u - 1024u) / stage_bytes);
+  const size_t slack = 8 * (size_t)p.rpl * p.b_row;
+  int ctas = (2 * p.tmem_cols <= 512 && 2 * stage_bytes + 1024 + slack <= 107 * 1024) ? 2 : 1;
+  int stages = (int)(((ctas == 2 ? 107u : 198u) * 1024u - 1024u - slack) / stage_bytes);
   if (stages > 4) stages = 4;
   if (stages < 2) return false;
   p.stages = stages;
-  size_t smem = (size_t)stages * stage_bytes + 1024;
+  // + slack: the activation operand always spans 128 accumulator rows = 128 / bw line-blocks, the unused ones read
+  // (and discard) whatever follows the box
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (size_t)p.rpl * p.b_row;
   const size_t smem_floor = (220u * 1024u) / (ctas + 1) + 1024;          // one more CTA must NOT fit
   if (smem < smem_floor) smem = smem_floor;
   // ---- tensor maps ----
