@@ -246,6 +246,9 @@ bool try_launch_wgrad_halo(const WgradLaunch& L, cudaStream_t stream, const char
   const bool up = w.G == 4 && w.T == 4 && w.dy_stride == 2;      // sub-pixel (upsample) form
   const bool same = w.G == 1 && w.T == 9 && w.dy_stride == 1;    // 3x3, same resolution
   if (!up && !same) return false;
+  // measured (profiles/kernel_bench_r2_*): with the gradient on the N side this kernel wins for narrow gradients; for
+  // Co >= 128 (and the sub-pixel form at Co = 64) wgrad_taps_kernel's arrangement (gradient on M) is faster
+  if (w.Co > 64 || (up && w.Co > 32)) return false;
   // tap window of x: all offsets inside 3x3, canonical tables
   int y0 = 1 << 20, x0 = 1 << 20, y1 = -(1 << 20), x1 = -(1 << 20);
   for (int g = 0; g < w.G; ++g)
