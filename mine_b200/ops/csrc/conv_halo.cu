@@ -175,81 +175,82 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       mbar_wait(&accum_full[as], (j >> 1) & 1);
       tc_fence_after();
       const float* pbias = p.plane_bias ? p.plane_bias + (size_t)n_img * p.Co : nullptr;
-      for (int g = 0; g < p.G; ++g) {
-        const int out_y = oy * p.out_sy + p.out_oy[g], out_x = ox * p.out_sx + p.out_ox[g];
-        const size_t out_pix = ((size_t)n_img * p.Ho + out_y) * p.Wo + out_x;
-        const uint32_t t_acc = tmem_base + (uint32_t)((as * p.G + g) * p.BN) + ((uint32_t)(q * 32) << 16);
-        const float* smap = nullptr;
-        if (p.shared_map && valid)
-          smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
-          // two 16-column loads in flight before the wait
-          uint32_t v[32];
-          const bool two = c0 + 16 < p.BN;
-          tmem_ld16_nowait(t_acc + (uint32_t)c0, v);
-          if (two) tmem_ld16_nowait(t_acc + (uint32_t)(c0 + 16), v + 16);
-          tmem_ld_wait();
+      // the accumulators of all groups are contiguous in TMEM: walk them as one range, two 16-column loads in flight per
+      // wait (a 16-column chunk never straddles two groups: BN is a multiple of 16)
+      const uint32_t t_acc0 = tmem_base + (uint32_t)(as * p.G * p.BN) + ((uint32_t)(q * 32) << 16);
+      const int ncols_all = p.G * p.BN;
+      for (int f0 = 0; f0 < ncols_all; f0 += 32) {
+        uint32_t v[32];
+        const bool two = f0 + 16 < ncols_all;
+        tmem_ld16_nowait(t_acc0 + (uint32_t)f0, v);
+        if (two) tmem_ld16_nowait(t_acc0 + (uint32_t)(f0 + 16), v + 16);
+        tmem_ld_wait();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cc = c0 + 16 * h;
-            if (h == 1 && !two) break;
-            if (cc >= p.Co) break;
-            float f[16];
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !two) break;
+          const int f = f0 + 16 * h;
+          const int g = f / p.BN, cc = f - g * p.BN;
+          if (cc >= p.Co) continue;
+          const int out_y = oy * p.out_sy + p.out_oy[g], out_x = ox * p.out_sx + p.out_ox[g];
+          const size_t out_pix = ((size_t)n_img * p.Ho + out_y) * p.Wo + out_x;
+          const float* smap = nullptr;
+          if (p.shared_map && valid)
+            smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
+          float fv[16];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(v[16 * h + jj]);
-            if (p.chan_bias) {
+          for (int jj = 0; jj < 16; ++jj) fv[jj] = __uint_as_float(v[16 * h + jj]);
+          if (p.chan_bias) {
 #pragma unroll
-              for (int jj = 0; jj < 16; ++jj) if (cc + jj < p.Co) f[jj] += p.chan_bias[cc + jj];
-            }
-            if (pbias) {
+            for (int jj = 0; jj < 16; ++jj) if (cc + jj < p.Co) fv[jj] += p.chan_bias[cc + jj];
+          }
+          if (pbias) {
 #pragma unroll
-              for (int jj = 0; jj < 16; ++jj) if (cc + jj < p.Co) f[jj] += pbias[cc + jj];
-            }
-            if (smap) {
+            for (int jj = 0; jj < 16; ++jj) if (cc + jj < p.Co) fv[jj] += pbias[cc + jj];
+          }
+          if (smap) {
 #pragma unroll
-              for (int jj = 0; jj < 16; jj += 4) {
-                const float4 m = *reinterpret_cast<const float4*>(smap + cc + jj);
-                f[jj] += m.x; f[jj + 1] += m.y; f[jj + 2] += m.z; f[jj + 3] += m.w;
-              }
-            }
-            if (reg_stats) {
-              if (cc == 0) {
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) { const float x = valid ? f[jj] : 0.f; ra1[jj] += x; ra2[jj] += x * x; }
-              } else {
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) { const float x = valid ? f[jj] : 0.f; rb1[jj] += x; rb2[jj] += x * x; }
-              }
-            }
-            if (valid) {
-              if (p.act == 1) {                     // MPI head: 4 real channels -> packed fp32 MPI (+ sign of sigma)
-                float4 o;
-                o.x = 1.f / (1.f + __expf(-f[0])); o.y = 1.f / (1.f + __expf(-f[1])); o.z = 1.f / (1.f + __expf(-f[2]));
-                o.w = p.head_alpha ? 1.f / (1.f + __expf(-f[3])) : fabsf(f[3]) + 1e-4f;
-                reinterpret_cast<float4*>(p.out)[out_pix] = o;
-                if (p.raw_out) reinterpret_cast<int8_t*>(p.raw_out)[out_pix] = f[3] >= 0.f ? (int8_t)1 : (int8_t)-1;
-              } else if (p.out_fp32) {
-                float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + cc;
-#pragma unroll
-                for (int jj = 0; jj < 16; jj += 4)
-                  *reinterpret_cast<float4*>(dst + jj) = make_float4(f[jj], f[jj + 1], f[jj + 2], f[jj + 3]);
-              } else {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + cc;
-                uint4 o0, o1;
-                __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-                __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  h0[jj] = __floats2bfloat162_rn(f[2 * jj], f[2 * jj + 1]);
-                  h1[jj] = __floats2bfloat162_rn(f[8 + 2 * jj], f[8 + 2 * jj + 1]);
-                }
-                *reinterpret_cast<uint4*>(dst) = o0;
-                *reinterpret_cast<uint4*>(dst + 8) = o1;
-              }
+            for (int jj = 0; jj < 16; jj += 4) {
+              const float4 m = *reinterpret_cast<const float4*>(smap + cc + jj);
+              fv[jj] += m.x; fv[jj + 1] += m.y; fv[jj + 2] += m.z; fv[jj + 3] += m.w;
             }
           }
-          __syncwarp();
+          if (reg_stats) {
+            if (cc == 0) {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) { const float x = valid ? fv[jj] : 0.f; ra1[jj] += x; ra2[jj] += x * x; }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) { const float x = valid ? fv[jj] : 0.f; rb1[jj] += x; rb2[jj] += x * x; }
+            }
+          }
+          if (valid) {
+            if (p.act == 1) {                     // MPI head: 4 real channels -> packed fp32 MPI (+ sign of sigma)
+              float4 o;
+              o.x = 1.f / (1.f + __expf(-fv[0])); o.y = 1.f / (1.f + __expf(-fv[1])); o.z = 1.f / (1.f + __expf(-fv[2]));
+              o.w = p.head_alpha ? 1.f / (1.f + __expf(-fv[3])) : fabsf(fv[3]) + 1e-4f;
+              reinterpret_cast<float4*>(p.out)[out_pix] = o;
+              if (p.raw_out) reinterpret_cast<int8_t*>(p.raw_out)[out_pix] = fv[3] >= 0.f ? (int8_t)1 : (int8_t)-1;
+            } else if (p.out_fp32) {
+              float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + cc;
+#pragma unroll
+              for (int jj = 0; jj < 16; jj += 4)
+                *reinterpret_cast<float4*>(dst + jj) = make_float4(fv[jj], fv[jj + 1], fv[jj + 2], fv[jj + 3]);
+            } else {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + cc;
+              uint4 o0, o1;
+              __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+              __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                h0[jj] = __floats2bfloat162_rn(fv[2 * jj], fv[2 * jj + 1]);
+                h1[jj] = __floats2bfloat162_rn(fv[8 + 2 * jj], fv[8 + 2 * jj + 1]);
+              }
+              *reinterpret_cast<uint4*>(dst) = o0;
+              *reinterpret_cast<uint4*>(dst + 8) = o1;
+            }
+          }
         }
+        __syncwarp();
       }
       // this warp has finished reading the accumulators of the tile: hand them back to the MMA issuer
       tc_fence_before();

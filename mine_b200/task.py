@@ -28,7 +28,7 @@ from .config import get as cfg_get
 from .models import checkpoint as ckpt
 from .models.decoder import DepthDecoder
 from .models.encoder import ResnetEncoder
-from .models.norm import set_stat_reducer
+from .models.norm import BatchNorm, flush_batch_counters, set_stat_reducer
 from .ops import api as ops
 from .optim import ArenaAdam, MultiStepLR
 from .parallel import bootstrap
@@ -400,7 +400,12 @@ class SynthesisTask:
         self.set_data(items)
         self.grad_sync.begin_step()
         self.optimizer.zero_grad()
-        loss_dict, _ = self.loss_fcn(is_val=False)
+        BatchNorm.defer_counters = True
+        try:
+            loss_dict, _ = self.loss_fcn(is_val=False)
+        finally:
+            BatchNorm.defer_counters = False
+        flush_batch_counters(self.backbone, self.decoder)
         with self.profiler.phase("backward"):
             loss_dict["loss"].backward()
         with self.profiler.phase("grad_sync"):
