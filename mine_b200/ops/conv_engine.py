@@ -50,6 +50,8 @@ def set_precision(precision: str) -> None:
     emu.ACT_DTYPE = ACT_DTYPE
     if not _emulated and _ext is not None:
         _ext.set_operand_size(4 if precision == "tf32" else 2)
+    if "_PACK_STATE" in globals():
+        _PACK_STATE["plan"] = _PACK_STATE["seen"] = None                 # packs of the other operand type are stale
 
 
 def round_tf32(t: torch.Tensor) -> torch.Tensor:
@@ -161,12 +163,49 @@ def unpack_up_grad(dwp: torch.Tensor) -> torch.Tensor:
     return dw9.reshape(3, 3, co, ci).permute(2, 3, 0, 1)
 
 
+class PackPlan:
+    """The operand packs of a fixed set of ``(weight, mode)`` pairs re-made by ONE kernel launch per step
+    (``pack_weights_multi_kernel``; 26 launches per step before).  Outputs and the device-resident job table persist; the
+    weights are addressed by pointer, so they must keep their storage (they live in the flat parameter arena)."""
+
+    def __init__(self, items):
+        self.items = list(items)
+        self.es = ext().get_operand_size()
+        self.outs, self.table, self.nblocks = ext().pack_plan_create([w for w, _ in self.items],
+                                                                     [int(m) for _, m in self.items])
+        self.index = {(_pack_key(w), int(m)): o for (w, m), o in zip(self.items, self.outs)}
+
+    def run(self) -> None:
+        ext().pack_plan_run(self.table, self.nblocks)
+        _count()
+
+
+_PACK_STATE = {"plan": None, "seen": None}
+
+
+def _pack_key(w: torch.Tensor):
+    return (w.data_ptr(), tuple(w.shape), tuple(w.stride()))
+
+
+def pack_plan_enabled() -> bool:
+    return not _emulated and os.environ.get("MINE_B200_PACK_PLAN", "1") == "1"
+
+
 def pack(w: torch.Tensor, mode: int) -> torch.Tensor:
-    """bf16 GEMM operand pack of a [Co,Ci,3,3] fp32 weight (any strides) in ONE kernel launch.
+    """GEMM operand pack of a [Co,Ci,3,3] fp32 weight (any strides): served from the active :class:`PackPlan` (one launch
+    per step for all layers) or made by its own kernel launch.
     mode 0/1: fprop same / upsample, 2/3: dgrad same / upsample (see csrc/conv_tcgen05.cu)."""
     w = w.detach()
     if w.dtype != torch.float32:
         w = w.float()
+    plan = _PACK_STATE["plan"]
+    if plan is not None:
+        hit = plan.index.get((_pack_key(w), int(mode)))
+        if hit is not None:
+            return hit
+    seen = _PACK_STATE["seen"]
+    if seen is not None:
+        seen.append((w, int(mode)))
     _count()
     return ext().pack_weights(w, mode)
 
@@ -518,10 +557,39 @@ class ConvEngine:
                 return m.reducer
         return None
 
+    def _begin_packs(self, device) -> None:
+        """Batched weight packing: the first training step records which ``(weight, mode)`` packs the model asks for (forward
+        and backward); from the second step on one launch re-makes all of them before the encoder runs."""
+        if not pack_plan_enabled() or device.type != "cuda":
+            _PACK_STATE["plan"] = _PACK_STATE["seen"] = None
+            return
+        plan = getattr(self, "_pack_plan", None)
+        if plan is not None and plan.es != ext().get_operand_size():
+            plan = self._pack_plan = None                               # precision changed: other operand type
+        if plan is None and not torch.cuda.is_current_stream_capturing():
+            seen = getattr(self, "_pack_seen", None)
+            if seen:
+                # only weights that live in parameter storage (persistent addresses), not per-step temporaries
+                homes = {q.untyped_storage().data_ptr() for mod in (self.backbone, self.decoder) for q in mod.parameters()}
+                uniq = {}
+                for w, m in seen:
+                    if w.untyped_storage().data_ptr() in homes:
+                        uniq.setdefault((_pack_key(w), m), (w, m))
+                if uniq:
+                    plan = self._pack_plan = PackPlan(uniq.values())
+                self._pack_seen = None if uniq else []
+            else:
+                self._pack_seen = []
+        _PACK_STATE["plan"] = plan
+        _PACK_STATE["seen"] = getattr(self, "_pack_seen", None) if plan is None else None
+        if plan is not None:
+            plan.run()
+
     def predict(self, src_imgs: torch.Tensor, disparity: torch.Tensor) -> List[torch.Tensor]:
         dec = self.decoder
         b, s = disparity.shape
         n = b * s
+        self._begin_packs(src_imgs.device)
         amp = dict(device_type=src_imgs.device.type, dtype=torch.bfloat16,
                    enabled=src_imgs.is_cuda and ACT_DTYPE == torch.bfloat16)
         if self.encoder_engine is not None:

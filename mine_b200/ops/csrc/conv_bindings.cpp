@@ -3,6 +3,9 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstring>
+#include <tuple>
+
 #include "conv_engine.h"
 #include "kernels.h"
 
@@ -134,6 +137,46 @@ at::Tensor pack_weights(const at::Tensor& w, int64_t mode) {
   mine::launch_pack_weights(w.data_ptr<float>(), w.stride(0), w.stride(1), w.stride(2), w.stride(3), Co, Ci, (int)mode,
                             rows_pad, out.data_ptr(), g_operand_es, cur_stream());
   return out;
+}
+
+// Batched packer: the operand packs of many weights in one launch per step.  ``pack_plan_create`` allocates the
+// (persistent) outputs and uploads the job table once; ``pack_plan_run`` re-packs all of them from the current weights.
+std::tuple<std::vector<at::Tensor>, at::Tensor, int64_t> pack_plan_create(const std::vector<at::Tensor>& ws,
+                                                                         const std::vector<int64_t>& modes) {
+  TORCH_CHECK(ws.size() == modes.size() && !ws.empty(), "pack_plan_create: one mode per weight");
+  c10::cuda::CUDAGuard guard(ws[0].device());
+  std::vector<at::Tensor> outs;
+  std::vector<mine::PackJob> jobs(ws.size());
+  int block0 = 0;
+  for (size_t i = 0; i < ws.size(); ++i) {
+    const at::Tensor& w = ws[i];
+    const int mode = (int)modes[i];
+    TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.dim() == 4 && w.size(2) == 3 && w.size(3) == 3,
+                "pack_plan_create expects CUDA fp32 [Co,Ci,3,3] tensors (any strides)");
+    const int Co = w.size(0), Ci = w.size(1);
+    const int rows = mode >= 2 ? Ci : Co, cols = mode >= 2 ? Co : Ci;
+    const int rows_pad = (rows + 15) / 16 * 16;
+    at::Tensor out = at::empty({(mode & 1) ? 16 : 9, rows_pad, cols}, w.options().dtype(operand_dtype()));
+    mine::PackJob& j = jobs[i];
+    j.w = w.data_ptr<float>(); j.out = out.data_ptr();
+    j.so = w.stride(0); j.si = w.stride(1); j.sy = w.stride(2); j.sx = w.stride(3);
+    j.Co = Co; j.Ci = Ci; j.mode = mode; j.rows_pad = rows_pad; j.total = (int)out.numel(); j.block0 = block0;
+    block0 += (j.total + 255) / 256;
+    outs.push_back(out);
+  }
+  const int64_t bytes = (int64_t)(jobs.size() * sizeof(mine::PackJob));
+  at::Tensor host = at::empty({bytes}, at::TensorOptions().dtype(at::kByte));
+  memcpy(host.data_ptr(), jobs.data(), (size_t)bytes);
+  at::Tensor table = host.to(ws[0].device());
+  return std::make_tuple(outs, table, (int64_t)block0);
+}
+
+void pack_plan_run(const at::Tensor& table, int64_t nblocks) {
+  TORCH_CHECK(table.is_cuda() && table.scalar_type() == at::kByte, "pack_plan_run: job table");
+  c10::cuda::CUDAGuard guard(table.device());
+  mine::launch_pack_weights_multi(reinterpret_cast<const mine::PackJob*>(table.data_ptr()),
+                                  (int)(table.numel() / (int64_t)sizeof(mine::PackJob)), (int)nblocks, g_operand_es,
+                                  cur_stream());
 }
 
 void wgrad_taps(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_t Hg, int64_t Wg, int64_t G, int64_t T,
@@ -384,6 +427,8 @@ void register_conv(pybind11::module_& m) {
   m.def("conv_taps", &conv_taps);
   m.def("wgrad_taps", &wgrad_taps);
   m.def("pack_weights", &pack_weights);
+  m.def("pack_plan_create", &pack_plan_create);
+  m.def("pack_plan_run", &pack_plan_run);
   m.def("bn_act_pad_fwd", &bn_act_pad_fwd);
   m.def("bn_act_pad_fwd_x", &bn_act_pad_fwd_x);
   m.def("bn_bwd_apply_x", &bn_bwd_apply_x);

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "conv_engine.h"
+
 namespace mine {
 
 // ------------------------------------------------------------------------------------------------
@@ -123,6 +125,26 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int
   const uint32_t fmt = tf32 ? 2u : 1u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Role code runs WARP-UNIFORM (all 32 lanes walk the loops and wait on the barriers); only the asynchronous instruction
+// itself (TMA, tcgen05.mma, commit) is predicated on one elected lane.  With a divergent ``if (lane == 0)`` around the whole
+// role the compiler keeps every address / descriptor in vector registers and pays an R2UR per operand of every UTCMMA /
+// UTMALDG; in uniform control flow they live in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
+// n / d and n % d through the launcher-made multiplier (conv_engine.h::make_fastdiv)
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return f.d == 1u ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+__device__ __forceinline__ void fdivmod(int n, const FastDiv& f, int& q, int& r) {
+  q = fdiv(n, f);
+  r = n - q * (int)f.d;
 }
 
 __device__ __forceinline__ float warp_sum32(float v) {

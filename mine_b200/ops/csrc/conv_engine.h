@@ -5,6 +5,20 @@
 
 namespace mine {
 
+// n / d for 0 <= n < 2^31 as one multiply-high and a shift (the persistent kernels decompose work-item indices in
+// every role of every tile; an integer divide is ~40 dependent instructions on the epilogue warps' critical path)
+struct FastDiv { uint32_t mul, shr, d; };
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f{0u, 0u, (uint32_t)(d < 1 ? 1 : d)};
+  if (d <= 1) return f;
+  int lg = 0;
+  while ((1u << lg) < (uint32_t)d) ++lg;
+  const int p = 31 + lg;
+  f.mul = (uint32_t)((((uint64_t)1 << p) + (uint32_t)d - 1) / (uint32_t)d);
+  f.shr = (uint32_t)(p - 32);
+  return f;
+}
+
 struct ConvParams {
   // logical GEMM pixel grid (per image) and its 128-pixel tiling
   int N, Hg, Wg, TH, TW, tiles_x, tiles_y;
@@ -34,6 +48,8 @@ struct ConvParams {
   int halo_y0, halo_x0;
   int8_t rel_y[4][16], rel_x[4][16];
   int box_stride, w_tile_bytes, w_bytes;
+  // divisors of the work-item decomposition (filled by the launchers)
+  FastDiv fd_tiles, fd_tiles_x, fd_n, fd_g, fd_planes;
 };
 
 struct ConvLaunch {
@@ -79,6 +95,13 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream);
 bool try_launch_conv_halo(const ConvLaunch& L, cudaStream_t stream, const char** err);
 void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co, int Ci, int mode,
                          int rows_pad, void* out, int es, cudaStream_t stream);
+// one entry of the device-resident job table of the batched weight packer (256 threads per block)
+struct PackJob {
+  const float* w; void* out;
+  int64_t so, si, sy, sx;
+  int Co, Ci, mode, rows_pad, total, block0;
+};
+void launch_pack_weights_multi(const PackJob* jobs, int njobs, int nblocks, int es, cudaStream_t stream);
 const char* launch_wgrad_taps(const WgradLaunch& L, cudaStream_t stream);
 // wgrad_halo.cu: returns true when the layer was eligible and has been launched (err set on launch failure)
 bool try_launch_wgrad_halo(const WgradLaunch& L, cudaStream_t stream, const char** err);

@@ -36,10 +36,11 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// MMA-issue loop of one CTA (single thread).  s_tab[(g * T + t) * kblocks + kb] = {A offset inside a halo set, B tile
-// address}, both in 16-byte descriptor units and constant for the lifetime of the CTA.
+// MMA-issue loop of one CTA: the whole warp walks it (uniform control flow -> descriptors in uniform registers), one
+// elected lane issues.  Tap (g, t) of k-block kb reads the halo set at  rel_x * box_stride + rel_y * line_bytes  and the
+// resident weight tile (g * T + t) * kblocks + kb; both offsets come straight from the parameter block.
 template <bool TF32, int KS>
-__device__ __forceinline__ void halo_issue_loop(const ConvParams& p, const uint2* s_tab, uint8_t* ring, uint32_t set_bytes,
+__device__ __forceinline__ void halo_issue_loop(const ConvParams& p, uint32_t w_base, uint32_t ring_base, uint32_t set_bytes,
                                                 uint32_t tmem_base, uint64_t* full_bar, uint64_t* empty_bar,
                                                 uint64_t* accum_full, uint64_t* accum_empty, int total_work) {
   const int row_bytes = p.KB * p.es;
@@ -47,6 +48,8 @@ __device__ __forceinline__ void halo_issue_loop(const ConvParams& p, const uint2
   const uint64_t desc0 = make_smem_desc(0, 16, 8u * row_bytes, layout_type_for(row_bytes));
   const uint32_t lo0 = (uint32_t)desc0, hi = (uint32_t)(desc0 >> 32);
   const int G = p.G, T = p.T, KBK = p.kblocks, BN = p.BN;
+  const uint32_t line16 = (uint32_t)(p.TW * row_bytes) >> 4, box16 = (uint32_t)p.box_stride >> 4;
+  const uint32_t wt16 = (uint32_t)p.w_tile_bytes >> 4;
   int s = 0, j = 0;
   uint32_t par = 0;
   for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
@@ -56,25 +59,27 @@ __device__ __forceinline__ void halo_issue_loop(const ConvParams& p, const uint2
     for (int kb = 0; kb < KBK; ++kb) {
       mbar_wait(&full_bar[s], par);
       tc_fence_after();
-      const uint32_t slot_lo = lo0 + (smem_u32(ring + (size_t)s * set_bytes) >> 4);
-      const uint2* tab = s_tab + kb;
-      uint32_t d_tmem = tmem_base + (uint32_t)(as * G * BN);
-      for (int g = 0; g < G; ++g, d_tmem += BN) {
-        uint32_t acc = kb ? 1u : 0u;
-        for (int t = 0; t < T; ++t, tab += KBK) {
-          const uint2 e = *tab;
-          const uint32_t a_lo = slot_lo + e.x, b_lo = lo0 + e.y;
+      if (elect_one()) {
+        const uint32_t slot_lo = lo0 + ((ring_base + (uint32_t)s * set_bytes) >> 4);
+        uint32_t b_lo = lo0 + (w_base >> 4) + (uint32_t)kb * wt16;
+        uint32_t d_tmem = tmem_base + (uint32_t)(as * G * BN);
+        for (int g = 0; g < G; ++g, d_tmem += BN) {
+          uint32_t acc = kb ? 1u : 0u;
+          for (int t = 0; t < T; ++t, b_lo += (uint32_t)KBK * wt16) {
+            const uint32_t a_lo = slot_lo + (uint32_t)p.rel_x[g][t] * box16 + (uint32_t)p.rel_y[g][t] * line16;
 #pragma unroll
-          for (int k = 0; k < KS; ++k) {
-            umma_lohi<TF32>(d_tmem, a_lo + 2u * k, b_lo + 2u * k, hi, idesc, acc);
-            acc = 1u;
+            for (int k = 0; k < KS; ++k) {
+              umma_lohi<TF32>(d_tmem, a_lo + 2u * k, b_lo + 2u * k, hi, idesc, acc);
+              acc = 1u;
+            }
           }
         }
+        umma_commit(&empty_bar[s]);
+        if (kb == KBK - 1) umma_commit(&accum_full[as]);
       }
-      umma_commit(&empty_bar[s]);
+      __syncwarp();
       if (++s == p.stages) { s = 0; par ^= 1u; }
     }
-    umma_commit(&accum_full[as]);
   }
 }
 
@@ -89,9 +94,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __shared__ __align__(8) uint64_t w_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_stats[2][64];
-  __shared__ uint2 s_tab[4 * 16 * 4];                  // per (group, tap, k-block): {A offset, B tile address} >> 4
+  __shared__ __align__(16) float s_cbias[64];                        // per-channel bias (zeros without one): read once per CTA
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int tiles = p.tiles_x * p.tiles_y;
   const int total_work = tiles * p.N;                  // w -> (tile, image); the G groups share one halo
   const int row_bytes = p.KB * p.es;
@@ -110,11 +115,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 128; i += blockDim.x) (&s_stats[0][0])[i] = 0.f;
-  for (int i = threadIdx.x; i < p.G * p.T * p.kblocks; i += blockDim.x) {
-    const int gt = i / p.kblocks, g = gt / p.T, t = gt - g * p.T;
-    const uint32_t a_off = (uint32_t)p.rel_x[g][t] * p.box_stride + (uint32_t)p.rel_y[g][t] * (uint32_t)(p.TW * row_bytes);
-    s_tab[i] = make_uint2(a_off >> 4, (smem_u32(w_smem) + (uint32_t)i * p.w_tile_bytes) >> 4);
-  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_cbias[i] = (p.chan_bias && i < p.Co) ? p.chan_bias[i] : 0.f;
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -122,63 +123,73 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---------------- TMA producer: warp-uniform loop, one elected lane issues ----------------
+    if (elect_one()) {
       // resident weights: every (group, tap, k-block) tile once per CTA
       const int gt_n = p.G * p.T;
       mbar_expect_tx(&w_bar, (uint32_t)gt_n * p.kblocks * (uint32_t)p.BN * row_bytes);
       for (int gt = 0; gt < gt_n; ++gt)
         for (int kb = 0; kb < p.kblocks; ++kb)
           tma_load_3d(&map_w, &w_bar, w_smem + (size_t)(gt * p.kblocks + kb) * p.w_tile_bytes, kb * p.KB, 0, gt);
-      int s = 0;
-      uint32_t par = 0;
-      bool ring_full = false;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int tile = w % tiles, n_img = w / tiles;
-        const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-        const int iy = tile_y * p.TH + p.halo_y0, ix = tile_x * p.TW + p.halo_x0;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          if (ring_full) mbar_wait(&empty_bar[s], par ^ 1u);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t par = 0;
+    bool ring_full = false;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int tile, n_img, tile_y, tile_x;
+      fdivmod(w, p.fd_tiles, n_img, tile);
+      fdivmod(tile, p.fd_tiles_x, tile_y, tile_x);
+      const int iy = tile_y * p.TH + p.halo_y0, ix = tile_x * p.TW + p.halo_x0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        if (ring_full) mbar_wait(&empty_bar[s], par ^ 1u);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[s], 3u * box_bytes);
           uint8_t* slot = ring + (size_t)s * set_bytes;
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx)
             tma_load_4d(&map_x, &full_bar[s], slot + dx * p.box_stride, kb * p.KB, ix + dx, iy, n_img);
-          if (++s == p.stages) { s = 0; par ^= 1u; ring_full = true; }
         }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; par ^= 1u; ring_full = true; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(&w_bar, 0);
-      const int ks = row_bytes / 32;
-#define HALO_ISSUE(TF, KS_) halo_issue_loop<TF, KS_>(p, s_tab, ring, set_bytes, tmem_base, full_bar, empty_bar, accum_full, accum_empty, total_work)
-      if (p.es == 4) { if (ks == 4) HALO_ISSUE(true, 4); else if (ks == 2) HALO_ISSUE(true, 2); else HALO_ISSUE(true, 1); }
-      else { if (ks == 4) HALO_ISSUE(false, 4); else if (ks == 2) HALO_ISSUE(false, 2); else HALO_ISSUE(false, 1); }
+    // ---------------- MMA issue: warp-uniform loop, one elected lane issues ----------------
+    mbar_wait(&w_bar, 0);
+    const int ks = row_bytes / 32;
+#define HALO_ISSUE(TF, KS_) halo_issue_loop<TF, KS_>(p, smem_u32(w_smem), smem_u32(ring), set_bytes, tmem_base, full_bar, empty_bar, accum_full, accum_empty, total_work)
+    if (p.es == 4) { if (ks == 4) HALO_ISSUE(true, 4); else if (ks == 2) HALO_ISSUE(true, 2); else HALO_ISSUE(true, 1); }
+    else { if (ks == 4) HALO_ISSUE(false, 4); else if (ks == 2) HALO_ISSUE(false, 2); else HALO_ISSUE(false, 1); }
 #undef HALO_ISSUE
-    }
   } else {
     // ---------------- epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) ----------------
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int ty = r / p.TW, tx = r - ty * p.TW;
     const bool reg_stats = p.stats != nullptr;           // BN <= 32 (launcher): sums stay in registers across tiles
+    const bool has_cbias = p.chan_bias != nullptr;
     float ra1[16], ra2[16], rb1[16], rb2[16];
 #pragma unroll
     for (int jj = 0; jj < 16; ++jj) ra1[jj] = ra2[jj] = rb1[jj] = rb2[jj] = 0.f;
     int j = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
-      const int tile = w % tiles, n_img = w / tiles;
-      const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+      int tile, n_img, tile_y, tile_x;                     // multiply-high decomposition: no integer divides per tile
+      fdivmod(w, p.fd_tiles, n_img, tile);
+      fdivmod(tile, p.fd_tiles_x, tile_y, tile_x);
       const int oy = tile_y * p.TH + ty, ox = tile_x * p.TW + tx;
       const bool valid = (oy < p.Hg) && (ox < p.Wg);
       const int as = j & 1;
+      const float* pbias = p.plane_bias ? p.plane_bias + (size_t)n_img * p.Co : nullptr;
+      const size_t img_pix = (size_t)n_img * p.Ho;
+      const size_t smap_img = p.shared_map ? (size_t)fdiv(n_img, p.fd_planes) * p.Ho : 0;
       mbar_wait(&accum_full[as], (j >> 1) & 1);
       tc_fence_after();
-      const float* pbias = p.plane_bias ? p.plane_bias + (size_t)n_img * p.Co : nullptr;
       // the accumulators of all groups are contiguous in TMEM: walk them as one range, two 16-column loads in flight per
       // wait (a 16-column chunk never straddles two groups: BN is a multiple of 16)
       const uint32_t t_acc0 = tmem_base + (uint32_t)(as * p.G * p.BN) + ((uint32_t)(q * 32) << 16);
       const int ncols_all = p.G * p.BN;
+      int g = 0, cc = 0;                                   // group / first channel of the current 16-column chunk
       for (int f0 = 0; f0 < ncols_all; f0 += 32) {
         uint32_t v[32];
         const bool two = f0 + 16 < ncols_all;
@@ -188,34 +199,44 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h == 1 && !two) break;
-          const int f = f0 + 16 * h;
-          const int g = f / p.BN, cc = f - g * p.BN;
-          if (cc >= p.Co) continue;
-          const int out_y = oy * p.out_sy + p.out_oy[g], out_x = ox * p.out_sx + p.out_ox[g];
-          const size_t out_pix = ((size_t)n_img * p.Ho + out_y) * p.Wo + out_x;
-          const float* smap = nullptr;
-          if (p.shared_map && valid)
-            smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co;
+          const int g_now = g, cc_now = cc;
+          cc += 16;
+          if (cc >= p.BN) { cc = 0; ++g; }
+          if (cc_now >= p.Co) continue;
+          const int out_y = oy * p.out_sy + p.out_oy[g_now], out_x = ox * p.out_sx + p.out_ox[g_now];
+          const size_t out_pix = (img_pix + out_y) * p.Wo + out_x;
           float fv[16];
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) fv[jj] = __uint_as_float(v[16 * h + jj]);
-          if (p.chan_bias) {
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) if (cc + jj < p.Co) fv[jj] += p.chan_bias[cc + jj];
-          }
-          if (pbias) {
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) if (cc + jj < p.Co) fv[jj] += pbias[cc + jj];
-          }
-          if (smap) {
+          if (has_cbias) {
 #pragma unroll
             for (int jj = 0; jj < 16; jj += 4) {
-              const float4 m = *reinterpret_cast<const float4*>(smap + cc + jj);
+              const float4 b = *reinterpret_cast<const float4*>(&s_cbias[cc_now + jj]);
+              fv[jj] += b.x; fv[jj + 1] += b.y; fv[jj + 2] += b.z; fv[jj + 3] += b.w;
+            }
+          }
+          if (pbias) {
+            if (cc_now + 16 <= p.Co) {            // Co is a multiple of 4 whenever a plane bias exists (decoder widths)
+#pragma unroll
+              for (int jj = 0; jj < 16; jj += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(pbias + cc_now + jj));
+                fv[jj] += b.x; fv[jj + 1] += b.y; fv[jj + 2] += b.z; fv[jj + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) if (cc_now + jj < p.Co) fv[jj] += pbias[cc_now + jj];
+            }
+          }
+          if (p.shared_map && valid) {
+            const float* smap = p.shared_map + ((smap_img + out_y) * p.Wo + out_x) * p.Co + cc_now;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) {
+              const float4 m = *reinterpret_cast<const float4*>(smap + jj);
               fv[jj] += m.x; fv[jj + 1] += m.y; fv[jj + 2] += m.z; fv[jj + 3] += m.w;
             }
           }
           if (reg_stats) {
-            if (cc == 0) {
+            if (cc_now == 0) {
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) { const float x = valid ? fv[jj] : 0.f; ra1[jj] += x; ra2[jj] += x * x; }
             } else {
@@ -226,17 +247,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (valid) {
             if (p.act == 1) {                     // MPI head: 4 real channels -> packed fp32 MPI (+ sign of sigma)
               float4 o;
-              o.x = 1.f / (1.f + __expf(-fv[0])); o.y = 1.f / (1.f + __expf(-fv[1])); o.z = 1.f / (1.f + __expf(-fv[2]));
-              o.w = p.head_alpha ? 1.f / (1.f + __expf(-fv[3])) : fabsf(fv[3]) + 1e-4f;
+              o.x = __fdividef(1.f, 1.f + __expf(-fv[0]));
+              o.y = __fdividef(1.f, 1.f + __expf(-fv[1]));
+              o.z = __fdividef(1.f, 1.f + __expf(-fv[2]));
+              o.w = p.head_alpha ? __fdividef(1.f, 1.f + __expf(-fv[3])) : fabsf(fv[3]) + 1e-4f;
               reinterpret_cast<float4*>(p.out)[out_pix] = o;
               if (p.raw_out) reinterpret_cast<int8_t*>(p.raw_out)[out_pix] = fv[3] >= 0.f ? (int8_t)1 : (int8_t)-1;
             } else if (p.out_fp32) {
-              float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + cc;
+              float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + cc_now;
 #pragma unroll
               for (int jj = 0; jj < 16; jj += 4)
                 *reinterpret_cast<float4*>(dst + jj) = make_float4(fv[jj], fv[jj + 1], fv[jj + 2], fv[jj + 3]);
             } else {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + cc;
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + cc_now;
               uint4 o0, o1;
               __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
               __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
@@ -316,6 +339,9 @@ bool try_launch_conv_halo(const ConvLaunch& L, cudaStream_t stream, const char**
   if (u8 >= u16) { p.TW = 8; p.TH = 16; } else { p.TW = 16; p.TH = 8; }
   p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
   p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
+  p.fd_tiles = make_fastdiv(p.tiles_x * p.tiles_y);
+  p.fd_tiles_x = make_fastdiv(p.tiles_x);
+  p.fd_planes = make_fastdiv(p.planes_per_image > 0 ? p.planes_per_image : 1);
   const uint32_t box_bytes = (uint32_t)(p.TH + 2) * p.TW * row_bytes;
   p.box_stride = (int)((box_bytes + 1023u) / 1024u * 1024u);
   p.w_tile_bytes = (int)(((uint32_t)p.BN * row_bytes + 1023u) / 1024u * 1024u);

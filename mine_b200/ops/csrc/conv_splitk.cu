@@ -23,6 +23,14 @@ namespace mine {
 
 namespace sk {
 
+// one elected lane / provably uniform warp index: see conv_common.cuh (role code on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -139,7 +147,7 @@ conv_splitk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __shared__ __align__(8) uint64_t accum_full;
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int tiles = p.tiles_x * p.tiles_y;
   const int w = blockIdx.x;                                 // (tile, image, channel block), tile fastest
   const int tile = w % tiles, wi = w / tiles;
@@ -170,7 +178,7 @@ conv_splitk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {                                       // one elected lane: uniform code (conv_common.cuh)
       const int oy0 = tile_y * p.TH * p.in_stride, ox0 = tile_x * p.TW * p.in_stride;
       int t = i0 / p.kblocks, kb = i0 - t * p.kblocks;
       for (int i = 0; i < my_iters; ++i) {
@@ -184,7 +192,7 @@ conv_splitk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const bool tf32 = p.es == 4;
       const uint32_t idesc = make_idesc(128, p.BN, tf32);
       const uint64_t desc0 = make_smem_desc(0, 16, 8u * row_bytes, layout_type_for(row_bytes));

@@ -44,12 +44,12 @@ namespace mine {
 // ------------------------------------------------------------------------------------------------
 // conv_taps: fprop / phase-upsample fprop / dgrad
 // ------------------------------------------------------------------------------------------------
-// MMA-issue loop (one thread per CTA).  The issuing thread is a latency-bound scalar instruction stream: for narrow
-// layers (N = 16..64) its per-instruction bookkeeping - not the tensor pipe - paces the kernel (ncu source view of round
-// 2: ~80 SASS instructions per tap), so the loop is specialised on the operand kind and the K steps per row and works
-// on the low descriptor words only.
+// MMA-issue loop: the whole warp walks it in uniform control flow (descriptors, TMEM addresses and the instruction
+// descriptor stay in uniform registers; conv_common.cuh::elect_one), one elected lane issues.  For the narrow layers
+// (N = 16..64) the issue stream - not the tensor pipe - paces the kernel, so the loop is specialised on the operand kind
+// and the K steps per row and works on the low descriptor words only.
 template <bool TF32, int KS>
-__device__ __forceinline__ void taps_issue_loop(const ConvParams& p, uint8_t* smem_aligned, uint32_t stage_bytes,
+__device__ __forceinline__ void taps_issue_loop(const ConvParams& p, uint32_t ring_base, uint32_t stage_bytes,
                                                 uint32_t sub_bytes, uint32_t a_bytes, uint32_t tmem_base,
                                                 uint64_t* full_bar, uint64_t* empty_bar, uint64_t* accum_full,
                                                 uint64_t* accum_empty, int total_work, int iters) {
@@ -71,19 +71,22 @@ __device__ __forceinline__ void taps_issue_loop(const ConvParams& p, uint8_t* sm
       const int n_in = remaining < ipb ? remaining : ipb;
       mbar_wait(&full_bar[s], par);
       tc_fence_after();
-      uint32_t a_lo = lo0 + (smem_u32(smem_aligned + (size_t)s * stage_bytes) >> 4);
-      for (int u = 0; u < n_in; ++u, a_lo += sub16) {
-#pragma unroll
-        for (int k = 0; k < KS; ++k) {
-          umma_lohi<TF32>(d_tmem, a_lo + 2u * k, a_lo + ab16 + 2u * k, hi, idesc, first);
-          first = 1u;
-        }
-      }
-      umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
       remaining -= n_in;
+      if (elect_one()) {
+        uint32_t a_lo = lo0 + ((ring_base + (uint32_t)s * stage_bytes) >> 4);
+        for (int u = 0; u < n_in; ++u, a_lo += sub16) {
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            umma_lohi<TF32>(d_tmem, a_lo + 2u * k, a_lo + ab16 + 2u * k, hi, idesc, (u | k) ? 1u : first);
+          }
+        }
+        umma_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
+        if (remaining == 0) umma_commit(&accum_full[as]);   // accumulator of this tile complete
+      }
+      __syncwarp();
+      first = 1u;
       if (++s == stages) { s = 0; par ^= 1u; }
     }
-    umma_commit(&accum_full[as]);           // accumulator of this tile complete
   }
 }
 
@@ -100,13 +103,8 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __shared__ __align__(8) uint64_t accum_empty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_stats[2][256];
-  __shared__ int s_tap[4][16][2];                      // (dy, dx) of every (group, tap): smem, not param-space indexing
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < 64) {
-    s_tap[threadIdx.x >> 4][threadIdx.x & 15][0] = p.tap_y[threadIdx.x >> 4][threadIdx.x & 15];
-    s_tap[threadIdx.x >> 4][threadIdx.x & 15][1] = p.tap_x[threadIdx.x >> 4][threadIdx.x & 15];
-  }
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int tiles = p.tiles_x * p.tiles_y;
   const int total_work = tiles * p.N * p.G * p.CB;     // w -> (tile, image, group, channel block), tile fastest
 
@@ -132,23 +130,25 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
   const int iters = p.T * p.kblocks;
   if (warp == 0) {
-    if (lane == 0) {
-      // Scalar bookkeeping is kept division-free inside the loops (one thread issues everything; integer
-      // divides and parameter-array indexing were the dominant cost for the 16/32-channel layers).
+    // ---------------- TMA producer: one elected lane (an elect.sync region is uniform code for the compiler:
+    // coordinates, addresses and the tap table of the parameter block stay on the uniform datapath) ----------------
+    if (elect_one()) {
       int s = 0;                                        // ring slot and its parity, carried across tiles
       uint32_t par = 0;
       bool ring_full = false;                           // becomes true once every slot has been used once
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int tile = w % tiles, wi = w / tiles;
-        const int n_img = wi % p.N, gc = wi / p.N;
-        const int g = gc % p.G, wcol0 = (gc / p.G) * p.BN;
-        const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+        int tile, wi, n_img, gc, g, cb, tile_y, tile_x;      // multiply-high decomposition (conv_engine.h::FastDiv)
+        fdivmod(w, p.fd_tiles, wi, tile);
+        fdivmod(wi, p.fd_n, gc, n_img);
+        fdivmod(gc, p.fd_g, cb, g);
+        fdivmod(tile, p.fd_tiles_x, tile_y, tile_x);
+        const int wcol0 = cb * p.BN;
         const int oy0 = tile_y * p.TH * p.in_stride, ox0 = tile_x * p.TW * p.in_stride;
         const int wrow0 = g * p.T;
         int u = 0, n_in = 0, remaining = iters;
         uint8_t* slot = nullptr;
         for (int t = 0; t < p.T; ++t) {
-          const int iy = oy0 + s_tap[g][t][0], ix = ox0 + s_tap[g][t][1];
+          const int iy = oy0 + p.tap_y[g][t], ix = ox0 + p.tap_x[g][t];
           for (int kb = 0; kb < p.kblocks; ++kb) {
             if (u == 0) {                               // open the next pipeline stage
               if (ring_full) mbar_wait(&empty_bar[s], par ^ 1u);
@@ -168,13 +168,12 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const int ks = row_bytes / 32;
-#define TAPS_ISSUE(TF, KS_) taps_issue_loop<TF, KS_>(p, smem_aligned, stage_bytes, sub_bytes, a_bytes, tmem_base, full_bar, empty_bar, accum_full, accum_empty, total_work, iters)
-      if (p.es == 4) { if (ks == 4) TAPS_ISSUE(true, 4); else if (ks == 2) TAPS_ISSUE(true, 2); else TAPS_ISSUE(true, 1); }
-      else { if (ks == 4) TAPS_ISSUE(false, 4); else if (ks == 2) TAPS_ISSUE(false, 2); else TAPS_ISSUE(false, 1); }
+    // ---------------- MMA issue: warp-uniform loop, one elected lane issues ----------------
+    const int ks = row_bytes / 32;
+#define TAPS_ISSUE(TF, KS_) taps_issue_loop<TF, KS_>(p, smem_u32(smem_aligned), stage_bytes, sub_bytes, a_bytes, tmem_base, full_bar, empty_bar, accum_full, accum_empty, total_work, iters)
+    if (p.es == 4) { if (ks == 4) TAPS_ISSUE(true, 4); else if (ks == 2) TAPS_ISSUE(true, 2); else TAPS_ISSUE(true, 1); }
+    else { if (ks == 4) TAPS_ISSUE(false, 4); else if (ks == 2) TAPS_ISSUE(false, 2); else TAPS_ISSUE(false, 1); }
 #undef TAPS_ISSUE
-    }
   } else {
     // ---------------- epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) ----------------
     const int q = warp & 3;
@@ -188,9 +187,12 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     for (int jj = 0; jj < 16; ++jj) ra1[jj] = ra2[jj] = rb1[jj] = rb2[jj] = 0.f;
     int j = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++j) {
-      const int tile = w % tiles, n_img = (w / tiles) % p.N, gc = w / (tiles * p.N);
-      const int g = gc % p.G, cbase = (gc / p.G) * p.BN;     // first output channel of this work item's block
-      const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+      int tile, wi, n_img, gc, g, cb, tile_y, tile_x;
+      fdivmod(w, p.fd_tiles, wi, tile);
+      fdivmod(wi, p.fd_n, gc, n_img);
+      fdivmod(gc, p.fd_g, cb, g);
+      fdivmod(tile, p.fd_tiles_x, tile_y, tile_x);
+      const int cbase = cb * p.BN;                           // first output channel of this work item's block
       const int oy = tile_y * p.TH + ty, ox = tile_x * p.TW + tx;
       const bool valid = (oy < p.Hg) && (ox < p.Wg);
       const int out_y = oy * p.out_sy + p.out_oy[g], out_x = ox * p.out_sx + p.out_ox[g];
@@ -203,7 +205,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const float* cbias = p.chan_bias ? p.chan_bias + cbase : nullptr;
       const float* smap = nullptr;
       if (p.shared_map && valid)
-        smap = p.shared_map + (((size_t)(n_img / p.planes_per_image) * p.Ho + out_y) * p.Wo + out_x) * p.Co + cbase;
+        smap = p.shared_map + (((size_t)fdiv(n_img, p.fd_planes) * p.Ho + out_y) * p.Wo + out_x) * p.Co + cbase;
       const int co_left = p.Co - cbase;                      // real channels in this block (may be < BN: padding)
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
@@ -246,8 +248,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (valid) {
           if (p.act == 1) {                     // MPI head: 4 real channels -> packed fp32 MPI (+ sign of sigma)
             float4 o;
-            o.x = 1.f / (1.f + __expf(-f[0])); o.y = 1.f / (1.f + __expf(-f[1])); o.z = 1.f / (1.f + __expf(-f[2]));
-            o.w = p.head_alpha ? 1.f / (1.f + __expf(-f[3])) : fabsf(f[3]) + 1e-4f;
+            o.x = __fdividef(1.f, 1.f + __expf(-f[0]));
+            o.y = __fdividef(1.f, 1.f + __expf(-f[1]));
+            o.z = __fdividef(1.f, 1.f + __expf(-f[2]));
+            o.w = p.head_alpha ? __fdividef(1.f, 1.f + __expf(-f[3])) : fabsf(f[3]) + 1e-4f;
             reinterpret_cast<float4*>(p.out)[out_pix] = o;
             if (p.raw_out) reinterpret_cast<int8_t*>(p.raw_out)[out_pix] = f[3] >= 0.f ? (int8_t)1 : (int8_t)-1;
           } else if (p.out_fp32) {
@@ -351,7 +355,7 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // blockIdx.y enumerates (group, tap chunk, co block, ci block)
   int rem = blockIdx.y;
   const int nb = rem % p.ci_blocks; rem /= p.ci_blocks;
@@ -389,7 +393,7 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {                                   // TMA producer: one elected lane, uniform code
       const int b_cblocks = p.b_slabs / 2;               // channel blocks per parity of the B operand (diag modes, Ci >= 32)
       for (int i = 0; i < my_tiles; ++i) {
         const int tid = blockIdx.x + i * gridDim.x;
@@ -426,7 +430,7 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {                                   // MMA issue: one elected lane, uniform code
       const uint32_t lta = tf32 ? 1u : layout_type_for(a_row), ltb = tf32 ? 1u : layout_type_for(b_row);
       const int kpi = 32 / p.es;                         // K rows per instruction: 16 (bf16) or 8 (tf32)
       const uint32_t sbo_a = tf32 ? 512u : 8u * a_row, sbo_b = tf32 ? 512u : 8u * b_row;
@@ -654,11 +658,9 @@ __device__ __forceinline__ void store_operand(float* p, float v) {   // round to
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   *p = __uint_as_float(r);
 }
-template <typename T>
-__global__ void pack_weights_kernel(const float* __restrict__ w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co,
-                                    int Ci, int mode, int rows_pad, T* __restrict__ out, int total) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+// element `idx` of the [9 | 16, rows_pad, cols] operand pack of one [Co, Ci, 3, 3] weight (modes: header comment)
+__device__ __forceinline__ float pack_value(const float* __restrict__ w, int64_t so, int64_t si, int64_t sy, int64_t sx,
+                                            int Co, int Ci, int mode, int rows_pad, int idx) {
   const bool dgrad = mode >= 2, up = (mode & 1) != 0;
   const int cols = dgrad ? Co : Ci;
   const int col = idx % cols;
@@ -677,7 +679,35 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int64_t so, int
           if (phase_has(py, a, ky) && phase_has(px, b, kx)) v += base[ky * sy + kx * sx];
     }
   }
-  store_operand(out + idx, v);
+  return v;
+}
+
+template <typename T>
+__global__ void pack_weights_kernel(const float* __restrict__ w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co,
+                                    int Ci, int mode, int rows_pad, T* __restrict__ out, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  store_operand(out + idx, pack_value(w, so, si, sy, sx, Co, Ci, mode, rows_pad, idx));
+}
+
+// All operand packs of a model in ONE launch: block b belongs to the job whose [block0, block0 + blocks) range holds it
+// (the job table lives in device memory, built once per plan: conv_bindings.cpp::pack_plan_create).
+template <typename T>
+__global__ void pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ int s_job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;                          // last job with block0 <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_job = lo;
+  }
+  __syncthreads();
+  const PackJob j = jobs[s_job];
+  const int idx = ((int)blockIdx.x - j.block0) * blockDim.x + threadIdx.x;
+  if (idx >= j.total) return;
+  store_operand(reinterpret_cast<T*>(j.out) + idx, pack_value(j.w, j.so, j.si, j.sy, j.sx, j.Co, j.Ci, j.mode, j.rows_pad, idx));
 }
 
 void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int64_t sx, int Co, int Ci, int mode,
@@ -691,6 +721,12 @@ void launch_pack_weights(const float* w, int64_t so, int64_t si, int64_t sy, int
   else
     pack_weights_kernel<__nv_bfloat16><<<(total + 255) / 256, 256, 0, stream>>>(w, so, si, sy, sx, Co, Ci, mode, rows_pad,
                                                                                 (__nv_bfloat16*)out, total);
+}
+
+void launch_pack_weights_multi(const PackJob* jobs, int njobs, int nblocks, int es, cudaStream_t stream) {
+  if (njobs <= 0 || nblocks <= 0) return;
+  if (es == 4) pack_weights_multi_kernel<float><<<nblocks, 256, 0, stream>>>(jobs, njobs);
+  else pack_weights_multi_kernel<__nv_bfloat16><<<nblocks, 256, 0, stream>>>(jobs, njobs);
 }
 
 const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
@@ -710,6 +746,11 @@ const char* launch_conv_taps(const ConvLaunch& L, cudaStream_t stream) {
   p.kblocks = p.Ci / p.KB;
   p.tiles_x = (p.Wg + p.TW - 1) / p.TW;
   p.tiles_y = (p.Hg + p.TH - 1) / p.TH;
+  p.fd_tiles = make_fastdiv(p.tiles_x * p.tiles_y);
+  p.fd_tiles_x = make_fastdiv(p.tiles_x);
+  p.fd_n = make_fastdiv(p.N);
+  p.fd_g = make_fastdiv(p.G);
+  p.fd_planes = make_fastdiv(p.planes_per_image > 0 ? p.planes_per_image : 1);
   p.tmem_cols = next_pow2_cols(2 * p.BN);                  // double-buffered accumulator
   const uint32_t sub_bytes = 128u * p.KB * p.es + (((uint32_t)p.BN * p.KB * p.es + 1023u) / 1024u) * 1024u;
   int ipb = (int)(24u * 1024u / sub_bytes);                // (tap, k-block) iterations per barrier round trip

@@ -65,30 +65,40 @@ struct WHParams {
   WHChunk chunk[4];
 };
 
-// MMA issue loop of ONE issuer thread.  The ops of a K step are dealt round-robin to `n_issuers` threads (lane 0 of
-// the MMA warp and of the otherwise idle epilogue warps): a single issuing thread is a latency-bound scalar stream
-// (~150 cycles per tcgen05.mma measured in round 2), several of them keep the tensor pipe fed.  Every issuer commits its
-// own MMAs, so the slot / accumulator barriers expect `n_issuers` arrivals.
+// MMA issue loop of ONE issuer (an elected lane; the loop itself is uniform code, so the per-op constants are read
+// from the parameter block on the uniform datapath and descriptors never leave uniform registers).  The ops of a tile are
+// dealt round-robin to `n_issuers` warps (the MMA warp and the otherwise idle epilogue warps): a single issue stream is
+// latency bound, several of them keep the tensor pipe fed.  Every issuer commits its own MMAs, so the slot / accumulator
+// barriers expect `n_issuers` arrivals.  Per op the K steps run back to back (same accumulator).
 template <bool TF32>
-__device__ __forceinline__ void wh_issue_loop(const WHParams& p, const uint4* s_opc, int nops, int issuer, int n_issuers,
-                                              uint8_t* smem_aligned, uint32_t stage_bytes, uint32_t a_lo0, uint32_t a_hi,
+__device__ __forceinline__ void wh_issue_loop(const WHParams& p, const WHChunk& ck, int issuer, int n_issuers,
+                                              uint32_t ring_base, uint32_t stage_bytes, uint32_t a_lo0, uint32_t a_hi,
                                               uint32_t b_lo0, uint32_t b_hi, uint32_t a_step, uint32_t b_step, int ksteps,
-                                              int my_tiles, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* accum_bar) {
+                                              int my_tiles, uint32_t tmem_base, uint32_t a_slab16, uint32_t a_bytes,
+                                              uint32_t b_region, uint32_t line_bytes, uint64_t* full_bar,
+                                              uint64_t* empty_bar, uint64_t* accum_bar) {
+  const uint32_t idesc = make_idesc(128, p.ncols, 1, 1, TF32);
+  const int nops = ck.nops;
+  int s = 0;
+  uint32_t par = 0;
   for (int i = 0; i < my_tiles; ++i) {
-    const int s = i % p.stages, round = i / p.stages;
-    mbar_wait(&full_bar[s], round & 1);
+    mbar_wait(&full_bar[s], par);
     tc_fence_after();
-    const uint32_t base16 = smem_u32(smem_aligned + (size_t)s * stage_bytes) >> 4;
-    uint32_t acc = i > 0 ? 1u : 0u;
-    uint32_t ka = a_lo0 + base16, kb = b_lo0 + base16;
-    for (int k = 0; k < ksteps; ++k, ka += a_step, kb += b_step) {
-      for (int o = issuer; o < nops; o += n_issuers) {
-        const uint4 c = s_opc[o];
-        umma_lohi2<TF32>(c.z, kb + c.y, b_hi, ka + c.x, a_hi, c.w, acc);       // A = activation blocks, B = gradient
+    const uint32_t base16 = (ring_base + (uint32_t)s * stage_bytes) >> 4;
+    const uint32_t acc0 = i > 0 ? 1u : 0u;
+    for (int o = issuer; o < nops; o += n_issuers) {
+      const WHOp& op = ck.ops[o];
+      uint32_t ka = a_lo0 + base16 + (uint32_t)(op.a_idx * p.a_slabs) * a_slab16;
+      uint32_t kb = b_lo0 + base16 + ((a_bytes + (uint32_t)op.load * b_region + (uint32_t)op.ty0 * line_bytes) >> 4);
+      const uint32_t d_tmem = tmem_base + op.col;
+      uint32_t acc = acc0;
+      for (int k = 0; k < ksteps; ++k, ka += a_step, kb += b_step) {
+        umma_lohi2<TF32>(d_tmem, kb, b_hi, ka, a_hi, idesc, acc);            // A = activation blocks, B = gradient
+        acc = 1u;
       }
-      acc = 1u;
     }
     umma_commit(&empty_bar[s]);
+    if (++s == p.stages) { s = 0; par ^= 1u; }
   }
   umma_commit(accum_bar);
 }
@@ -102,9 +112,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ WHChunk ck;
-  __shared__ uint4 s_opc[12];                             // per op: {A offset, B offset, TMEM address, idesc}
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&p.chunk[blockIdx.y]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&ck);
@@ -129,16 +138,6 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  {
-    // per-op constants, read back with one 16-byte shared-memory load per MMA
-    const uint32_t line_bytes_ = (uint32_t)p.rpl * p.b_row;
-    for (int o = threadIdx.x; o < ck.nops; o += blockDim.x) {
-      const WHOp& op = ck.ops[o];
-      s_opc[o] = make_uint4((uint32_t)(op.a_idx * p.a_slabs) * (a_slab >> 4),
-                            (a_bytes + (uint32_t)op.load * b_region + (uint32_t)op.ty0 * line_bytes_) >> 4,
-                            tmem_base + op.col, make_idesc(128, p.ncols, 1, 1, tf32));
-    }
-  }
   __syncthreads();
   // issue-loop constants (every issuer thread needs them)
   const uint32_t lta = tf32 ? 1u : layout_type_for(p.a_row), ltb = tf32 ? 1u : layout_type_for(p.b_row);
@@ -152,10 +151,13 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int ksteps = p.rows / kpi;
 #define WH_ISSUE(ID)                                                                                                        \
   do {                                                                                                                      \
-    if (tf32) wh_issue_loop<true>(p, s_opc, ck.nops, ID, n_issuers, smem_aligned, stage_bytes, a_lo0, a_hi, b_lo0, b_hi,    \
-                                  a_step, b_step, ksteps, my_tiles, full_bar, empty_bar, &accum_bar);                       \
-    else wh_issue_loop<false>(p, s_opc, ck.nops, ID, n_issuers, smem_aligned, stage_bytes, a_lo0, a_hi, b_lo0, b_hi,        \
-                              a_step, b_step, ksteps, my_tiles, full_bar, empty_bar, &accum_bar);                           \
+    const WHChunk& pck = p.chunk[blockIdx.y];          /* parameter space: uniform loads */                                \
+    if (tf32) wh_issue_loop<true>(p, pck, ID, n_issuers, smem_u32(smem_aligned), stage_bytes, a_lo0, a_hi, b_lo0, b_hi,     \
+                                  a_step, b_step, ksteps, my_tiles, tmem_base, a_slab >> 4, a_bytes, b_region,              \
+                                  (uint32_t)p.rpl * p.b_row, full_bar, empty_bar, &accum_bar);                              \
+    else wh_issue_loop<false>(p, pck, ID, n_issuers, smem_u32(smem_aligned), stage_bytes, a_lo0, a_hi, b_lo0, b_hi,         \
+                              a_step, b_step, ksteps, my_tiles, tmem_base, a_slab >> 4, a_bytes, b_region,                  \
+                              (uint32_t)p.rpl * p.b_row, full_bar, empty_bar, &accum_bar);                                  \
   } while (0)
   const uint32_t stage_bytes = ((a_bytes + b_region * ck.nl + 1023u) / 1024u) * 1024u;
   uint8_t* smem_aligned = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
@@ -165,33 +167,38 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {                                     // TMA producer: one elected lane, uniform code
+      const WHChunk& pck = p.chunk[blockIdx.y];
+      int s = 0;
+      uint32_t par = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int tid = blockIdx.x + i * gridDim.x;
         const int n_img = tid / tiles_per_img, tt = tid - n_img * tiles_per_img;
         const int tile_y = tt / p.tiles_x, tile_x = tt - tile_y * p.tiles_x;
         const int oy0 = tile_y * p.TH, ox0 = tile_x * p.TW;
-        const int s = i % p.stages, round = i / p.stages;
-        if (i >= p.stages) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        if (i >= p.stages) mbar_wait(&empty_bar[s], par ^ 1u);
         uint8_t* a_dst = smem_aligned + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], a_bytes + b_region * ck.nl);
+        mbar_expect_tx(&full_bar[s], a_bytes + b_region * pck.nl);
         for (int g = 0; g < p.a_groups; ++g) {
           const int ay = oy0 * p.dy_stride + p.a_oy[g], ax = ox0 * p.dy_xmul + p.a_ox[g];
           for (int sl = 0; sl < p.a_slabs; ++sl)
             tma_load_4d(&map_dy, &full_bar[s], a_dst + (size_t)(g * p.a_slabs + sl) * a_slab, p.a_kind ? 0 : sl * p.a_cb, ax, ay, n_img);
         }
         uint8_t* b_dst = a_dst + a_bytes;
-        for (int l = 0; l < ck.nl; ++l, b_dst += b_region)
-          tma_load_4d(&map_x, &full_bar[s], b_dst, p.b_kind ? 0 : (nb * (p.NB / p.b_cb) + ck.loads[l].cb) * p.b_cb,
-                      ox0 + p.x0 + ck.loads[l].x_off, oy0 + p.y0, n_img);
+        for (int l = 0; l < pck.nl; ++l, b_dst += b_region)
+          tma_load_4d(&map_x, &full_bar[s], b_dst, p.b_kind ? 0 : (nb * (p.NB / p.b_cb) + pck.loads[l].cb) * p.b_cb,
+                      ox0 + p.x0 + pck.loads[l].x_off, oy0 + p.y0, n_img);
+        if (++s == p.stages) { s = 0; par ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) WH_ISSUE(0);
+    if (elect_one()) WH_ISSUE(0);
   } else {
     const int q = warp & 3;
     const int m = q * 32 + lane;                           // TMEM lane == accumulator row
-    if (lane == 0 && warp - 1 < n_issuers) WH_ISSUE(warp - 1);     // warps 2..4: extra issuers during the main loop
+    if (warp - 1 < n_issuers) {                            // warps 2..4: extra issuers during the main loop
+      if (elect_one()) WH_ISSUE(warp - 1);
+    }
     __syncwarp();
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
