@@ -154,6 +154,49 @@ __device__ __forceinline__ float warp_sum32(float v) {
 }
 
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait + make the 16 destination registers of an earlier tmem_ld16_nowait data-dependent on the wait (the compiler must
+// not read them before it)
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+
+// Sums of 16 per-lane values over the 32 lanes of a warp with 16 shuffles (a butterfly that halves the number of live
+// values at every step) instead of 16 x 5: afterwards lane l holds the total of x[(l >> 1) & 15].
+__device__ __forceinline__ float warp_reduce16(const float (&x)[16], int lane) {
+  float a[8], b[4], c[2];
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h16 ? x[i + 8] : x[i], send = h16 ? x[i] : x[i + 8];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h8 ? a[i + 4] : a[i], send = h8 ? a[i] : a[i + 4];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h4 ? b[i + 2] : b[i], send = h4 ? b[i] : b[i + 2];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float keep = h2 ? c[1] : c[0], send = h2 ? c[0] : c[1];
+  const float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
 // tcgen05.mma with the descriptors given as (low word, shared high word): the per-tap work of the issuing thread is one
 // 8-byte shared-memory load and two 32-bit adds (the address field of a descriptor never carries into its high word).
 template <bool TF32>

@@ -27,15 +27,6 @@
 
 namespace mine {
 
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // MMA-issue loop of one CTA: the whole warp walks it (uniform control flow -> descriptors in uniform registers), one
 // elected lane issues.  Tap (g, t) of k-block kb reads the halo set at  rel_x * box_stride + rel_y * line_bytes  and the
 // resident weight tile (g * T + t) * kblocks + kb; both offsets come straight from the parameter block.
@@ -195,7 +186,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const bool two = f0 + 16 < ncols_all;
         tmem_ld16_nowait(t_acc0 + (uint32_t)f0, v);
         if (two) tmem_ld16_nowait(t_acc0 + (uint32_t)(f0 + 16), v + 16);
-        tmem_ld_wait();
+        tmem_ld_wait16(v);
+        tmem_ld_wait16(v + 16);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h == 1 && !two) break;

@@ -207,20 +207,35 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (p.shared_map && valid)
         smap = p.shared_map + (((size_t)fdiv(n_img, p.fd_planes) * p.Ho + out_y) * p.Wo + out_x) * p.Co + cbase;
       const int co_left = p.Co - cbase;                      // real channels in this block (may be < BN: padding)
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_acc + (uint32_t)c0, v);
-        if (c0 >= co_left) continue;
+      auto process_chunk = [&](const uint32_t (&v)[16], const int c0) {
+        if (c0 >= co_left) return;
         float f[16];
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(v[jj]);
+        const bool full16 = (c0 + 16 <= co_left) && ((p.Co & 3) == 0);     // whole chunk real + 16-byte aligned rows
         if (cbias) {
+          if (full16) {
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) if (c0 + jj < co_left) f[jj] += cbias[c0 + jj];
+            for (int jj = 0; jj < 16; jj += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(cbias + c0 + jj));
+              f[jj] += b.x; f[jj + 1] += b.y; f[jj + 2] += b.z; f[jj + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) if (c0 + jj < co_left) f[jj] += cbias[c0 + jj];
+          }
         }
         if (pbias) {
+          if (full16) {
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) if (c0 + jj < co_left) f[jj] += pbias[c0 + jj];
+            for (int jj = 0; jj < 16; jj += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(pbias + c0 + jj));
+              f[jj] += b.x; f[jj + 1] += b.y; f[jj + 2] += b.z; f[jj + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) if (c0 + jj < co_left) f[jj] += pbias[c0 + jj];
+          }
         }
         if (smap) {
 #pragma unroll
@@ -238,11 +253,15 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             for (int jj = 0; jj < 16; ++jj) { const float x = valid ? f[jj] : 0.f; rb1[jj] += x; rb2[jj] += x * x; }
           }
         } else if (p.stats) {
+          // wide layers: 16 channel sums and 16 sums of squares over the warp's 32 pixels with 2 x 16 shuffles
+          // (round 1: 2 x 16 x 5 - the epilogue, not the MMA stream, paced the 64..256-channel layers)
+          float x1[16], x2[16];
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float x = valid ? f[jj] : 0.f;
-            const float s1 = warp_sum32(x), s2 = warp_sum32(x * x);
-            if (lane == 0) { atomicAdd(&s_stats[0][c0 + jj], s1); atomicAdd(&s_stats[1][c0 + jj], s2); }
+          for (int jj = 0; jj < 16; ++jj) { x1[jj] = valid ? f[jj] : 0.f; x2[jj] = x1[jj] * x1[jj]; }
+          const float s1 = warp_reduce16(x1, lane), s2 = warp_reduce16(x2, lane);
+          if ((lane & 1) == 0) {
+            const int ch = c0 + ((lane >> 1) & 15);
+            atomicAdd(&s_stats[0][ch], s1); atomicAdd(&s_stats[1][ch], s2);
           }
         }
         if (valid) {
@@ -283,7 +302,19 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             *reinterpret_cast<uint4*>(dst + 8) = o1;
           }
         }
-        __syncwarp();
+      };
+      // two accumulator chunks in flight: the tcgen05.ld of chunk c + 1 overlaps the arithmetic / stores of chunk c
+      {
+        uint32_t cur[16], nxt[16];
+        tmem_ld16_nowait(t_acc, nxt);
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+          tmem_ld_wait16(nxt);
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) cur[jj] = nxt[jj];
+          if (c0 + 16 < p.BN) tmem_ld16_nowait(t_acc + (uint32_t)(c0 + 16), nxt);
+          process_chunk(cur, c0);
+          __syncwarp();
+        }
       }
       // this warp has finished reading the accumulator: hand it back to the MMA issuer
       tc_fence_before();
