@@ -138,15 +138,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
-// n / d and n % d through the launcher-made multiplier (conv_engine.h::make_fastdiv)
-__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
-  return f.d == 1u ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
-}
-__device__ __forceinline__ void fdivmod(int n, const FastDiv& f, int& q, int& r) {
-  q = fdiv(n, f);
-  r = n - q * (int)f.d;
-}
-
 __device__ __forceinline__ float warp_sum32(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -19,6 +19,17 @@ inline FastDiv make_fastdiv(int d) {
   return f;
 }
 
+#ifdef __CUDACC__
+// n / d and n % d through the launcher-made multiplier (conv_engine.h::make_fastdiv)
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return f.d == 1u ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+__device__ __forceinline__ void fdivmod(int n, const FastDiv& f, int& q, int& r) {
+  q = fdiv(n, f);
+  r = n - q * (int)f.d;
+}
+#endif
+
 struct ConvParams {
   // logical GEMM pixel grid (per image) and its 128-pixel tiling
   int N, Hg, Wg, TH, TW, tiles_x, tiles_y;

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "act_types.cuh"
+#include "conv_engine.h"
 #include "ll_exchange.cuh"
 #include "kernels.h"
 
@@ -166,10 +167,11 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
 // v1 issue bound at 0.23 of HBM peak), and the second sum is accumulated as sum(g * y); every thread converts its
 // partial to sum(g * xhat) = invstd * (sum(g*y) - mean * sum(g)) once, before the block reduction.
 template <typename T>
-__global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_v2_kernel(
+__global__ void __launch_bounds__(256, 2) bn_act_bwd_reduce_v2_kernel(
     const T* __restrict__ dapad, const T* __restrict__ y, const float* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ g_out,
-    float* __restrict__ sums, int N, int H, int W, int C, int pad_mode, float inv_count, float eps) {
+    float* __restrict__ sums, int N, int H, int W, int C, int pad_mode, float inv_count, float eps,
+    const FastDiv fd_w, const FastDiv fd_h) {
   extern __shared__ float s_mem[];     // [2][C] block partial sums
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_mem[i] = 0.f;
   __syncthreads();
@@ -191,41 +193,53 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_v2_kernel(
     acc1[j] = acc2[j] = 0.f;
   }
   const int lo = pad_mode == 0 ? 1 : 0;
+  // element i -> (image, row, column) by multiply-high (no integer divides), folded border gradient + activation input
+  auto load = [&](unsigned i, V8& d, V8& yv, size_t& o) {
+    int pix = (int)(i >> cg_shift), x, yy, n, t;
+    fdivmod(pix, fd_w, t, x);
+    fdivmod(t, fd_h, n, yy);
+    const T* base = dapad + ((size_t)n * Hp * Wp) * C + c0;
+    d = ld8(base + ((size_t)(yy + 1) * Wp + (x + 1)) * C);
+    o = (((size_t)n * H + yy) * W + x) * C + c0;
+    yv = ld8(y + o);
+    const bool top = (yy == lo), bot = (yy == H - 1 - lo), lef = (x == lo), rig = (x == W - 1 - lo);
+    if (top | bot | lef | rig) {
+      int ry[3], rx[3], ny = 1, nx = 1;
+      ry[0] = yy + 1; rx[0] = x + 1;
+      if (top) ry[ny++] = 0;
+      if (bot) ry[ny++] = H + 1;
+      if (lef) rx[nx++] = 0;
+      if (rig) rx[nx++] = W + 1;
+      for (int p = 0; p < ny; ++p)
+        for (int q = 0; q < nx; ++q) {
+          if (p == 0 && q == 0) continue;
+          const V8 tt = ld8(base + ((size_t)ry[p] * Wp + rx[q]) * C);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d.f[j] += tt.f[j];
+        }
+    }
+  };
+  auto finish = [&](const V8& d, const V8& yv, size_t o) {
+    V8 g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float u = fmaf(yv.f[j], a[j], b[j]);
+      g.f[j] = d.f[j] * (u > 0.f ? 1.f : __expf(u));
+      acc1[j] += g.f[j];
+      acc2[j] = fmaf(g.f[j], yv.f[j], acc2[j]);
+    }
+    st8(g_out + o, g);
+  };
   if (i0 < stride) {
-    for (unsigned i = i0; i < total; i += stride) {
-      unsigned pix = i >> cg_shift;
-      const int x = (int)(pix % (unsigned)W); pix /= (unsigned)W;
-      const int yy = (int)(pix % (unsigned)H);
-      const int n = (int)(pix / (unsigned)H);
-      const T* base = dapad + ((size_t)n * Hp * Wp) * C + c0;
-      V8 d = ld8(base + ((size_t)(yy + 1) * Wp + (x + 1)) * C);
-      const bool top = (yy == lo), bot = (yy == H - 1 - lo), lef = (x == lo), rig = (x == W - 1 - lo);
-      if (top | bot | lef | rig) {
-        int ry[3], rx[3], ny = 1, nx = 1;
-        ry[0] = yy + 1; rx[0] = x + 1;
-        if (top) ry[ny++] = 0;
-        if (bot) ry[ny++] = H + 1;
-        if (lef) rx[nx++] = 0;
-        if (rig) rx[nx++] = W + 1;
-        for (int p = 0; p < ny; ++p)
-          for (int q = 0; q < nx; ++q) {
-            if (p == 0 && q == 0) continue;
-            const V8 t = ld8(base + ((size_t)ry[p] * Wp + rx[q]) * C);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) d.f[j] += t.f[j];
-          }
-      }
-      const size_t o = (((size_t)n * H + yy) * W + x) * C + c0;
-      const V8 yv = ld8(y + o);
-      V8 g;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float u = fmaf(yv.f[j], a[j], b[j]);
-        g.f[j] = d.f[j] * (u > 0.f ? 1.f : __expf(u));
-        acc1[j] += g.f[j];
-        acc2[j] = fmaf(g.f[j], yv.f[j], acc2[j]);
-      }
-      st8(g_out + o, g);
+    // two elements per trip: four independent 32-byte loads in flight per thread
+    for (unsigned i = i0; i < total; i += 2 * stride) {
+      V8 d0, y0, d1, y1;
+      size_t o0, o1 = 0;
+      const bool two = i + stride < total;
+      load(i, d0, y0, o0);
+      if (two) load(i + stride, d1, y1, o1);
+      finish(d0, y0, o0);
+      if (two) finish(d1, y1, o1);
     }
   }
 #pragma unroll
@@ -378,7 +392,8 @@ void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* sta
   static const bool v1 = getenv("MINE_B200_BN_REDUCE") && getenv("MINE_B200_BN_REDUCE")[0] == 'o';   // "old"
   if (!v1) {
     MINE_DISPATCH_ES(es, T, (bn_act_bwd_reduce_v2_kernel<T><<<blocks, 256, 2 * C * sizeof(float), stream>>>(
-        (const T*)dapad, (const T*)y, stats, gamma, beta, (T*)g_out, sums, N, H, W, C, pad_mode, inv_count, eps)));
+        (const T*)dapad, (const T*)y, stats, gamma, beta, (T*)g_out, sums, N, H, W, C, pad_mode, inv_count, eps,
+        make_fastdiv(W), make_fastdiv(H))));
     return;
   }
   // the grid-stride must be a multiple of the channel-group count so every thread keeps its channels
