@@ -374,17 +374,8 @@ class PlaneConvBNAct(torch.autograd.Function):
         xpad, w, y, stats, g32, b32 = ctx.saved_tensors
         up, planes, pad_out, count, reducer, has_cb, has_pb, has_sm = ctx.cfg
         dapad = dapad.contiguous()
-        g, sums = ext().bn_act_bwd_reduce(dapad, y, stats, g32, b32, pad_out, count, BN_EPS)
-        dgamma, dbeta = sums[1], sums[0]     # the LOCAL sums are the parameter gradients
-        fx = fused_exchange(reducer, sums.numel())
-        if fx is not None:               # cross-replica SUM of the two reductions inside the apply kernel
-            dy, dshared, dpb = ext().bn_bwd_apply_x(g, y, stats, g32, sums, planes, has_sm, has_pb, count, BN_EPS, *fx)
-        else:
-            if reducer is not None:      # separate all-reduce launch (in place: keep the local values first)
-                dgamma, dbeta = sums[1].clone(), sums[0].clone()
-                sums = reducer(sums.reshape(-1)).reshape(2, -1).contiguous()
-            dy, dshared, dpb = ext().bn_bwd_apply(g, y, stats, g32, sums, planes, has_sm, has_pb, count, BN_EPS)
-        _count(2)
+        dy, dshared, dpb, dgamma, dbeta = bn_act_backward(dapad, y, stats, g32, b32, pad_out, count, reducer, planes,
+                                                          has_sm, has_pb)
         dcb = None
         if has_cb:
             # a bias in front of BatchNorm has an exactly-zero gradient (dy of a BatchNorm sums to zero over the batch);
@@ -397,6 +388,38 @@ class PlaneConvBNAct(torch.autograd.Function):
             dx = (dgrad_up_raw if up else dgrad_same_raw)(dy, w)
         return (dx, dw, dcb, dpb if has_pb else None, dshared if has_sm else None, dgamma.to(g32.dtype),
                 dbeta.to(b32.dtype), None, None, None, None, None)
+
+
+def bn_act_backward(dapad, y, stats, g32, b32, pad_out, count, reducer, planes, has_sm, has_pb):
+    """Backward of ``pad(ELU(BN(y)))``: two kernels.  ``bn_act_bwd_reduce`` folds the pad adjoint, applies ELU', writes g
+    and reduces ``[sum g, sum g * xhat]``; ``bn_bwd_apply`` writes dy (+ shared-map / plane-bias gradients), with the
+    cross-replica SUM of the two reductions in its prologue when data parallel.  ``MINE_B200_BN_BWD=fused`` never writes g
+    (``bn_act_bwd_sums`` + ``bn_bwd_apply_fused`` recompute it from the padded gradient): one tensor less through HBM,
+    but measured SLOWER on B200 (level 0, tf32: 0.173 + 0.271 ms vs 0.218 + 0.189 ms - the halo-addressed read and the
+    second exp() cost more than the saved write + read), so it stays opt-in.
+    Returns ``(dy, dshared, dplane_bias, dgamma, dbeta)``."""
+    fused_g = os.environ.get("MINE_B200_BN_BWD", "split") == "fused"
+    if fused_g:
+        g, sums = None, ext().bn_act_bwd_sums(dapad, y, stats, g32, b32, pad_out, count, BN_EPS)
+    else:
+        g, sums = ext().bn_act_bwd_reduce(dapad, y, stats, g32, b32, pad_out, count, BN_EPS)
+    dgamma, dbeta = sums[1], sums[0]     # the LOCAL sums are the parameter gradients
+    fx = fused_exchange(reducer, sums.numel())
+    if fx is None and reducer is not None:   # separate all-reduce launch (in place: keep the local values first)
+        dgamma, dbeta = sums[1].clone(), sums[0].clone()
+        sums = reducer(sums.reshape(-1)).reshape(2, -1).contiguous()
+    if fused_g:
+        if fx is not None:
+            out = ext().bn_bwd_apply_fused_x(dapad, y, stats, g32, b32, sums, planes, has_sm, has_pb, count, BN_EPS,
+                                             pad_out, *fx)
+        else:
+            out = ext().bn_bwd_apply_fused(dapad, y, stats, g32, b32, sums, planes, has_sm, has_pb, count, BN_EPS, pad_out)
+    elif fx is not None:                 # cross-replica SUM of the two reductions inside the apply kernel
+        out = ext().bn_bwd_apply_x(g, y, stats, g32, sums, planes, has_sm, has_pb, count, BN_EPS, *fx)
+    else:
+        out = ext().bn_bwd_apply(g, y, stats, g32, sums, planes, has_sm, has_pb, count, BN_EPS)
+    _count(2)
+    return out[0], out[1], out[2], dgamma, dbeta
 
 
 class BNActPad(torch.autograd.Function):
@@ -437,17 +460,8 @@ class BNActPad(torch.autograd.Function):
     def backward(ctx, dapad):
         y, stats, g32, b32 = ctx.saved_tensors
         pad_out, count, reducer = ctx.cfg
-        g, sums = ext().bn_act_bwd_reduce(dapad.contiguous(), y, stats, g32, b32, pad_out, count, BN_EPS)
-        dgamma, dbeta = sums[1], sums[0]
-        fx = fused_exchange(reducer, sums.numel())
-        if fx is not None:
-            dy = ext().bn_bwd_apply_x(g, y, stats, g32, sums, 1, False, False, count, BN_EPS, *fx)[0]
-        else:
-            if reducer is not None:
-                dgamma, dbeta = sums[1].clone(), sums[0].clone()
-                sums = reducer(sums.reshape(-1)).reshape(2, -1).contiguous()
-            dy = ext().bn_bwd_apply(g, y, stats, g32, sums, 1, False, False, count, BN_EPS)[0]
-        _count(2)
+        dy, _, _, dgamma, dbeta = bn_act_backward(dapad.contiguous(), y, stats, g32, b32, pad_out, count, reducer, 1,
+                                                  False, False)
         return dy, dgamma.to(g32.dtype), dbeta.to(b32.dtype), None, None, None
 
 

@@ -231,31 +231,51 @@ at::Tensor bn_act_pad_fwd(const at::Tensor& y, const at::Tensor& stats, const at
   return bn_act_pad_fwd_x(y, stats, gamma, beta, pad_mode, count, eps, {}, 0, 0, c10::nullopt, c10::nullopt)[0];
 }
 
-std::vector<at::Tensor> bn_act_bwd_reduce(const at::Tensor& dapad, const at::Tensor& y, const at::Tensor& stats,
-                                          const at::Tensor& gamma, const at::Tensor& beta, int64_t pad_mode, double count,
-                                          double eps) {
+static std::vector<at::Tensor> bn_act_bwd_reduce_impl(const at::Tensor& dapad, const at::Tensor& y, const at::Tensor& stats,
+                                                      const at::Tensor& gamma, const at::Tensor& beta, int64_t pad_mode,
+                                                      double count, double eps, bool want_g) {
   check_act_nhwc(dapad, "dapad"); check_act_nhwc(y, "y"); check_same_type(dapad, y, "bn_act_bwd_reduce");
   c10::cuda::CUDAGuard guard(y.device());
   const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
-  TORCH_CHECK(dapad.size(1) == H + 2 && dapad.size(2) == W + 2 && dapad.size(3) == C, "dapad shape");
+  TORCH_CHECK(dapad.size(0) == N && dapad.size(1) == H + 2 && dapad.size(2) == W + 2 && dapad.size(3) == C, "dapad shape");
   TORCH_CHECK((C & (C - 1)) == 0 && C >= 16, "channels must be a power of two >= 16");
   TORCH_CHECK((int64_t)N * (H + 2) * (W + 2) * (C / 8) < (1ll << 31), "tensor too large for 32-bit indexing");
-  at::Tensor g = at::empty_like(y);
+  at::Tensor g = want_g ? at::empty_like(y) : at::Tensor();
   at::Tensor sums = at::zeros({2, C}, stats.options());
   mine::launch_bn_act_bwd_reduce(dapad.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(),
-                                 beta.data_ptr<float>(), g.data_ptr(), sums.data_ptr<float>(), N, H, W, C, (int)pad_mode,
-                                 (float)(1.0 / count), (float)eps, esize(y), cur_stream());
+                                 beta.data_ptr<float>(), want_g ? g.data_ptr() : nullptr, sums.data_ptr<float>(), N, H, W,
+                                 C, (int)pad_mode, (float)(1.0 / count), (float)eps, esize(y), cur_stream());
   return {g, sums};
 }
 
-std::vector<at::Tensor> bn_bwd_apply_x(const at::Tensor& g, const at::Tensor& y, const at::Tensor& stats,
-                                       const at::Tensor& gamma, const at::Tensor& sums, int64_t planes_per_image,
-                                       bool want_shared, bool want_plane_bias, double count, double eps,
-                                       std::vector<int64_t> ll_ptrs, int64_t rank, int64_t cap,
-                                       const c10::optional<at::Tensor>& epoch, const c10::optional<at::Tensor>& ticket) {
+std::vector<at::Tensor> bn_act_bwd_reduce(const at::Tensor& dapad, const at::Tensor& y, const at::Tensor& stats,
+                                          const at::Tensor& gamma, const at::Tensor& beta, int64_t pad_mode, double count,
+                                          double eps) {
+  return bn_act_bwd_reduce_impl(dapad, y, stats, gamma, beta, pad_mode, count, eps, true);
+}
+
+// the two BatchNorm backward sums only (the activation-gradient tensor is not materialised: bn_bwd_apply_fused_x)
+at::Tensor bn_act_bwd_sums(const at::Tensor& dapad, const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma,
+                           const at::Tensor& beta, int64_t pad_mode, double count, double eps) {
+  return bn_act_bwd_reduce_impl(dapad, y, stats, gamma, beta, pad_mode, count, eps, false)[1];
+}
+
+static std::vector<at::Tensor> bn_bwd_apply_impl(const at::Tensor& g, const at::Tensor& y, const at::Tensor& stats,
+                                                 const at::Tensor& gamma, const at::Tensor& sums, int64_t planes_per_image,
+                                                 bool want_shared, bool want_plane_bias, double count, double eps,
+                                                 std::vector<int64_t> ll_ptrs, int64_t rank, int64_t cap,
+                                                 const c10::optional<at::Tensor>& epoch,
+                                                 const c10::optional<at::Tensor>& ticket, const at::Tensor* beta,
+                                                 int64_t pad_mode) {
   check_act_nhwc(g, "g"); check_act_nhwc(y, "y"); check_same_type(g, y, "bn_bwd_apply");
   c10::cuda::CUDAGuard guard(y.device());
   const int N = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
+  if (beta) {
+    TORCH_CHECK(g.size(0) == N && g.size(1) == H + 2 && g.size(2) == W + 2 && g.size(3) == C, "dapad shape");
+    TORCH_CHECK(beta->is_cuda() && beta->scalar_type() == at::kFloat && beta->numel() == C, "beta");
+  } else {
+    TORCH_CHECK(g.sizes() == y.sizes(), "g shape");
+  }
   const int S = planes_per_image, B = N / S;
   FusedX f = make_fused(ll_ptrs, rank, cap, epoch, ticket, 2 * C);
   at::Tensor dy = at::empty_like(y);
@@ -264,8 +284,18 @@ std::vector<at::Tensor> bn_bwd_apply_x(const at::Tensor& g, const at::Tensor& y,
   mine::launch_bn_bwd_apply(g.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(),
                             sums.data_ptr<float>(), dy.data_ptr(), want_shared ? dshared.data_ptr<float>() : nullptr,
                             want_plane_bias ? dpb.data_ptr<float>() : nullptr, B, S, H, W, C, (float)(1.0 / count),
-                            (float)eps, esize(y), f.on ? &f.x : nullptr, cur_stream());
+                            (float)eps, esize(y), f.on ? &f.x : nullptr, beta ? beta->data_ptr<float>() : nullptr,
+                            (int)pad_mode, cur_stream());
   return {dy, dshared, dpb};
+}
+
+std::vector<at::Tensor> bn_bwd_apply_x(const at::Tensor& g, const at::Tensor& y, const at::Tensor& stats,
+                                       const at::Tensor& gamma, const at::Tensor& sums, int64_t planes_per_image,
+                                       bool want_shared, bool want_plane_bias, double count, double eps,
+                                       std::vector<int64_t> ll_ptrs, int64_t rank, int64_t cap,
+                                       const c10::optional<at::Tensor>& epoch, const c10::optional<at::Tensor>& ticket) {
+  return bn_bwd_apply_impl(g, y, stats, gamma, sums, planes_per_image, want_shared, want_plane_bias, count, eps, ll_ptrs,
+                           rank, cap, epoch, ticket, nullptr, 0);
 }
 
 std::vector<at::Tensor> bn_bwd_apply(const at::Tensor& g, const at::Tensor& y, const at::Tensor& stats,
@@ -273,6 +303,25 @@ std::vector<at::Tensor> bn_bwd_apply(const at::Tensor& g, const at::Tensor& y, c
                                      bool want_shared, bool want_plane_bias, double count, double eps) {
   return bn_bwd_apply_x(g, y, stats, gamma, sums, planes_per_image, want_shared, want_plane_bias, count, eps, {}, 0, 0,
                         c10::nullopt, c10::nullopt);
+}
+
+// BatchNorm + ELU + pad backward straight from the PADDED upstream gradient (pad adjoint and ELU' recomputed in-kernel)
+std::vector<at::Tensor> bn_bwd_apply_fused_x(const at::Tensor& dapad, const at::Tensor& y, const at::Tensor& stats,
+                                             const at::Tensor& gamma, const at::Tensor& beta, const at::Tensor& sums,
+                                             int64_t planes_per_image, bool want_shared, bool want_plane_bias, double count,
+                                             double eps, int64_t pad_mode, std::vector<int64_t> ll_ptrs, int64_t rank,
+                                             int64_t cap, const c10::optional<at::Tensor>& epoch,
+                                             const c10::optional<at::Tensor>& ticket) {
+  return bn_bwd_apply_impl(dapad, y, stats, gamma, sums, planes_per_image, want_shared, want_plane_bias, count, eps, ll_ptrs,
+                           rank, cap, epoch, ticket, &beta, pad_mode);
+}
+
+std::vector<at::Tensor> bn_bwd_apply_fused(const at::Tensor& dapad, const at::Tensor& y, const at::Tensor& stats,
+                                           const at::Tensor& gamma, const at::Tensor& beta, const at::Tensor& sums,
+                                           int64_t planes_per_image, bool want_shared, bool want_plane_bias, double count,
+                                           double eps, int64_t pad_mode) {
+  return bn_bwd_apply_fused_x(dapad, y, stats, gamma, beta, sums, planes_per_image, want_shared, want_plane_bias, count, eps,
+                              pad_mode, {}, 0, 0, c10::nullopt, c10::nullopt);
 }
 
 std::vector<at::Tensor> head_bwd(const at::Tensor& g_mpi, const at::Tensor& mpi, const at::Tensor& sign, bool use_alpha) {
@@ -435,6 +484,9 @@ void register_conv(pybind11::module_& m) {
   m.def("bn_res_act_fwd_x", &bn_res_act_fwd_x);
   m.def("bn_act_bwd_reduce", &bn_act_bwd_reduce);
   m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("bn_act_bwd_sums", &bn_act_bwd_sums);
+  m.def("bn_bwd_apply_fused", &bn_bwd_apply_fused);
+  m.def("bn_bwd_apply_fused_x", &bn_bwd_apply_fused_x);
   m.def("head_bwd", &head_bwd);
   m.def("bn_res_act_fwd", &bn_res_act_fwd);
   m.def("bn_res_act_bwd_reduce", &bn_res_act_bwd_reduce);

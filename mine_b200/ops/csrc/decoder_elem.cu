@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256, 2) bn_act_bwd_reduce_v2_kernel(
       acc1[j] += g.f[j];
       acc2[j] = fmaf(g.f[j], yv.f[j], acc2[j]);
     }
-    st8(g_out + o, g);
+    if (g_out) st8(g_out + o, g);       // null: the apply kernel recomputes g from dapad (one tensor less written + read)
   };
   if (i0 < stride) {
     // two elements per trip: four independent 32-byte loads in flight per thread
@@ -242,25 +242,38 @@ __global__ void __launch_bounds__(256, 2) bn_act_bwd_reduce_v2_kernel(
       if (two) finish(d1, y1, o1);
     }
   }
+  // block reduction: lanes with equal (lane % cg) own the same channels (cg and the warp size are powers of two), so the
+  // warp is folded with shuffles first and only cg lanes per warp touch shared memory (4096 contended shared-memory
+  // atomics per block on 2C addresses cost a third of the kernel for the 16-channel layers)
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float m = stats[c0 + j] * inv_count;
     float var = stats[C + c0 + j] * inv_count - m * m;
     var = var < 0.f ? 0.f : var;
-    atomicAdd(&s_mem[c0 + j], acc1[j]);
-    atomicAdd(&s_mem[C + c0 + j], rsqrtf(var + eps) * (acc2[j] - m * acc1[j]));
+    float v1 = acc1[j], v2 = rsqrtf(var + eps) * (acc2[j] - m * acc1[j]);
+    for (int o2 = 16; o2 >= cg && o2 > 0; o2 >>= 1) {
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o2);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o2);
+    }
+    if (lane < cg || cg >= 32) {
+      atomicAdd(&s_mem[c0 + j], v1);
+      atomicAdd(&s_mem[C + c0 + j], v2);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], s_mem[i]);
 }
 
 // One thread = 8 channels of one pixel of one IMAGE; loops over its S planes.
-template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+// FUSED: ``g`` is the PADDED upstream gradient ``dapad``; the pad adjoint and ELU' are recomputed here (same arithmetic as
+// bn_act_bwd_reduce) instead of being written by the reduction kernel and read back.
+template <typename T, bool FUSED>
+__global__ void __launch_bounds__(256, FUSED ? 3 : 4) bn_bwd_apply_kernel(
     const T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ sums, T* __restrict__ dy,
     float* __restrict__ dshared, float* __restrict__ dplane_bias, int B, int S, int H, int W, int C, float inv_count,
-    float eps, const LLExchange x) {
+    float eps, const LLExchange x, const float* __restrict__ beta, int pad_mode) {
   extern __shared__ float s_pb[];      // [S][C] per-plane bias gradient partials (if wanted), then [2C] reduced sums
   const bool want_pb = dplane_bias != nullptr;
   if (x.world > 1) {                   // cross-GPU SUM of the two BatchNorm backward reductions, fused into this kernel
@@ -280,32 +293,66 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   const size_t ii = active ? i : 0;
   const int c0 = (int)(ii % cg) * 8;
   const size_t pix = ii / cg;
-  float mean[8], invstd[8], coef[8], mg[8], mgx[8];
+  // dy = coef * (g - mean_g - xhat * mean_gx)  with xhat = (y - mean) * invstd, folded into  coef * g + k1 * y + k0
+  float coef[8], k1[8], k0[8], bb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float m = stats[c0 + j] * inv_count;
     float var = stats[C + c0 + j] * inv_count - m * m;
     var = var < 0.f ? 0.f : var;
-    mean[j] = m; invstd[j] = rsqrtf(var + eps);
-    coef[j] = gamma[c0 + j] * invstd[j];
-    mg[j] = sums[c0 + j] * inv_count;
-    mgx[j] = sums[C + c0 + j] * inv_count;
+    const float invstd = rsqrtf(var + eps);
+    coef[j] = gamma[c0 + j] * invstd;
+    const float mg = sums[c0 + j] * inv_count, mgx = sums[C + c0 + j] * inv_count;
+    k1[j] = -coef[j] * mgx * invstd;
+    k0[j] = -coef[j] * mg - k1[j] * m;
+    bb[j] = FUSED ? beta[c0 + j] - m * coef[j] : 0.f;     // BN(y) = coef * y + bb
   }
   float ds[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) ds[j] = 0.f;
   const int lane = threadIdx.x & 31;
+  // FUSED: pixel coordinates inside the padded gradient and which border rows / columns fold onto this pixel
+  const int Hp = H + 2, Wp = W + 2;
+  const int py = (int)(pix / (size_t)W), px = (int)(pix - (size_t)py * W);
+  const int lo = pad_mode == 0 ? 1 : 0;
+  const bool top = (py == lo), bot = (py == H - 1 - lo), lef = (px == lo), rig = (px == W - 1 - lo);
   for (int s = 0; s < S; ++s) {
     V8 d;
 #pragma unroll
     for (int j = 0; j < 8; ++j) d.f[j] = 0.f;
     if (active) {
       const size_t o = (((size_t)(b * S + s) * H * W) + pix) * C + c0;
-      const V8 gv = ld8(g + o), yv = ld8(y + o);
+      const V8 yv = ld8(y + o);
+      V8 gv;
+      if (FUSED) {
+        const T* base = g + ((size_t)(b * S + s) * Hp * Wp) * C + c0;
+        gv = ld8(base + ((size_t)(py + 1) * Wp + (px + 1)) * C);
+        if (top | bot | lef | rig) {
+          int ry[3], rx[3], ny = 1, nx = 1;
+          ry[0] = py + 1; rx[0] = px + 1;
+          if (top) ry[ny++] = 0;
+          if (bot) ry[ny++] = H + 1;
+          if (lef) rx[nx++] = 0;
+          if (rig) rx[nx++] = W + 1;
+          for (int p = 0; p < ny; ++p)
+            for (int q = 0; q < nx; ++q) {
+              if (p == 0 && q == 0) continue;
+              const V8 tt = ld8(base + ((size_t)ry[p] * Wp + rx[q]) * C);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gv.f[j] += tt.f[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float u = fmaf(yv.f[j], coef[j], bb[j]);
+          gv.f[j] *= (u > 0.f ? 1.f : __expf(u));
+        }
+      } else {
+        gv = ld8(g + o);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xhat = (yv.f[j] - mean[j]) * invstd[j];
-        d.f[j] = coef[j] * (gv.f[j] - mg[j] - xhat * mgx[j]);
+        d.f[j] = fmaf(coef[j], gv.f[j], fmaf(k1[j], yv.f[j], k0[j]));
         ds[j] += d.f[j];
       }
       st8_op(dy + o, d);
@@ -403,7 +450,9 @@ void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* sta
 
 void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const float* gamma, const float* sums,
                          void* dy, float* dshared, float* dplane_bias, int B, int S, int H, int W, int C,
-                         float inv_count, float eps, int es, const LLExchange* x, cudaStream_t stream) {
+                         float inv_count, float eps, int es, const LLExchange* x, const float* beta, int pad_mode,
+                         cudaStream_t stream) {
+  // beta != null: ``g`` is the padded upstream gradient [B*S, H+2, W+2, C] (fused pad adjoint + ELU')
   const size_t per_img = (size_t)H * W * (C / 8);
   dim3 grid((unsigned)((per_img + 255) / 256), B);
   LLExchange xx{};
@@ -411,12 +460,21 @@ void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const
   const size_t smem = (dplane_bias ? (size_t)S * C * sizeof(float) : 0) + (xx.world > 1 ? 2 * (size_t)C * sizeof(float) : 0);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(bn_bwd_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-    cudaFuncSetAttribute(bn_bwd_apply_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(bn_bwd_apply_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     attr = true;
   }
-  MINE_DISPATCH_ES(es, T, (bn_bwd_apply_kernel<T><<<grid, 256, smem, stream>>>(
-      (const T*)g, (const T*)y, stats, gamma, sums, (T*)dy, dshared, dplane_bias, B, S, H, W, C, inv_count, eps, xx)));
+  if (beta) {
+    MINE_DISPATCH_ES(es, T, (bn_bwd_apply_kernel<T, true><<<grid, 256, smem, stream>>>(
+        (const T*)g, (const T*)y, stats, gamma, sums, (T*)dy, dshared, dplane_bias, B, S, H, W, C, inv_count, eps, xx,
+        beta, pad_mode)));
+  } else {
+    MINE_DISPATCH_ES(es, T, (bn_bwd_apply_kernel<T, false><<<grid, 256, smem, stream>>>(
+        (const T*)g, (const T*)y, stats, gamma, sums, (T*)dy, dshared, dplane_bias, B, S, H, W, C, inv_count, eps, xx,
+        nullptr, 0)));
+  }
 }
 
 void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, void* dz, float* dbias, size_t npix,

@@ -78,9 +78,17 @@ __global__ void __launch_bounds__(256) bn_res_act_fwd_kernel(
 // publishes acc1/acc2 (8 channels starting at c0) through a [2][C] shared buffer
 __device__ __forceinline__ void publish_sums(float* s_sum, float* __restrict__ sums, int C, int c0, bool active,
                                              const float* acc1, const float* acc2) {
-  if (active) {
+  // lanes with equal (lane % cg) own the same channels: fold the warp with shuffles first (narrow layers), then one
+  // shared-memory atomic per channel and warp instead of one per thread
+  const int cg = C >> 3, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[c0 + j], acc1[j]); atomicAdd(&s_sum[C + c0 + j], acc2[j]); }
+  for (int j = 0; j < 8; ++j) {
+    float v1 = active ? acc1[j] : 0.f, v2 = active ? acc2[j] : 0.f;
+    for (int o2 = 16; o2 >= cg && o2 > 0; o2 >>= 1) {
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o2);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o2);
+    }
+    if (active && (lane < cg || cg >= 32)) { atomicAdd(&s_sum[c0 + j], v1); atomicAdd(&s_sum[C + c0 + j], v2); }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {

@@ -62,7 +62,8 @@ void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* sta
                               float inv_count, float eps, int es, cudaStream_t stream);
 void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const float* gamma, const float* sums,
                          void* dy, float* dshared, float* dplane_bias, int B, int S, int H, int W, int C,
-                         float inv_count, float eps, int es, const LLExchange* x, cudaStream_t stream);
+                         float inv_count, float eps, int es, const LLExchange* x, const float* beta, int pad_mode,
+                         cudaStream_t stream);
 void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, void* dz, float* dbias, size_t npix,
                      int use_alpha, int es, cudaStream_t stream);
 }  // namespace mine

@@ -156,8 +156,8 @@ def bn_act_pad_fwd(y, stats, gamma, beta, pad_mode, count, eps):
     return _round_op(u[:, sy][:, :, sx].to(y.dtype).contiguous())
 
 
-def bn_act_bwd_reduce(dapad, y, stats, gamma, beta, pad_mode, count, eps):
-    """Adjoint of the pad, times ELU', plus the two BatchNorm backward sums ``[sum g, sum g*xhat]``."""
+def _bn_act_g(dapad, y, stats, gamma, beta, pad_mode, count, eps):
+    """fp32 gradient w.r.t. the BatchNorm output: adjoint of the pad times ELU' (shared by the two forms below)."""
     n, h, w, c = y.shape
     mean, invstd, a, b = _bn_coef(stats.float(), gamma.float(), beta.float(), count, eps)
     sy, sx = _pad_src(h, pad_mode, y.device), _pad_src(w, pad_mode, y.device)
@@ -168,8 +168,25 @@ def bn_act_bwd_reduce(dapad, y, stats, gamma, beta, pad_mode, count, eps):
     u = yf * a + b
     g = d * torch.where(u > 0, torch.ones_like(u), torch.exp(u))
     xhat = (yf - mean) * invstd
-    sums = torch.stack([g.sum(dim=(0, 1, 2)), (g * xhat).sum(dim=(0, 1, 2))])
+    return g, torch.stack([g.sum(dim=(0, 1, 2)), (g * xhat).sum(dim=(0, 1, 2))])
+
+
+def bn_act_bwd_reduce(dapad, y, stats, gamma, beta, pad_mode, count, eps):
+    """Adjoint of the pad, times ELU', plus the two BatchNorm backward sums ``[sum g, sum g*xhat]``."""
+    g, sums = _bn_act_g(dapad, y, stats, gamma, beta, pad_mode, count, eps)
     return [g.to(y.dtype), sums]
+
+
+def bn_act_bwd_sums(dapad, y, stats, gamma, beta, pad_mode, count, eps):
+    """The two sums of :func:`bn_act_bwd_reduce` without materialising ``g`` (default backward path)."""
+    return _bn_act_g(dapad, y, stats, gamma, beta, pad_mode, count, eps)[1]
+
+
+def bn_bwd_apply_fused(dapad, y, stats, gamma, beta, sums, planes_per_image, want_shared, want_plane_bias, count, eps,
+                       pad_mode):
+    """:func:`bn_bwd_apply` with ``g`` recomputed from the padded upstream gradient (kept in fp32: never stored)."""
+    g = _bn_act_g(dapad, y, stats, gamma, beta, pad_mode, count, eps)[0]
+    return bn_bwd_apply(g, y, stats, gamma, sums, planes_per_image, want_shared, want_plane_bias, count, eps)
 
 
 def bn_bwd_apply(g, y, stats, gamma, sums, planes_per_image, want_shared, want_plane_bias, count, eps):

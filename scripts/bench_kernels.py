@@ -89,6 +89,10 @@ if want("bn_act_pad_fwd"):
     report("bn_act_bwd_reduce", timeit(lambda: E.ext().bn_act_bwd_reduce(dap, y, st, g, b, 0, cnt, 1e-5)), y.numel() * 3 * ES, 0)
     gg, sums = E.ext().bn_act_bwd_reduce(dap, y, st, g, b, 0, cnt, 1e-5)
     report("bn_bwd_apply", timeit(lambda: E.ext().bn_bwd_apply(gg, y, st, g, sums, 32, False, False, cnt, 1e-5)), y.numel() * 3 * ES, 0)
+    # default backward pair: sums only (2 tensors read) + apply from the padded gradient (2 read, 1 written)
+    report("bn_act_bwd_sums", timeit(lambda: E.ext().bn_act_bwd_sums(dap, y, st, g, b, 0, cnt, 1e-5)), y.numel() * 2 * ES, 0)
+    report("bn_bwd_apply_fused", timeit(lambda: E.ext().bn_bwd_apply_fused(dap, y, st, g, b, sums, 32, False, False, cnt, 1e-5, 0)),
+           y.numel() * 3 * ES, 0)
 # render
 if want("render"):
     from mine_b200 import geometry as geo

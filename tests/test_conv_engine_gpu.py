@@ -164,6 +164,13 @@ def test_bn_act_pad_fwd_bwd(pad_mode, n, h, w, c):
     ref_dsh = yr.grad.reshape(2, n // 2, c, h, w).sum(1).permute(0, 2, 3, 1)
     assert _rel(dsh, ref_dsh) < _tol(2e-2, 1e-3)
     assert _rel(dpb, yr.grad.sum(dim=(2, 3))) < _tol(2e-2, 1e-3)
+    # default backward form: the activation gradient is never materialised (sums only + apply from the padded gradient)
+    sums2 = ext.bn_act_bwd_sums(_act(dap), _act(y), stats, gamma, beta, pad_mode, count, 1e-5)
+    assert _rel(sums2, sums) < 1e-5
+    dy2, dsh2, dpb2 = ext.bn_bwd_apply_fused(_act(dap), _act(y), stats, gamma, beta, sums, n // 2, True, True, count, 1e-5,
+                                             pad_mode)
+    assert _rel(_nchw(dy2), yr.grad) < _tol(2e-2, 1e-3)
+    assert _rel(dy2, dy) < _tol(1e-2, 1e-5) and _rel(dsh2, dsh) < _tol(1e-2, 1e-5) and _rel(dpb2, dpb) < _tol(1e-2, 1e-4)
 
 
 def test_fused_layer_and_head_autograd():
