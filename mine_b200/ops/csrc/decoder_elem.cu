@@ -54,7 +54,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_act_pad_fwd_kernel(
     const T* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, T* __restrict__ out, int N, int H, int W, int C, int pad_mode,
-    float inv_count, float eps, const LLExchange x, float* __restrict__ red_out) {
+    float inv_count, float eps, const LLExchange x, float* __restrict__ red_out, const FastDiv fd_wp,
+    const FastDiv fd_hp) {
   extern __shared__ float s_red[];               // [2C] cross-GPU reduced statistics (only when x.world > 1)
   if (x.world > 1) { ll_exchange_sum(stats, s_red, 2 * C, x, red_out); stats = s_red; }
   const int cg = C >> 3;                         // power of two (C in {16,...,256})
@@ -67,10 +68,9 @@ __global__ void __launch_bounds__(256) bn_act_pad_fwd_kernel(
   const int c0 = (int)(i0 & (cg - 1)) * 8;
   const BnCoef k = bn_coef(stats, gamma, beta, C, c0, inv_count, eps);
   for (unsigned i = i0; i < total; i += stride) {
-    unsigned pix = i >> cg_shift;
-    const int px = (int)(pix % (unsigned)Wp); pix /= (unsigned)Wp;
-    const int py = (int)(pix % (unsigned)Hp);
-    const int n = (int)(pix / (unsigned)Hp);
+    int px, py, n, t;                              // multiply-high decomposition (conv_engine.h::FastDiv)
+    fdivmod((int)(i >> cg_shift), fd_wp, t, px);
+    fdivmod(t, fd_hp, n, py);
     const int sy = pad_src(py, H, pad_mode), sx = pad_src(px, W, pad_mode);
     V8 v = ld8(y + (((size_t)n * H + sy) * W + sx) * C + c0);
 #pragma unroll
@@ -428,7 +428,8 @@ void launch_bn_act_pad_fwd(const void* y, const float* stats, const float* gamma
   if (x) xx = *x;
   const size_t smem = xx.world > 1 ? 2 * (size_t)C * sizeof(float) : 0;
   MINE_DISPATCH_ES(es, T, (bn_act_pad_fwd_kernel<T><<<grid_for(total, 148 * 32), 256, smem, stream>>>(
-      (const T*)y, stats, gamma, beta, (T*)out, N, H, W, C, pad_mode, inv_count, eps, xx, red_out)));
+      (const T*)y, stats, gamma, beta, (T*)out, N, H, W, C, pad_mode, inv_count, eps, xx, red_out, make_fastdiv(W + 2),
+      make_fastdiv(H + 2))));
 }
 
 void launch_bn_act_bwd_reduce(const void* dapad, const void* y, const float* stats, const float* gamma,
