@@ -260,17 +260,82 @@ def conv_up_raw(xpad_lo, w, chan_bias=None, plane_bias=None, shared_map=None, pl
     return out
 
 
-def dgrad_same_raw(dy, w):
-    """Gradient w.r.t. the PADDED input of :func:`conv_same_raw`: ``dy [N,H,W,Co]`` -> ``[N,H+2,W+2,Ci]``."""
+def dgrad_same_raw(dy, w, accumulate_into=None):
+    """Gradient w.r.t. the PADDED input of :func:`conv_same_raw`: ``dy [N,H,W,Co]`` -> ``[N,H+2,W+2,Ci]``
+    (``accumulate_into``: add it onto an existing gradient of that shape inside the kernel epilogue)."""
     n, h, w_, co = dy.shape
     ci = w.shape[1]
     pack_ = pack(w, 2)                                                            # [tap][Ci][Co]
-    out = torch.empty((n, h + 2, w_ + 2, ci), dtype=ACT_DTYPE, device=dy.device)
+    acc = accumulate_into is not None
+    out = accumulate_into if acc else torch.empty((n, h + 2, w_ + 2, ci), dtype=ACT_DTYPE, device=dy.device)
     th, tw = pick_tile(h + 2, w_ + 2)
     ext().conv_taps(dy, pack_, out, h + 2, w_ + 2, 1, 9, [-k for k in SAME_TAPS_Y], [-k for k in SAME_TAPS_X], 1, ci,
-                    1, 1, [0], [0], False, None, None, None, 1, None, 0, False, None, th, tw)
+                    1, 1, [0], [0], acc, None, None, None, 1, None, 0, False, None, th, tw)
     _count()
     return out
+
+
+class SplitWeight(torch.autograd.Function):
+    """``w[:, :cp], w[:, cp:cp+cs], w[:, cp+cs:]`` (per-plane / shared-skip / embedding input channels of a factorised
+    decoder conv) with ONE gradient buffer: backward writes the three parts into an ``empty_like(w)`` (3 strided copies).
+    Plain slicing costs three zero-filled full-size tensors, three slice copies and two adds per block, and the summed
+    gradient misses the parameter's channels-last layout (one more clone in AccumulateGrad)."""
+
+    @staticmethod
+    def forward(ctx, w, cp, cs):
+        ctx.set_materialize_grads(False)
+        ctx.split = (int(cp), int(cs))
+        ctx.like = w
+        return w[:, :cp], w[:, cp:cp + cs], w[:, cp + cs:]
+
+    @staticmethod
+    def backward(ctx, gp, gs, ge):
+        cp, cs = ctx.split
+        w = ctx.like
+        g = torch.empty_like(w)                    # preserves the (channels-last) strides of the parameter
+        for lo, hi, part in ((0, cp, gp), (cp, cp + cs, gs), (cp + cs, w.shape[1], ge)):
+            if hi > lo:
+                if part is None:
+                    g[:, lo:hi].zero_()
+                else:
+                    g[:, lo:hi].copy_(part)
+        return g, None, None
+
+
+def split_block_weights(blk):
+    """The three input-channel groups of a decoder block's conv weight (see :class:`SplitWeight`)."""
+    w = blk.conv.conv.weight
+    if blk.c_shared == 0 and blk.c_emb == 0:
+        return w, w[:, :0], w[:, :0]
+    if not (w.requires_grad and torch.is_grad_enabled()) or os.environ.get("MINE_B200_SPLIT_WEIGHT", "1") != "1":
+        return blk.split_weights()
+    return SplitWeight.apply(w, blk.c_plane, blk.c_shared)
+
+
+class GradSlot:
+    """Meeting point of the gradients of an activation with TWO consumers (a decoder level feeds its MPI head and the next
+    level): the consumer whose backward runs first returns its data gradient to autograd and parks the tensor here; the
+    second one ADDS its gradient onto that tensor inside the dgrad kernel epilogue and returns ``None`` - no separate
+    ``add_`` pass over a [N, H+2, W+2, C] tensor (206 MB at level 1).  Both backward calls precede the producer's backward
+    (autograd dependency order), so the in-place update is seen by it."""
+
+    __slots__ = ("buf",)
+
+    def __init__(self):
+        self.buf = None
+
+    def deliver(self, dgrad_fn):
+        """``dgrad_fn(accumulate_into)`` -> gradient tensor; returns what the caller hands to autograd."""
+        if self.buf is None:
+            self.buf = dgrad_fn(None)
+            return self.buf
+        dgrad_fn(self.buf)
+        self.buf = None
+        return None
+
+
+def grad_slots_enabled() -> bool:
+    return os.environ.get("MINE_B200_GRAD_SLOT", "1") == "1"
 
 
 def dgrad_up_raw(dy, w):
@@ -336,7 +401,8 @@ class PlaneConvBNAct(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, xpad, w, chan_bias, plane_bias, shared_map, gamma, beta, up, planes, pad_out, bn, reducer):
+    def forward(ctx, xpad, w, chan_bias, plane_bias, shared_map, gamma, beta, up, planes, pad_out, bn, reducer,
+                slot=None):
         co = w.shape[0]
         training = bn is None or bn.training
         stats = torch.zeros((2, co), dtype=torch.float32, device=xpad.device) if training else None
@@ -367,6 +433,7 @@ class PlaneConvBNAct(torch.autograd.Function):
         ctx.save_for_backward(xpad, w, y, stats, g32, b32)
         ctx.cfg = (bool(up), int(planes), int(pad_out), count, reducer, chan_bias is not None, plane_bias is not None,
                    shared_map is not None)
+        ctx.slot = slot if not up else None      # input shared with another consumer (GradSlot): same-resolution convs only
         return apad
 
     @staticmethod
@@ -385,9 +452,12 @@ class PlaneConvBNAct(torch.autograd.Function):
         dw = (wgrad_up_raw if up else wgrad_same_raw)(dy, xpad).to(w.dtype)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = (dgrad_up_raw if up else dgrad_same_raw)(dy, w)
+            if ctx.slot is not None:
+                dx = ctx.slot.deliver(lambda acc: dgrad_same_raw(dy, w, accumulate_into=acc))
+            else:
+                dx = (dgrad_up_raw if up else dgrad_same_raw)(dy, w)
         return (dx, dw, dcb, dpb if has_pb else None, dshared if has_sm else None, dgamma.to(g32.dtype),
-                dbeta.to(b32.dtype), None, None, None, None, None)
+                dbeta.to(b32.dtype), None, None, None, None, None, None)
 
 
 def bn_act_backward(dapad, y, stats, g32, b32, pad_out, count, reducer, planes, has_sm, has_pb):
@@ -508,7 +578,7 @@ class HeadConv(torch.autograd.Function):
     """Packed fp32 MPI ``[N,H,W,4]`` = act(conv3x3(apad) + bias) with apad reflection padded."""
 
     @staticmethod
-    def forward(ctx, apad, w, bias, use_alpha):
+    def forward(ctx, apad, w, bias, use_alpha, slot=None):
         if head_mode() == "direct" and apad.shape[3] in (16, 32):
             # narrow full-resolution levels: bandwidth bound, CUDA-core kernel with one halo load (head_direct.cu)
             wpk = w.detach().float().permute(2, 3, 1, 0).contiguous()                 # [ky, kx, ci, co] = [9, C, 4]
@@ -519,6 +589,7 @@ class HeadConv(torch.autograd.Function):
                                       head_alpha=use_alpha)
         ctx.save_for_backward(apad, w, mpi, sign)
         ctx.use_alpha = bool(use_alpha)
+        ctx.slot = slot
         return mpi
 
     @staticmethod
@@ -528,8 +599,13 @@ class HeadConv(torch.autograd.Function):
         _count()
         w16 = F.pad(w.detach(), (0, 0, 0, 0, 0, 0, 0, 16 - w.shape[0]))           # Co 4 -> 16 (zero rows)
         dw = wgrad_same_raw(dz, apad)[: w.shape[0]].to(w.dtype)
-        dx = dgrad_same_raw(dz, w16) if ctx.needs_input_grad[0] else None
-        return dx, dw, dbias.to(w.dtype), None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if ctx.slot is not None:
+                dx = ctx.slot.deliver(lambda acc: dgrad_same_raw(dz, w16, accumulate_into=acc))
+            else:
+                dx = dgrad_same_raw(dz, w16)
+        return dx, dw, dbias.to(w.dtype), None, None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -623,7 +699,7 @@ class ConvEngine:
         use_alpha = bool(dec.use_alpha)
 
         def shared_and_bias(blk, feat):
-            wp, ws, we = blk.split_weights()
+            wp, ws, we = split_block_weights(blk)
             bias = blk.conv.conv.bias
             smap = None
             if feat is not None and own_convs:
@@ -651,12 +727,14 @@ class ConvEngine:
             xpad = pad_nhwc(to_operand(a), "replicate")                      # feeds the upsample conv
 
         outputs: Dict[int, torch.Tensor] = {}
+        slot = None                                  # set when the current ``xpad`` also fed an MPI head (two consumers)
         for i in range(4, -1, -1):
             if i < 4:
                 blk = dec.blocks[f"upconv_{i}_0"]
                 wp, _, cb, _ = shared_and_bias(blk, None)
                 xpad = PlaneConvBNAct.apply(xpad, wp, cb, None, None, blk.bn.weight, blk.bn.bias, False, s, 1,
-                                            blk.bn, reducer)
+                                            blk.bn, reducer, slot)
+            slot = None
             blk = dec.blocks[f"upconv_{i}_1"]
             feat = feats[i - 1] if (dec.use_skips and i > 0) else None
             wp, smap, cb, pbias = shared_and_bias(blk, feat)
@@ -664,6 +742,8 @@ class ConvEngine:
                                         blk.bn, reducer)
             if i in dec.scales:
                 head = dec.heads[f"dispconv_{i}"]
-                mpi = HeadConv.apply(xpad, head.conv.weight, head.conv.bias, use_alpha)
+                if i > 0 and grad_slots_enabled() and torch.is_grad_enabled() and xpad.requires_grad:
+                    slot = GradSlot()                # head_i and upconv_{i-1}_0 both read xpad: gradients meet in the kernel
+                mpi = HeadConv.apply(xpad, head.conv.weight, head.conv.bias, use_alpha, slot)
                 outputs[i] = mpi.reshape(b, s, *mpi.shape[1:])
         return [outputs[k] for k in range(4)]

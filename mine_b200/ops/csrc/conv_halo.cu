@@ -248,10 +248,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             } else if (p.out_fp32) {
               float* dst = reinterpret_cast<float*>(p.out) + out_pix * p.Co + cc_now;
 #pragma unroll
-              for (int jj = 0; jj < 16; jj += 4)
-                *reinterpret_cast<float4*>(dst + jj) = make_float4(fv[jj], fv[jj + 1], fv[jj + 2], fv[jj + 3]);
+              for (int jj = 0; jj < 16; jj += 4) {
+                float4 o = make_float4(fv[jj], fv[jj + 1], fv[jj + 2], fv[jj + 3]);
+                if (p.accumulate) {               // second gradient contribution lands on top of the first (no add kernel)
+                  const float4 e = *reinterpret_cast<const float4*>(dst + jj);
+                  o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+                }
+                *reinterpret_cast<float4*>(dst + jj) = o;
+              }
             } else {
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + out_pix * p.Co + cc_now;
+              if (p.accumulate) {
+                const uint4 e0 = *reinterpret_cast<const uint4*>(dst), e1 = *reinterpret_cast<const uint4*>(dst + 8);
+                const __nv_bfloat16* eb0 = reinterpret_cast<const __nv_bfloat16*>(&e0);
+                const __nv_bfloat16* eb1 = reinterpret_cast<const __nv_bfloat16*>(&e1);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) { fv[jj] += __bfloat162float(eb0[jj]); fv[8 + jj] += __bfloat162float(eb1[jj]); }
+              }
               uint4 o0, o1;
               __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
               __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
@@ -304,7 +317,8 @@ bool try_launch_conv_halo(const ConvLaunch& L, cudaStream_t stream, const char**
   if (!enabled) return false;
   ConvParams p = L.p;
   if (p.CB < 1) p.CB = 1;
-  if (p.in_stride != 1 || p.CB != 1 || p.accumulate) return false;
+  if (p.in_stride != 1 || p.CB != 1) return false;
+  if (p.accumulate && (p.act != 0 || p.stats)) return false;
   if (p.es != 2 && p.es != 4) return false;
   if (p.BN % 16 || p.BN < 16 || p.BN > 64) return false;
   if (p.stats && p.BN > 32) return false;                              // BatchNorm sums live in registers: <= 32 channels

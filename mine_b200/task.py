@@ -70,6 +70,36 @@ def _get_disparity_list(config: Mapping, B: int, device=None, generator=None) ->
     return S.disparity_planes(config, B, device=device, generator=generator)
 
 
+class _LossTerms:
+    """Collects the differentiable scalar terms of all pyramid scales and assembles them with THREE small kernels
+    (stack, ``w * t + b``, dot) instead of one framework op per addition / lambda multiplication (~75 scalar launches per
+    step forward, ~25 backward).  ``add`` returns the position of the term; ``finish`` returns the weighted values (what
+    the loss dictionary reports) and their selected sum (the training loss)."""
+    _CONST: Dict = {}
+
+    def __init__(self):
+        self.raw, self.w, self.b, self.sel = [], [], [], []
+
+    def add(self, raw: torch.Tensor, weight: float = 1.0, offset: float = 0.0, in_total: bool = True) -> int:
+        self.raw.append(raw.reshape(()))
+        self.w.append(float(weight)); self.b.append(float(offset)); self.sel.append(1.0 if in_total else 0.0)
+        return len(self.raw) - 1
+
+    @classmethod
+    def _const(cls, values, device) -> torch.Tensor:
+        key = (tuple(values), str(device))
+        t = cls._CONST.get(key)
+        if t is None:                      # first (eager) step: host -> device copies are illegal under graph capture
+            t = cls._CONST[key] = torch.tensor(values, dtype=torch.float32, device=device)
+        return t
+
+    def finish(self):
+        dev = self.raw[0].device
+        stacked = torch.stack([r.float() for r in self.raw])
+        vals = torch.addcmul(self._const(self.b, dev), stacked, self._const(self.w, dev))
+        return vals, torch.dot(vals, self._const(self.sel, dev))
+
+
 class SynthesisTask:
     def __init__(self, config: Dict, logger=None, is_val: bool = False, device=None,
                  comm: Optional[Communicator] = None):
@@ -240,6 +270,13 @@ class SynthesisTask:
                                           bool(self.config.get("mpi.use_alpha", False)), self._bg_inf())
         return {"tgt_imgs_syn": rgb, "tgt_disparity_syn": torch.reciprocal(depth), "tgt_mask_syn": mask}
 
+    def _zero_scalar(self, device) -> torch.Tensor:
+        """A cached fp32 zero (reported for the loss terms whose lambda is 0: no fill kernel per scale and step)."""
+        z = getattr(self, "_zero_cache", None)
+        if z is None or z.device != device:
+            z = self._zero_cache = torch.zeros((), device=device)
+        return z
+
     def compute_scale_factor(self, disparity_syn_pt3dsrc, pt3d_disp_src):
         if self.config["data.name"] in NO_SCALE_DATASETS:
             return torch.ones(pt3d_disp_src.shape[0], dtype=torch.float32, device=pt3d_disp_src.device)
@@ -248,7 +285,10 @@ class SynthesisTask:
     # ------------------------------------------------------------------------------------------
     # losses
     # ------------------------------------------------------------------------------------------
-    def loss_fcn_per_scale(self, scale, mpi_all_src, disparity_all_src, scale_factor=None, is_val=False):
+    def loss_fcn_per_scale(self, scale, mpi_all_src, disparity_all_src, scale_factor=None, is_val=False, _terms=None):
+        """Losses of one pyramid scale.  ``_terms`` (internal, set by :meth:`loss_fcn`): the differentiable terms are
+        recorded raw in a :class:`_LossTerms` collector - the dictionary then maps their names to collector positions and
+        carries no ``"loss"`` entry; :meth:`loss_fcn` assembles everything for all scales at once."""
         c = self.config
         src_img, tgt_img = self._src_pyr[scale], self._tgt_pyr[scale]
         B = src_img.shape[0]
@@ -285,19 +325,46 @@ class SynthesisTask:
                 loss_rgb_src = (src_imgs_syn - src_img).abs().mean()
                 loss_ssim_src = 1 - ops.ssim(src_imgs_syn, src_img)
                 loss_smooth_src = ops.edge_aware_loss(src_img, src_disparity_syn, gmin, ratio)
+            raw_disp_tgt = ops.sparse_point_loss(tgt_disparity_syn, K_tgt, self.pt3d_tgt, scale_factor)[0]
+            raw_rgb_tgt = ops.masked_l1(tgt_rgb, tgt_img, tgt_mask, float(c["mpi.valid_mask_threshold"]))
+            raw_smooth_tgt = ops.edge_aware_loss(tgt_img, tgt_disparity_syn, gmin, ratio) if lam1 != 0.0 else None
+            raw_smooth_tgt_v2 = ops.edge_aware_loss_v2(tgt_img, tgt_disparity_syn) if lam2 != 0.0 else None
+            raw_smooth_src_v2 = ops.edge_aware_loss_v2(src_img, src_disparity_syn) if lam2 != 0.0 else None
+            raw_ssim_tgt = ops.ssim(tgt_rgb, tgt_img)
+            if _terms is not None:
+                # cross-scale rule of the reference: scale 0 counts every term; scales 1..3 count the sparse-disparity and
+                # v2-smoothness terms, plus RGB / SSIM under training.use_multi_scale, and never the v1 smoothness
+                multi = scale == 0 or bool(c.get("training.use_multi_scale", True))
+                zero = self._zero_scalar(tgt_rgb.device)
+                pos = {"loss_disp_pt3dtgt": _terms.add(raw_disp_tgt, disp_lambda),
+                       "loss_disp_pt3dsrc": _terms.add(loss_disp_src, disp_lambda),
+                       "loss_rgb_tgt": _terms.add(raw_rgb_tgt, 1.0, 0.0, multi),
+                       "loss_ssim_tgt": _terms.add(raw_ssim_tgt, -1.0, 1.0, multi)}
+                if raw_smooth_tgt is not None:
+                    pos["loss_smooth_tgt"] = _terms.add(raw_smooth_tgt, lam1, 0.0, scale == 0)
+                if raw_smooth_tgt_v2 is not None:
+                    pos["loss_smooth_tgt_v2"] = _terms.add(raw_smooth_tgt_v2, lam2)
+                    pos["loss_smooth_src_v2"] = _terms.add(raw_smooth_src_v2, lam2)
+                with torch.no_grad():
+                    if is_val and scale == 0 and self.lpips is not None:
+                        lpips_tgt = self.lpips(tgt_rgb, tgt_img).mean()
+                    else:
+                        lpips_tgt = zero
+                    psnr_tgt = ops.psnr(tgt_rgb, tgt_img)
+                loss_dict = {"_pos": pos, "loss_rgb_src": loss_rgb_src, "loss_ssim_src": loss_ssim_src,
+                             "loss_smooth_src": loss_smooth_src, "loss_smooth_tgt": zero, "loss_smooth_src_v2": zero,
+                             "loss_smooth_tgt_v2": zero, "lpips_tgt": lpips_tgt, "psnr_tgt": psnr_tgt}
+                vis = {"src_disparity_syn": src_disparity_syn, "tgt_disparity_syn": tgt_disparity_syn,
+                       "tgt_imgs_syn": tgt_rgb, "tgt_mask_syn": tgt_mask, "src_imgs_syn": src_imgs_syn}
+                return loss_dict, vis, scale_factor
             loss_disp_src = disp_lambda * loss_disp_src
-            loss_disp_tgt = disp_lambda * ops.sparse_point_loss(tgt_disparity_syn, K_tgt, self.pt3d_tgt, scale_factor)[0]
-            loss_rgb_tgt = ops.masked_l1(tgt_rgb, tgt_img, tgt_mask, float(c["mpi.valid_mask_threshold"]))
-            if lam1 != 0.0:
-                loss_smooth_tgt = lam1 * ops.edge_aware_loss(tgt_img, tgt_disparity_syn, gmin, ratio)
-            else:
-                loss_smooth_tgt = torch.zeros((), device=tgt_rgb.device)
-            if lam2 != 0.0:
-                loss_smooth_tgt_v2 = lam2 * ops.edge_aware_loss_v2(tgt_img, tgt_disparity_syn)
-                loss_smooth_src_v2 = lam2 * ops.edge_aware_loss_v2(src_img, src_disparity_syn)
-            else:
-                loss_smooth_tgt_v2 = loss_smooth_src_v2 = torch.zeros((), device=tgt_rgb.device)
-            loss_ssim_tgt = 1 - ops.ssim(tgt_rgb, tgt_img)
+            loss_disp_tgt = disp_lambda * raw_disp_tgt
+            loss_rgb_tgt = raw_rgb_tgt
+            zero = torch.zeros((), device=tgt_rgb.device)
+            loss_smooth_tgt = lam1 * raw_smooth_tgt if raw_smooth_tgt is not None else zero
+            loss_smooth_tgt_v2 = lam2 * raw_smooth_tgt_v2 if raw_smooth_tgt_v2 is not None else zero
+            loss_smooth_src_v2 = lam2 * raw_smooth_src_v2 if raw_smooth_src_v2 is not None else zero
+            loss_ssim_tgt = 1 - raw_ssim_tgt
             with torch.no_grad():
                 if is_val and scale == 0 and self.lpips is not None:
                     lpips_tgt = self.lpips(tgt_rgb, tgt_img).mean()
@@ -321,11 +388,22 @@ class SynthesisTask:
         with self.profiler.phase("network"):
             endpoints = self.network_forward()
         per_scale, vis_list, scale_factor = [], [], None
+        fused = os.environ.get("MINE_B200_LOSS_ASSEMBLY", "fused") == "fused"
+        terms = _LossTerms() if fused else None
         for scale in range(4):
             ld, vis, scale_factor = self.loss_fcn_per_scale(scale, endpoints["mpi_all_src_list"][scale],
-                                                            endpoints["disparity_all_src"], scale_factor, is_val=is_val)
+                                                            endpoints["disparity_all_src"], scale_factor, is_val=is_val,
+                                                            _terms=terms)
             per_scale.append(ld)
             vis_list.append(vis)
+        if fused:
+            vals, total = terms.finish()                   # all scalar arithmetic of the step: three small kernels
+            unbound = vals.unbind(0)
+            loss_dict = per_scale[0]
+            for name, i in loss_dict.pop("_pos").items():
+                loss_dict[name] = unbound[i]
+            loss_dict["loss"] = total
+            return loss_dict, vis_list[0]
         loss_dict = per_scale[0]
         total = loss_dict["loss"]
         for s in range(1, 4):

@@ -23,7 +23,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 agg = collections.defaultdict(lambda: [0, 0.0])
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
-        name = re.sub(r'\(.*', '', ev.name); name = re.sub(r'<.*', '', name)[:70]
+        name = ev.name.replace('(anonymous namespace)::', ''); name = re.sub(r'\(.*', '', name); name = re.sub(r'<.*', '', name)[:70]
         agg[name][0] += 1; agg[name][1] += ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
 tot = sum(v[1] for v in agg.values())
 print("precision %s, conv engine %s, encoder %s" % (cfg["engine.precision"], t.runner.mode,

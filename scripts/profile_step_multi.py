@@ -29,7 +29,7 @@ if ctx.rank == 0:
     agg = collections.defaultdict(lambda: [0, 0.0])
     for ev in prof.events():
         if ev.device_type == torch.autograd.DeviceType.CUDA:
-            name = re.sub(r'\(.*', '', ev.name); name = re.sub(r'<.*', '', name)[:70]
+            name = ev.name.replace('(anonymous namespace)::', ''); name = re.sub(r'\(.*', '', name); name = re.sub(r'<.*', '', name)[:70]
             agg[name][0] += 1; agg[name][1] += ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
     tot = sum(v[1] for v in agg.values())
     print("world %d, precision %s, encoder %s, comm %s" % (ctx.world_size, cfg["engine.precision"],

@@ -139,6 +139,25 @@ def test_dgrad_and_wgrad_up(n, h, w, ci, co):
     assert _rel(dw, wt.grad) < _tol(1e-2, 2e-4)
 
 
+@pytest.mark.parametrize("n,h,w,co,ci", [(2, 16, 24, 16, 32), (3, 9, 13, 16, 16), (2, 8, 16, 128, 64)])
+def test_dgrad_accumulates_into_existing_gradient(n, h, w, co, ci):
+    """Two consumers of one activation: the second data gradient is added onto the first inside the kernel epilogue
+    (``GradSlot``) - must equal the separate sum."""
+    from mine_b200.ops import conv_engine as E
+    dy = _act(_q(_rand((n, co, h, w), 0)))
+    wt = _q(_rand((co, ci, 3, 3), 1, 0.1))
+    base = _act(_q(_rand((n, ci, h + 2, w + 2), 2)))
+    want = base.float() + E.dgrad_same_raw(dy, wt).float()
+    got = E.dgrad_same_raw(dy, wt, accumulate_into=base.clone())
+    assert _rel(got.float(), want) < _tol(1e-2, 1e-6)
+    slot = E.GradSlot()
+    first = slot.deliver(lambda acc: E.dgrad_same_raw(dy, wt, accumulate_into=acc))
+    assert first is not None and slot.buf is first
+    second = slot.deliver(lambda acc: E.dgrad_same_raw(dy, wt, accumulate_into=acc))
+    assert second is None and slot.buf is None
+    assert _rel(first.float(), 2 * E.dgrad_same_raw(dy, wt).float()) < _tol(1e-2, 1e-6)
+
+
 @pytest.mark.parametrize("pad_mode", [0, 1])
 @pytest.mark.parametrize("n,h,w,c", [(4, 12, 20, 32), (2, 33, 17, 16), (6, 8, 12, 256)])
 def test_bn_act_pad_fwd_bwd(pad_mode, n, h, w, c):
