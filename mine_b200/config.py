@@ -85,6 +85,7 @@ SCHEMA: Dict[str, tuple] = {
     "training.use_multi_scale": (bool, True),
     "testing.frames_apart": ("any", "random"),      # dead
     # ---- extensions of this framework (absent upstream; all optional) ----
+    "engine.deterministic": (bool, False),          # reproducible BatchNorm reductions in the hybrid / tcgen05 encoder (slower)
     "engine.precision": (str, "tf32"),              # tf32: fp32 tensors + TF32 tensor-core convs (reference numerics) | bf16: fast mode
     "engine.compute_dtype": (str, "bf16"),          # deprecated alias, ignored (see engine.precision)
     "engine.cuda_graph": (bool, False),

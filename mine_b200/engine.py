@@ -44,6 +44,8 @@ class ModelRunner:
             from .ops import conv_engine
             if not conv_engine._emulated:
                 conv_engine.set_precision(self.precision)
+                conv_engine.set_deterministic(bool(config.get("engine.deterministic", False)) or
+                                              os.environ.get("MINE_B200_DETERMINISTIC", "0") == "1")
             self._engine = conv_engine.ConvEngine(backbone, decoder, config, self.device)
 
     def predict(self, src_imgs: torch.Tensor, disparity: torch.Tensor) -> List[torch.Tensor]:

@@ -54,6 +54,13 @@ def set_precision(precision: str) -> None:
         _PACK_STATE["plan"] = _PACK_STATE["seen"] = None                 # packs of the other operand type are stale
 
 
+def set_deterministic(on: bool) -> None:
+    """``engine.deterministic``: bitwise reproducible BatchNorm reductions in the encoder kernels of the "hybrid" /
+    "tcgen05" encoder modes (two-level fixed-order sums instead of fp32 atomics); process-wide."""
+    if not _emulated and ext() is not None and hasattr(ext(), "set_deterministic"):
+        ext().set_deterministic(bool(on))
+
+
 def round_tf32(t: torch.Tensor) -> torch.Tensor:
     """fp32 -> nearest TF32-representable fp32 (10 explicit mantissa bits, ties away from zero = ``cvt.rna.tf32.f32``).
     ``kind::tf32`` MMAs ignore the 13 low mantissa bits, i.e. truncate; every tensor-core operand is therefore rounded
@@ -62,10 +69,42 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+_OUTPUT_ROUNDING = True
+
+
+class output_rounding:
+    """``with output_rounding(False):`` - activations produced for LIBRARY convolutions (hybrid encoder) stay plain fp32
+    (the library rounds its own operands); the default rounds every produced activation to TF32 because the next
+    consumer is a tcgen05 kernel, whose MMA would otherwise truncate."""
+
+    def __init__(self, on: bool):
+        self.on = bool(on)
+
+    def __enter__(self):
+        global _OUTPUT_ROUNDING
+        self.prev, _OUTPUT_ROUNDING = _OUTPUT_ROUNDING, self.on
+        from . import emu
+        emu.ROUND_ENCODER_OUT = self.on
+        if not _emulated and _ext is not None:
+            _ext.set_output_rounding(self.on)
+        return self
+
+    def __exit__(self, *exc):
+        global _OUTPUT_ROUNDING
+        _OUTPUT_ROUNDING = self.prev
+        from . import emu
+        emu.ROUND_ENCODER_OUT = self.prev
+        if not _emulated and _ext is not None:
+            _ext.set_output_rounding(self.prev)
+        return False
+
+
 def to_operand(t: torch.Tensor) -> torch.Tensor:
     """Cast a framework tensor to the engine's operand storage type (bf16, or fp32 rounded to TF32)."""
     if ACT_DTYPE == torch.float32:
         t = t.float()
+        if not _OUTPUT_ROUNDING:
+            return t
         if _emulated:
             from . import emu
             if not emu.TF32_OPERANDS:          # exact-fp32 specification mode (CPU tier)
@@ -535,11 +574,37 @@ class BNActPad(torch.autograd.Function):
         return dy, dgamma.to(g32.dtype), dbeta.to(b32.dtype), None, None, None
 
 
+_RUNNING = {"defer": False, "pending": []}
+
+
+def defer_running_stats(on: bool) -> None:
+    """Trainer switch: collect the running-statistic updates of a step and apply them with one multi-layer launch
+    (:func:`flush_running_stats`) instead of one small kernel per BatchNorm layer (67 per step with the hybrid encoder)."""
+    if not on:
+        flush_running_stats()
+    _RUNNING["defer"] = bool(on)
+
+
+def flush_running_stats() -> None:
+    pend, _RUNNING["pending"] = _RUNNING["pending"], []
+    if not pend:
+        return
+    with torch.no_grad():
+        ext().bn_update_running_multi([p[1] for p in pend], [p[0].running_mean for p in pend],
+                                      [p[0].running_var for p in pend], [p[0].num_batches_tracked for p in pend],
+                                      [float(p[2]) for p in pend], [float(p[0].momentum) for p in pend])
+    _count((len(pend) + 47) // 48)
+
+
 def update_running_stats(bn, stats: torch.Tensor, count: float) -> None:
-    """Momentum update of ``bn``'s buffers from the reduced batch sums ``[2, C]``: one kernel (``bn_update_running``);
+    """Momentum update of ``bn``'s buffers from the reduced batch sums ``[2, C]``: one kernel (``bn_update_running``), or
+    queued for the multi-layer launch of :func:`flush_running_stats` when the trainer defers;
     ``MINE_B200_BN_RUNNING=aten`` selects the equivalent ~11 framework ops."""
     with torch.no_grad():
         if os.environ.get("MINE_B200_BN_RUNNING", "fused") == "fused" and (_emulated or stats.is_cuda):
+            if _RUNNING["defer"] and stats.dtype == torch.float32 and stats.is_contiguous():
+                _RUNNING["pending"].append((bn, stats, count))
+                return
             ext().bn_update_running(stats, bn.running_mean, bn.running_var, bn.num_batches_tracked, float(count),
                                     float(bn.momentum))
             _count()
@@ -626,10 +691,13 @@ class ConvEngine:
         self.backbone, self.decoder, self.config, self.device = backbone, decoder, config, device
         # encoder: "cudnn" (library convolutions + ATen BN under bf16 autocast), "hybrid" (library convolutions +
         # our fused BN kernels) or "tcgen05" (everything on the engine, encoder_engine.py)
-        # default: one GPU -> "cudnn" (the library's fused single-pass BatchNorm is the fastest there); data parallel ->
-        # "hybrid" (cross-replica BatchNorm through our fused kernels: 3 launches per layer and direction with the
-        # statistic exchange inside the normalise kernel, instead of ~15 framework ops around ATen's sync-BN pieces;
-        # measured at 2 GPUs, tf32: 17.8 vs 19.5 ms per step)
+        # default: one GPU -> "cudnn" (library convolutions + library BatchNorm: bitwise reproducible from run to run);
+        # data parallel -> "hybrid" (BatchNorm / residual / ReLU of the encoder on our kernels: statistics kernel + one
+        # fused normalise-residual-activation kernel per layer with the cross-replica exchange inside it; the library
+        # sync-BN path costs +1.7 ms per step at 2 GPUs).  Measured on one B200, LLFF step: tf32 hybrid 11.52 ms vs cudnn
+        # 11.59 ms, bf16 hybrid 9.81 ms vs cudnn 10.9 ms - hybrid is not the one-GPU default only because its fp32-atomic
+        # statistics vary in the last bits between runs, and ~50 BatchNorm layers over a few dozen samples each amplify
+        # that (scripts/graph_vs_eager_probe.py); ``engine.deterministic`` makes them reproducible at ~+1 ms per step.
         import torch.distributed as _dist
         multi = _dist.is_available() and _dist.is_initialized() and _dist.get_world_size() > 1
         self.encoder_mode = encoder_mode or os.environ.get("MINE_B200_ENCODER", "hybrid" if multi else "cudnn")

@@ -126,6 +126,11 @@ void set_operand_size(int64_t es) {
 }
 int64_t get_operand_size() { return g_operand_es; }
 
+// encoder activations: rounded to TF32 when the next convolution is a tcgen05 kernel (default), plain fp32 when it is a
+// library convolution ("hybrid" encoder)
+static bool g_round_encoder_out = true;
+void set_output_rounding(bool on) { g_round_encoder_out = on; }
+
 at::Tensor pack_weights(const at::Tensor& w, int64_t mode) {
   TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.dim() == 4 && w.size(2) == 3 && w.size(3) == 3,
               "pack_weights expects a CUDA fp32 [Co,Ci,3,3] tensor (any strides)");
@@ -382,13 +387,28 @@ std::vector<at::Tensor> bn_res_act_fwd_x(const at::Tensor& y, const at::Tensor& 
   mine::launch_bn_res_act_fwd(y.data_ptr(), stats.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(), res,
                               out.data_ptr(), (size_t)(y.numel() / y.size(3)), (int)y.size(3), (float)slope,
                               (float)(1.0 / count), (float)eps, esize(y), f.on ? &f.x : nullptr,
-                              f.on ? red.data_ptr<float>() : nullptr, cur_stream());
+                              f.on ? red.data_ptr<float>() : nullptr, g_round_encoder_out ? 1 : 0, cur_stream());
   return {out, red};
 }
 
 at::Tensor bn_res_act_fwd(const at::Tensor& y, const at::Tensor& stats, const at::Tensor& gamma, const at::Tensor& beta,
                           const c10::optional<at::Tensor>& residual, double slope, double count, double eps) {
   return bn_res_act_fwd_x(y, stats, gamma, beta, residual, slope, count, eps, {}, 0, 0, c10::nullopt, c10::nullopt)[0];
+}
+
+// engine.deterministic: bitwise reproducible BatchNorm reductions in the encoder kernels (two-level fixed-order sums
+// instead of fp32 atomics; ~10 us more per layer and direction)
+static bool g_deterministic = false;
+void set_deterministic(bool on) { g_deterministic = on; }
+bool get_deterministic() { return g_deterministic; }
+
+// ticket counters of the reproducible reductions (encoder_elem.cu::publish_sums), one zeroed array per device; every
+// launch leaves them at zero
+static unsigned* reduce_tickets(const at::Device& dev) {
+  static std::vector<at::Tensor> tickets(64);
+  at::Tensor& t = tickets[dev.index() < 0 ? 0 : dev.index()];
+  if (!t.defined()) t = at::zeros({64}, at::TensorOptions().device(dev).dtype(at::kInt));
+  return reinterpret_cast<unsigned*>(t.data_ptr<int>());
 }
 
 std::vector<at::Tensor> bn_res_act_bwd_reduce(const at::Tensor& dout, const at::Tensor& out, const at::Tensor& y,
@@ -401,19 +421,31 @@ std::vector<at::Tensor> bn_res_act_bwd_reduce(const at::Tensor& dout, const at::
   (void)gamma; (void)beta;                     // the reduction needs mean / invstd only; kept for a uniform signature
   c10::cuda::CUDAGuard guard(y.device());
   at::Tensor g = at::empty_like(y);
-  at::Tensor sums = at::zeros({2, y.size(3)}, stats.options());
+  const int64_t C = y.size(3), npix = y.numel() / C;
+  TORCH_CHECK(C <= 2048, "at most 2048 channels");
+  const bool det = g_deterministic;
+  at::Tensor sums = det ? at::empty({2, C}, stats.options()) : at::zeros({2, C}, stats.options());
+  at::Tensor scratch = det ? at::empty({(int64_t)mine::reduce_scratch_floats((size_t)npix, (int)C)}, stats.options())
+                           : at::Tensor();
   mine::launch_bn_res_act_bwd_reduce(dout.data_ptr(), out.data_ptr(), y.data_ptr(), stats.data_ptr<float>(), g.data_ptr(),
-                                     sums.data_ptr<float>(), (size_t)(y.numel() / y.size(3)), (int)y.size(3),
-                                     (float)slope, (float)(1.0 / count), (float)eps, esize(y), cur_stream());
+                                     sums.data_ptr<float>(), (size_t)npix, (int)C, (float)slope, (float)(1.0 / count),
+                                     (float)eps, esize(y), det ? scratch.data_ptr<float>() : nullptr,
+                                     det ? reduce_tickets(y.device()) : nullptr, cur_stream());
   return {g, sums};
 }
 
 at::Tensor channel_stats(const at::Tensor& y) {
   check_act_nhwc(y, "y"); check_channels(y);
   c10::cuda::CUDAGuard guard(y.device());
-  at::Tensor sums = at::zeros({2, y.size(3)}, y.options().dtype(at::kFloat));
-  mine::launch_channel_stats(y.data_ptr(), sums.data_ptr<float>(), (size_t)(y.numel() / y.size(3)), (int)y.size(3),
-                             esize(y), cur_stream());
+  const int64_t C = y.size(3), npix = y.numel() / C;
+  TORCH_CHECK(C <= 2048, "at most 2048 channels");
+  const bool det = g_deterministic;
+  at::Tensor sums = det ? at::empty({2, C}, y.options().dtype(at::kFloat)) : at::zeros({2, C}, y.options().dtype(at::kFloat));
+  at::Tensor scratch = det ? at::empty({(int64_t)mine::reduce_scratch_floats((size_t)npix, (int)C)}, sums.options())
+                           : at::Tensor();
+  mine::launch_channel_stats(y.data_ptr(), sums.data_ptr<float>(), (size_t)npix, (int)C, esize(y),
+                             det ? scratch.data_ptr<float>() : nullptr, det ? reduce_tickets(y.device()) : nullptr,
+                             cur_stream());
   return sums;
 }
 
@@ -445,8 +477,14 @@ std::vector<at::Tensor> splitk_finalize(const at::Tensor& acc, bool want_stats) 
   c10::cuda::CUDAGuard guard(acc.device());
   at::Tensor stats = want_stats ? at::zeros({2, C}, acc.options()) : at::empty({0}, acc.options());
   if (g_operand_es == 4) {       // fp32 operands: the partial-sum tensor IS the activation; only the BN sums are left
-    if (want_stats)
-      mine::launch_channel_stats(acc.data_ptr(), stats.data_ptr<float>(), (size_t)(acc.numel() / C), (int)C, 4, cur_stream());
+    if (want_stats) {
+      const bool det = g_deterministic;       // ``stats`` is zero filled above: fine for both variants
+      at::Tensor scratch = det ? at::empty({(int64_t)mine::reduce_scratch_floats((size_t)(acc.numel() / C), (int)C)}, acc.options())
+                               : at::Tensor();
+      mine::launch_channel_stats(acc.data_ptr(), stats.data_ptr<float>(), (size_t)(acc.numel() / C), (int)C, 4,
+                                 det ? scratch.data_ptr<float>() : nullptr, det ? reduce_tickets(acc.device()) : nullptr,
+                                 cur_stream());
+    }
     return {acc, stats};
   }
   at::Tensor y = at::empty(acc.sizes(), acc.options().dtype(at::kBFloat16));
@@ -468,11 +506,42 @@ void bn_update_running(const at::Tensor& stats, at::Tensor running_mean, at::Ten
                                  (float)count, (float)momentum, cur_stream());
 }
 
+// deferred form of bn_update_running: all layers of a step in one launch per 48 layers
+void bn_update_running_multi(const std::vector<at::Tensor>& stats, std::vector<at::Tensor> running_mean,
+                             std::vector<at::Tensor> running_var, std::vector<at::Tensor> num_batches_tracked,
+                             const std::vector<double>& count, const std::vector<double>& momentum) {
+  const size_t n = stats.size();
+  TORCH_CHECK(running_mean.size() == n && running_var.size() == n && num_batches_tracked.size() == n && count.size() == n &&
+              momentum.size() == n, "bn_update_running_multi: list lengths differ");
+  if (n == 0) return;
+  c10::cuda::CUDAGuard guard(stats[0].device());
+  std::vector<const float*> ps(n);
+  std::vector<float*> pm(n), pv(n);
+  std::vector<long long*> pn(n);
+  std::vector<int> cs(n);
+  std::vector<float> cnt(n), mom(n);
+  for (size_t i = 0; i < n; ++i) {
+    const int64_t C = running_mean[i].numel();
+    TORCH_CHECK(opt_f32(stats[i], "stats") && stats[i].numel() == 2 * C, "stats must be fp32 [2, C]");
+    TORCH_CHECK(opt_f32(running_mean[i], "running_mean") && opt_f32(running_var[i], "running_var") &&
+                running_var[i].numel() == C, "running statistics must be contiguous CUDA fp32");
+    TORCH_CHECK(num_batches_tracked[i].is_cuda() && num_batches_tracked[i].scalar_type() == at::kLong, "num_batches_tracked");
+    ps[i] = stats[i].data_ptr<float>(); pm[i] = running_mean[i].data_ptr<float>(); pv[i] = running_var[i].data_ptr<float>();
+    pn[i] = reinterpret_cast<long long*>(num_batches_tracked[i].data_ptr<int64_t>());
+    cs[i] = (int)C; cnt[i] = (float)count[i]; mom[i] = (float)momentum[i];
+  }
+  mine::launch_bn_update_running_multi((int)n, ps.data(), pm.data(), pv.data(), pn.data(), cs.data(), cnt.data(),
+                                       mom.data(), cur_stream());
+}
+
 }  // namespace
 
 void register_conv(pybind11::module_& m) {
   m.def("set_operand_size", &set_operand_size);
   m.def("get_operand_size", &get_operand_size);
+  m.def("set_output_rounding", &set_output_rounding);
+  m.def("set_deterministic", &set_deterministic);
+  m.def("get_deterministic", &get_deterministic);
   m.def("conv_taps", &conv_taps);
   m.def("wgrad_taps", &wgrad_taps);
   m.def("pack_weights", &pack_weights);
@@ -493,6 +562,7 @@ void register_conv(pybind11::module_& m) {
   m.def("channel_stats", &channel_stats);
   m.def("head_conv_direct", &head_conv_direct);
   m.def("bn_update_running", &bn_update_running);
+  m.def("bn_update_running_multi", &bn_update_running_multi);
   m.def("conv_taps_splitk", &conv_taps_splitk);
   m.def("splitk_finalize", &splitk_finalize);
 }

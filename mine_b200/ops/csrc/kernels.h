@@ -96,13 +96,19 @@ namespace mine {
 // ---- encoder_elem.cu (unpadded NHWC bf16, C a power of two in [16, 2048]) -------------------------------
 void launch_bn_res_act_fwd(const void* y, const float* stats, const float* gamma, const float* beta, const void* res,
                            void* out, size_t npix, int C, float slope, float inv_count, float eps, int es,
-                           const LLExchange* x, float* red_out, cudaStream_t stream);
+                           const LLExchange* x, float* red_out, int round_out, cudaStream_t stream);
+int reduce_blocks(size_t npix, int C);   // grid of the two reproducible reductions below
+size_t reduce_scratch_floats(size_t npix, int C);   // their per-call scratch; ticket: persistent zeroed unsigned[64] per device
 void launch_bn_res_act_bwd_reduce(const void* dout, const void* out, const void* y, const float* stats, void* g_out,
                                   float* sums, size_t npix, int C, float slope, float inv_count, float eps, int es,
-                                  cudaStream_t stream);
-void launch_channel_stats(const void* y, float* sums, size_t npix, int C, int es, cudaStream_t stream);
+                                  float* scratch, unsigned* ticket, cudaStream_t stream);
+void launch_channel_stats(const void* y, float* sums, size_t npix, int C, int es, float* scratch, unsigned* ticket,
+                          cudaStream_t stream);
 void launch_bn_update_running(const float* stats, float* running_mean, float* running_var, long long* num_batches, int C,
                               float count, float momentum, cudaStream_t stream);
+void launch_bn_update_running_multi(int n, const float* const* stats, float* const* mean, float* const* var,
+                                    long long* const* nbt, const int* C, const float* count, const float* momentum,
+                                    cudaStream_t stream);
 }  // namespace mine
 
 namespace mine {

@@ -213,6 +213,9 @@ def head_bwd(g_mpi, mpi, sign, use_alpha):
 
 
 # ---- encoder companions (csrc/encoder_elem.cu) ------------------------------------------------------------------
+ROUND_ENCODER_OUT = True          # conv_engine.output_rounding: False while the hybrid encoder feeds library convolutions
+
+
 def bn_res_act_fwd(y, stats, gamma, beta, residual, slope, count, eps):
     """``act(BN(y) [+ residual])`` on an unpadded NHWC tensor; ``act(v) = v if v > 0 else slope * v``
     (0: ReLU, 0.1: LeakyReLU, 1: identity)."""
@@ -221,7 +224,7 @@ def bn_res_act_fwd(y, stats, gamma, beta, residual, slope, count, eps):
     if residual is not None:
         u = u + residual.float()
     u = torch.where(u > 0, u, u * slope)
-    return _round_op(u.to(y.dtype))
+    return _round_op(u.to(y.dtype)) if ROUND_ENCODER_OUT else u.to(y.dtype)
 
 
 def bn_res_act_bwd_reduce(dout, out, y, stats, gamma, beta, slope, count, eps):
@@ -242,6 +245,11 @@ def bn_update_running(stats, running_mean, running_var, num_batches_tracked, cou
     running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
     running_var.mul_(1 - momentum).add_((var * (count / max(count - 1.0, 1.0))).to(running_var.dtype), alpha=momentum)
     num_batches_tracked += 1
+
+
+def bn_update_running_multi(stats, running_mean, running_var, num_batches_tracked, count, momentum):
+    for i in range(len(stats)):
+        bn_update_running(stats[i], running_mean[i], running_var[i], num_batches_tracked[i], count[i], momentum[i])
 
 
 def channel_stats(y):

@@ -379,6 +379,11 @@ def _upsample_nhwc(x: torch.Tensor, size) -> torch.Tensor:
 def receptive_field_extension(dec, top_nchw: torch.Tensor, reducer=None, library_conv: bool = False) -> torch.Tensor:
     """``DepthDecoder.receptive_field_extension`` (reference ``depth_decoder.py:55-61,96-101``) on the engine:
     pool -> 1x1 -> pool -> 3x3 -> up -> 3x3 -> up -> 1x1, every conv followed by BN + LeakyReLU(0.1)."""
+    with E.output_rounding(not library_conv):
+        return _receptive_field_extension(dec, top_nchw, reducer, library_conv)
+
+
+def _receptive_field_extension(dec, top_nchw, reducer, library_conv):
     top = E.to_operand(top_nchw.permute(0, 2, 3, 1)).contiguous()
 
     def layer(x, blk):
@@ -427,6 +432,11 @@ class EncoderEngine:
         return conv_bn_act(out, blk.conv2, blk.bn2, relu=True, residual=idt, **kw)
 
     def __call__(self, img: torch.Tensor):
+        # hybrid: every activation produced here feeds a library convolution -> plain fp32, no TF32 rounding on store
+        with E.output_rounding(not self.library_conv):
+            return self._forward(img)
+
+    def _forward(self, img: torch.Tensor):
         bb, e = self.backbone, self.backbone.encoder
         reducer = self._reducer()
         x = (img - bb.img_mean.to(img.dtype)) / bb.img_std.to(img.dtype)

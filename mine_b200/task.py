@@ -478,11 +478,14 @@ class SynthesisTask:
         self.set_data(items)
         self.grad_sync.begin_step()
         self.optimizer.zero_grad()
+        from .ops import conv_engine as _E
         BatchNorm.defer_counters = True
+        _E.defer_running_stats(True)               # running-statistic updates of all layers: one launch after the forward
         try:
             loss_dict, _ = self.loss_fcn(is_val=False)
         finally:
             BatchNorm.defer_counters = False
+            _E.defer_running_stats(False)          # flushes
         flush_batch_counters(self.backbone, self.decoder)
         with self.profiler.phase("backward"):
             loss_dict["loss"].backward()

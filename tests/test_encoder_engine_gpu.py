@@ -255,3 +255,36 @@ def test_split_k_convolution(k, stride, n, h, w, ci, co, monkeypatch):
         ref.backward(dy)
         got = EE.conv_dgrad(_nhwc(dy).to(_ACT()), wt.detach(), 1, h, w)
         assert _rel2(_nchw(got), x.grad) < _tol(6e-3, 1e-4)
+
+
+def test_deterministic_reductions_are_bitwise_reproducible_and_match_the_atomic_path():
+    """``engine.deterministic``: channel_stats / bn_res_act_bwd_reduce with the two-level fixed-order sums give bitwise
+    identical results on repeated calls (the fp32-atomic default does not have to) and agree with the default path."""
+    from mine_b200.ops import conv_engine as E
+    ext = E.ext()
+    if E.ACT_DTYPE != torch.float32:
+        pytest.skip("one precision is enough")
+    for (n, h, w, c) in [(2, 64, 96, 256), (2, 8, 12, 2048), (2, 128, 192, 64), (3, 5, 7, 512)]:
+        gen = torch.Generator(device="cuda").manual_seed(c)
+        y = torch.randn((n, h, w, c), device="cuda", generator=gen) * 1.7 + 0.3
+        d = torch.randn((n, h, w, c), device="cuda", generator=gen)
+        a = torch.relu(y)
+        gamma, beta = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+        count = float(n * h * w)
+        try:
+            E.set_deterministic(False)
+            ref_stats = ext.channel_stats(y)
+            ref_g, ref_sums = ext.bn_res_act_bwd_reduce(d, a, y, ref_stats, gamma, beta, 0.0, count, 1e-5)
+            E.set_deterministic(True)
+            runs = []
+            for _ in range(3):
+                st = ext.channel_stats(y)
+                g, sums = ext.bn_res_act_bwd_reduce(d, a, y, st, gamma, beta, 0.0, count, 1e-5)
+                runs.append((st.clone(), sums.clone(), g.clone()))
+        finally:
+            E.set_deterministic(False)
+        for st, sums, g in runs[1:]:
+            assert torch.equal(st, runs[0][0]) and torch.equal(sums, runs[0][1]) and torch.equal(g, runs[0][2])
+        want = torch.stack([y.double().sum((0, 1, 2)), (y.double() ** 2).sum((0, 1, 2))]).float()
+        assert _rel2(runs[0][0], want) < 1e-5 and _rel2(ref_stats, want) < 1e-5
+        assert _rel2(runs[0][1], ref_sums) < 1e-4

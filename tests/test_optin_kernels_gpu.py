@@ -125,3 +125,29 @@ def test_fused_running_stat_update_kernel(monkeypatch):
     assert torch.allclose(a.running_mean, b.running_mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(a.running_var, b.running_var, rtol=1e-5, atol=1e-6)
     assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 1
+
+
+def test_deferred_running_statistics_one_launch_for_many_layers():
+    """``defer_running_stats``: the updates of a step are queued and applied by ``bn_update_running_multi`` (block = layer,
+    more than one launch chunk) - same buffers as the immediate per-layer kernel."""
+    from mine_b200.models.norm import BatchNorm
+    from mine_b200.ops import conv_engine as E
+    widths = [16, 32, 64, 256, 2048] * 11                      # 55 layers: two chunks of the 48-layer launch
+    now = [BatchNorm(c).cuda() for c in widths]
+    later = [BatchNorm(c).cuda() for c in widths]
+    stats = []
+    for i, c in enumerate(widths):
+        gen = torch.Generator(device="cuda").manual_seed(100 + i)
+        x = torch.randn((512, c), device="cuda", generator=gen) * (1 + 0.1 * i) + 0.05 * i
+        stats.append(torch.stack([x.sum(0), (x * x).sum(0)]).contiguous())
+    for bn, st in zip(now, stats):
+        E.update_running_stats(bn, st, 512.0)
+    E.defer_running_stats(True)
+    for bn, st in zip(later, stats):
+        E.update_running_stats(bn, st, 512.0)
+    assert all(int(bn.num_batches_tracked) == 0 for bn in later)        # nothing applied yet
+    E.defer_running_stats(False)                                         # flush
+    for a, b in zip(now, later):
+        assert torch.allclose(a.running_mean, b.running_mean, rtol=1e-6, atol=1e-7)
+        assert torch.allclose(a.running_var, b.running_var, rtol=1e-6, atol=1e-7)
+        assert int(b.num_batches_tracked) == 1
