@@ -20,4 +20,4 @@ try:
 except Exception as e:
     print(tag, "no result:", e); print(open(tag + ".err").read()[-1500:])
 PY
-timeout 300 $TR scripts/profile_step_multi.py tf32 > gpurun_out/step_breakdown_n${NG}_tf32.txt 2>&1; grep -A40 "^world" gpurun_out/step_breakdown_n${NG}_tf32.txt | head -40
+[ "${SKIP_PROFILE:-0}" = "1" ] || timeout 300 $TR scripts/profile_step_multi.py tf32 > gpurun_out/step_breakdown_n${NG}_tf32.txt 2>&1; grep -A40 "^world" gpurun_out/step_breakdown_n${NG}_tf32.txt | head -40
