@@ -127,6 +127,17 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// TMA store (shared -> global, bulk async group) and the proxy fence that makes generic-proxy shared-memory writes visible
+// to it
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Role code runs WARP-UNIFORM (all 32 lanes walk the loops and wait on the barriers); only the asynchronous instruction
 // itself (TMA, tcgen05.mma, commit) is predicated on one elected lane.  With a divergent ``if (lane == 0)`` around the whole
 // role the compiler keeps every address / descriptor in vector registers and pays an R2UR per operand of every UTCMMA /
@@ -249,6 +260,7 @@ const char* nhwc_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int
 const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop, int GT, int kb, int bn, int esz);
 // 16-channel fp32 tensor as 128-byte rows of two adjacent pixels (overlapping view, see conv_tcgen05.cu)
 const char* overlap32_map(CUtensorMap* out, const void* ptr, int W, int H, int N, int bw, int bh, int esx, int esy);
+const char* phase_out_map(CUtensorMap* out, const void* ptr, int C, int Wg, int NH, int bw, int bh, int esz);
 int next_pow2_cols(int n);
 int sm_count();
 

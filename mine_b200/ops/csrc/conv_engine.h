@@ -59,6 +59,9 @@ struct ConvParams {
   int halo_y0, halo_x0;
   int8_t rel_y[4][16], rel_x[4][16];
   int box_stride, w_tile_bytes, w_bytes;
+  // TMA-store epilogue of the sub-pixel upsample form (conv_halo.cu): per phase the 128 output rows are staged in shared
+  // memory (swizzled, two buffers) and written by one bulk tensor store
+  int tma_out, out_rb, out_buf_bytes, out_stage_off;
   // divisors of the work-item decomposition (filled by the launchers)
   FastDiv fd_tiles, fd_tiles_x, fd_n, fd_g, fd_planes;
 };

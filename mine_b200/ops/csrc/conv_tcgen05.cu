@@ -647,6 +647,29 @@ const char* overlap32_map(CUtensorMap* out, const void* ptr, int W, int H, int N
   return nullptr;
 }
 
+// Output of the sub-pixel upsample convolution [N, 2 Hg, 2 Wg, C] seen as {C, px (2), Wg, py (2), N * Hg}: the pixels of ONE
+// phase (py, px) of a low-resolution tile are the box {C, 1, bw, 1, bh} at (0, px, x0, py, n * Hg + y0) - the TMA store
+// of the conv_halo epilogue.  Row r of the box = low-res pixel (r / bw, r % bw) = the accumulator row of that pixel.
+const char* phase_out_map(CUtensorMap* out, const void* ptr, int C, int Wg, int NH, int bw, int bh, int esz) {
+  MapKey key{ptr, C, Wg, NH, 2, C, bw, bh, 5, 1, 1, 5, esz};
+  std::lock_guard<std::mutex> lock(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return nullptr; }
+  const cuuint64_t rowb = (cuuint64_t)C * esz;
+  cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)Wg, 2, (cuuint64_t)NH};
+  cuuint64_t strides[4] = {rowb, 2 * rowb, 2 * (cuuint64_t)Wg * rowb, 4 * (cuuint64_t)Wg * rowb};
+  cuuint32_t box[5] = {(cuuint32_t)C, 1, (cuuint32_t)bw, 1, (cuuint32_t)bh};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return "cuTensorMapEncodeTiled is not available from this driver";
+  CUresult r = enc(out, dtype_for(esz), 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for((int)rowb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the phase output map";
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = *out;
+  return nullptr;
+}
+
 // packed weights: dims {Ci, Co_pad, GT}; box {kb, bn, 1}
 const char* weight_map(CUtensorMap* out, const void* ptr, int Ci, int Cop, int GT, int kb, int bn, int esz) {
   MapKey key{ptr, Ci, Cop, GT, 0, kb, bn, 1, 0, 1, 1, 3, esz};
