@@ -44,7 +44,7 @@ SCHEMA: Dict[str, tuple] = {
     "data.training_set_path": (str, ""),
     "data.val_set_path": (str, ""),
     "data.visible_point_count": (int, 256),
-    "data.num_workers": (int, 4),                # dead in reference; used by our pinned loader
+    "data.num_workers": (int, 0),                # dead in the reference; here: worker processes of the training DataLoader
     "data.rotation_pi_ratio": (float, 3),        # dead
     "data.is_exclude_views": (bool, True),       # dead
     # lr
@@ -59,6 +59,8 @@ SCHEMA: Dict[str, tuple] = {
     "model.decoder_type": (str, "batch_decoder"),    # dead; present only in params_dtu.yaml
     "model.pos_encoding_multires": (int, 10),
     "model.imagenet_pretrained": (bool, True),
+    "model.require_imagenet_weights": (bool, False),   # true: missing local ResNet weights are fatal instead of a logged fallback
+    "model.imagenet_weights_used": (str, ""),          # written by the task: which file initialised the encoder
     # mpi
     "mpi.disparity_start": (float, 1.0),
     "mpi.disparity_end": (float, 0.001),
@@ -95,7 +97,7 @@ SCHEMA: Dict[str, tuple] = {
     "training.seed": (int, 0),
     "training.checkpoint_interval": (int, 5000),
     "training.log_interval": (int, 10),
-    "training.all_rank_eval": (bool, True),
+    "training.all_rank_eval": (bool, True),         # accepted, no effect: rank 0 evaluates, the others wait (patient barrier)
     "training.max_steps": (int, 0),                 # 0 = no cap (used by tests / smoke runs)
 }
 

@@ -156,6 +156,8 @@ class ResnetEncoder(nn.Module):
         std = torch.tensor(IMAGENET_STD * num_input_images).view(1, -1, 1, 1)
         self.register_buffer("img_mean", mean, persistent=False)
         self.register_buffer("img_std", std, persistent=False)
+        self.pretrained_requested = bool(pretrained)
+        self.pretrained_source = None
         if pretrained and num_input_images == 1:
             self._load_imagenet(pretrained_path)
 
@@ -177,6 +179,7 @@ class ResnetEncoder(nn.Module):
 
     def _load_imagenet(self, path):
         found = self._find_imagenet(path, self.num_layers)
+        self.pretrained_source = found                 # None: requested but not found -> random initialisation
         if found is not None:
             sd = torch.load(found, map_location="cpu")
             self.encoder.load_state_dict({k: v for k, v in sd.items() if not k.startswith("fc.")}, strict=True)

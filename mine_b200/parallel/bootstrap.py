@@ -56,7 +56,21 @@ def init_distributed(local_rank: Optional[int] = None, backend: Optional[str] = 
                 kw["device_id"] = dev
             dist.init_process_group(backend=backend, rank=rank, world_size=world,
                                     timeout=datetime.timedelta(seconds=timeout_s), **kw)
+            _make_patient_group()
     return DistContext(rank, world, local_rank, dev, backend if dist.is_initialized() else None)
+
+
+_PATIENT = {"group": None}
+
+
+def _make_patient_group() -> None:
+    """A host-side (gloo) group with a 24 h timeout for waits that are not bounded by a training step: the ranks that do
+    not evaluate wait for rank 0's validation pass there (round-1 advice: a RealEstate10K validation longer than the
+    10-minute collective timeout of the main group aborted the job)."""
+    try:
+        _PATIENT["group"] = dist.new_group(backend="gloo", timeout=datetime.timedelta(hours=24))
+    except Exception:                                    # gloo unavailable: fall back to the main group
+        _PATIENT["group"] = None
 
 
 def barrier() -> None:
@@ -64,8 +78,19 @@ def barrier() -> None:
         dist.barrier()
 
 
+def patient_barrier() -> None:
+    """Barrier for long host-side waits (evaluation on rank 0): gloo group with a 24 h timeout when available."""
+    if dist.is_available() and dist.is_initialized():
+        g = _PATIENT["group"]
+        if g is not None:
+            dist.barrier(group=g)
+        else:
+            dist.barrier()
+
+
 def shutdown() -> None:
     if dist.is_available() and dist.is_initialized():
+        _PATIENT["group"] = None
         dist.destroy_process_group()
 
 

@@ -12,7 +12,7 @@ and checkpoint formats - on a different execution stack:
 * data parallelism = flat gradient arena + bucketed mean all-reduce overlapped with backward
   (own NVLink kernels or NCCL) + cross-replica BN statistics through the same communicator;
   static graph: no unused parameters, no buffer broadcast (SURVEY 2.4 N5/N8/N9);
-* exact resume (step, epoch, scheduler, RNG) and all-rank-consistent evaluation.
+* exact resume (step, epoch, scheduler, RNG); evaluation on rank 0 while the other ranks wait at a host-side barrier.
 """
 from __future__ import annotations
 
@@ -121,6 +121,17 @@ class SynthesisTask:
         self.decoder = DepthDecoder(num_ch_enc=self.backbone.num_ch_enc, use_alpha=bool(config.get("mpi.use_alpha", False)),
                                     num_output_channels=4, scales=range(4), use_skips=True,
                                     embedder=None, embedder_out_dim=out_dim, multires=multires).to(self.device)
+        # ImageNet initialisation: the reference downloads the weights, here they must be present locally.  A silent
+        # random-init fallback changes convergence, so it is logged (training.log), recorded in the config that is
+        # written next to the checkpoints, and fatal with model.require_imagenet_weights.
+        if self.backbone.pretrained_requested and self.backbone.pretrained_source is None:
+            msg = ("model.imagenet_pretrained=true but no local ResNet-50 weights were found (set MINE_RESNET50_WEIGHTS or "
+                   "model.imagenet_pretrained=false): the encoder starts from RANDOM initialisation")
+            if bool(config.get("model.require_imagenet_weights", False)):
+                raise FileNotFoundError(msg)
+            self.logger.warning(msg)
+        config["model.imagenet_weights_used"] = (self.backbone.pretrained_source or "none (random initialisation)") \
+            if self.backbone.pretrained_requested else "not requested"
 
         self.comm = comm if comm is not None else (
             Communicator() if is_val else make_communicator(cfg_get(config, "engine.comm", "auto"), self.device))
@@ -554,7 +565,8 @@ class SynthesisTask:
                 for f in [path, self.config.get("log_file")] + tb[-1:]:
                     if f:
                         run_shell_cmd(["hdfs", "dfs", "-put", "-f", f, self.config["hdfs_workspace"]], self.logger)
-        bootstrap.barrier()
+        bootstrap.patient_barrier()                # host-side group with a 24 h timeout: validation may take long
+        bootstrap.barrier()                        # ... then re-align the device streams of all ranks
 
     def save_checkpoint(self, name: str, with_optimizer: bool) -> Optional[str]:
         ws = self.config.get("local_workspace")

@@ -70,8 +70,9 @@ def get_dataset(config, logger, ctx):
             f"no loader for {name!r} was ever released upstream; use data.training_set_path=synthetic "
             f"or the LLFF format (eval pair definitions: mine_b200.data.assets)")
     sampler = ShardedSampler(train_ds, ctx.world_size, ctx.rank, shuffle=True, seed=int(config.get("training.seed", 0)))
-    train = DataLoader(train_ds, batch_size=bs, drop_last=True, num_workers=0, sampler=sampler,
-                       collate_fn=train_ds.collate_fn)
+    workers = max(0, int(config.get("data.num_workers", 0) or 0))     # host-side decode / augmentation workers
+    train = DataLoader(train_ds, batch_size=bs, drop_last=True, num_workers=workers, sampler=sampler,
+                       collate_fn=train_ds.collate_fn, persistent_workers=workers > 0)
     val = DataLoader(val_ds, batch_size=bs, shuffle=False, drop_last=False, num_workers=0, collate_fn=val_ds.collate_fn)
     return DevicePrefetcher(train, ctx.device), DevicePrefetcher(val, ctx.device)
 
