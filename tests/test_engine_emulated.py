@@ -293,3 +293,22 @@ def test_split_k_path_of_encoder_convs(monkeypatch):
     y2 = EE.conv_fprop(x, wt, 2, None)
     monkeypatch.setenv("MINE_B200_SPLITK", "0")
     assert torch.allclose(y2, EE.conv_fprop(x, wt, 2, None), atol=1e-4)
+
+
+def test_split_weight_gradient_equals_plain_slicing():
+    """``SplitWeight`` (one gradient buffer in the parameter's layout for the three input-channel groups of a factorised
+    decoder conv) == autograd through plain slices, incl. a group that receives no gradient."""
+    import torch
+    from mine_b200.ops import conv_engine as E
+    torch.manual_seed(0)
+    w0 = torch.randn(8, 11, 3, 3)
+    for use in ((True, True, True), (True, False, True), (False, True, False)):
+        grads = []
+        for split in (lambda w: E.SplitWeight.apply(w, 4, 5), lambda w: (w[:, :4], w[:, 4:9], w[:, 9:])):
+            w = w0.clone().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            parts = split(w)
+            loss = sum((p * (i + 1.5)).square().sum() for i, (p, u) in enumerate(zip(parts, use)) if u)
+            loss.backward()
+            grads.append(w.grad.clone())
+        assert torch.allclose(grads[0], grads[1], rtol=1e-6, atol=1e-6)
+        assert grads[0].stride() == w0.contiguous(memory_format=torch.channels_last).stride()
