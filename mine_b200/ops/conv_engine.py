@@ -314,6 +314,25 @@ def dgrad_same_raw(dy, w, accumulate_into=None):
     return out
 
 
+class ReflectPadNHWC(torch.autograd.Function):
+    """1-pixel reflection pad of a contiguous NHWC tensor, gradient by the adjoint kernel (``csrc/pad_nhwc.cu``): the padded
+    skip feature and its gradient stay channels-last, so the library convolution around it needs no layout copies."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _count()
+        return ext().pad_reflect_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, gp):
+        _count()
+        return ext().pad_reflect_nhwc_bwd(gp.contiguous())
+
+
+def skip_conv_own_pad() -> bool:
+    return not _emulated and os.environ.get("MINE_B200_SKIP_PAD", "own") == "own"
+
+
 class SplitWeight(torch.autograd.Function):
     """``w[:, :cp], w[:, cp:cp+cs], w[:, cp+cs:]`` (per-plane / shared-skip / embedding input channels of a factorised
     decoder conv) with ONE gradient buffer: backward writes the three parts into an ``empty_like(w)`` (3 strided copies).
@@ -773,8 +792,17 @@ class ConvEngine:
             if feat is not None and own_convs:
                 smap = EE.shared_skip_map(feat, ws)                               # [B,H,W,Co] fp32
             elif feat is not None:
-                with torch.autocast(**amp):
-                    smap = F.conv2d(F.pad(feat, (1, 1, 1, 1), mode="reflect"), ws)
+                f_nhwc = feat.permute(0, 2, 3, 1)
+                if (skip_conv_own_pad() and feat.is_cuda and f_nhwc.is_contiguous() and feat.shape[1] % 8 == 0
+                        and feat.dtype in (torch.float32, torch.bfloat16) and min(feat.shape[2:]) >= 2):
+                    # NHWC pad kernel + dense channels-last weight slice: the library convolution runs without a single
+                    # layout copy in either direction (framework pad: 3 copies + 2 pad kernels per level and step)
+                    padded = ReflectPadNHWC.apply(f_nhwc).permute(0, 3, 1, 2)
+                    with torch.autocast(**amp):
+                        smap = F.conv2d(padded, ws.contiguous(memory_format=torch.channels_last))
+                else:
+                    with torch.autocast(**amp):
+                        smap = F.conv2d(F.pad(feat, (1, 1, 1, 1), mode="reflect"), ws)
                 smap = smap.permute(0, 2, 3, 1).float().contiguous()            # [B,H,W,Co] fp32
             if blk.c_emb > 0:
                 pbias = emb @ we.float().sum(dim=(2, 3)).t() + bias.float()[None]

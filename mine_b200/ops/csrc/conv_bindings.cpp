@@ -506,6 +506,29 @@ void bn_update_running(const at::Tensor& stats, at::Tensor running_mean, at::Ten
                                  (float)count, (float)momentum, cur_stream());
 }
 
+at::Tensor pad_reflect_nhwc(const at::Tensor& x) {
+  check_act_nhwc(x, "x");
+  TORCH_CHECK(x.size(1) >= 2 && x.size(2) >= 2, "reflection pad needs at least 2 x 2 pixels");
+  TORCH_CHECK(x.numel() / 8 + (int64_t)x.size(0) * (2 * (x.size(1) + x.size(2)) + 4) * (x.size(3) / 8) < (1ll << 31),
+              "tensor too large for 32-bit indexing");
+  c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor out = at::empty({x.size(0), x.size(1) + 2, x.size(2) + 2, x.size(3)}, x.options());
+  mine::launch_pad_reflect_nhwc(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2),
+                                (int)x.size(3), esize(x), cur_stream());
+  return out;
+}
+
+at::Tensor pad_reflect_nhwc_bwd(const at::Tensor& gp) {
+  check_act_nhwc(gp, "gp");
+  TORCH_CHECK(gp.size(1) >= 4 && gp.size(2) >= 4, "padded gradient too small");
+  TORCH_CHECK(gp.numel() / 8 < (1ll << 31), "tensor too large for 32-bit indexing");
+  c10::cuda::CUDAGuard guard(gp.device());
+  at::Tensor gx = at::empty({gp.size(0), gp.size(1) - 2, gp.size(2) - 2, gp.size(3)}, gp.options());
+  mine::launch_pad_reflect_nhwc_bwd(gp.data_ptr(), gx.data_ptr(), (int)gp.size(0), (int)gp.size(1) - 2,
+                                    (int)gp.size(2) - 2, (int)gp.size(3), esize(gp), cur_stream());
+  return gx;
+}
+
 // deferred form of bn_update_running: all layers of a step in one launch per 48 layers
 void bn_update_running_multi(const std::vector<at::Tensor>& stats, std::vector<at::Tensor> running_mean,
                              std::vector<at::Tensor> running_var, std::vector<at::Tensor> num_batches_tracked,
@@ -563,6 +586,8 @@ void register_conv(pybind11::module_& m) {
   m.def("head_conv_direct", &head_conv_direct);
   m.def("bn_update_running", &bn_update_running);
   m.def("bn_update_running_multi", &bn_update_running_multi);
+  m.def("pad_reflect_nhwc", &pad_reflect_nhwc);
+  m.def("pad_reflect_nhwc_bwd", &pad_reflect_nhwc_bwd);
   m.def("conv_taps_splitk", &conv_taps_splitk);
   m.def("splitk_finalize", &splitk_finalize);
 }

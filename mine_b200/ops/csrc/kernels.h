@@ -64,6 +64,9 @@ void launch_bn_bwd_apply(const void* g, const void* y, const float* stats, const
                          void* dy, float* dshared, float* dplane_bias, int B, int S, int H, int W, int C,
                          float inv_count, float eps, int es, const LLExchange* x, const float* beta, int pad_mode,
                          cudaStream_t stream);
+// pad_nhwc.cu: 1-pixel reflection pad of an NHWC tensor [N,H,W,C] -> [N,H+2,W+2,C] and its adjoint (es: 2 bf16, 4 fp32)
+void launch_pad_reflect_nhwc(const void* x, void* out, int N, int H, int W, int C, int es, cudaStream_t stream);
+void launch_pad_reflect_nhwc_bwd(const void* gp, void* gx, int N, int H, int W, int C, int es, cudaStream_t stream);
 void launch_head_bwd(const float* g_mpi, const float* mpi, const int8_t* sign, void* dz, float* dbias, size_t npix,
                      int use_alpha, int es, cudaStream_t stream);
 }  // namespace mine

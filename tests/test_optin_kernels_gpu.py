@@ -151,3 +151,25 @@ def test_deferred_running_statistics_one_launch_for_many_layers():
         assert torch.allclose(a.running_mean, b.running_mean, rtol=1e-6, atol=1e-7)
         assert torch.allclose(a.running_var, b.running_var, rtol=1e-6, atol=1e-7)
         assert int(b.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96, 256), (2, 8, 12, 2048), (3, 5, 7, 64), (1, 2, 3, 16), (2, 3, 3, 8)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_reflect_pad_nhwc_and_adjoint(shape, dtype):
+    """``pad_nhwc.cu`` vs ``F.pad(mode="reflect")`` and its autograd, on NHWC storage (the skip features of the decoder)."""
+    from mine_b200.ops import conv_engine as E
+    n, h, w, c = shape
+    gen = torch.Generator(device="cuda").manual_seed(h * w + c)
+    x = torch.randn((n, h, w, c), device="cuda", generator=gen).to(dtype)
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref = torch.nn.functional.pad(xr, (1, 1, 1, 1), mode="reflect")
+    xo = x.clone().requires_grad_(True)
+    got = E.ReflectPadNHWC.apply(xo)
+    assert got.shape == (n, h + 2, w + 2, c) and got.is_contiguous()
+    assert torch.equal(got.float(), ref.detach().permute(0, 2, 3, 1).to(dtype).float())
+    g = torch.randn(got.shape, device="cuda", generator=gen).to(dtype)
+    got.backward(g)
+    ref.backward(g.float().permute(0, 3, 1, 2))
+    want = xr.grad.permute(0, 2, 3, 1)
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert torch.allclose(xo.grad.float(), want, rtol=tol, atol=tol)
