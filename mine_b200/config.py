@@ -97,7 +97,7 @@ SCHEMA: Dict[str, tuple] = {
     "training.seed": (int, 0),
     "training.checkpoint_interval": (int, 5000),
     "training.log_interval": (int, 10),
-    "training.all_rank_eval": (bool, True),         # accepted, no effect: rank 0 evaluates, the others wait (patient barrier)
+    "training.all_rank_eval": (bool, True),         # validation batches dealt round-robin to the ranks, meters summed over ranks
     "training.max_steps": (int, 0),                 # 0 = no cap (used by tests / smoke runs)
 }
 

@@ -88,6 +88,22 @@ def patient_barrier() -> None:
             dist.barrier()
 
 
+def allreduce_host_sum(values):
+    """SUM of a small list of Python floats over all ranks through the host-side group (evaluation meters)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return list(values)
+    t = torch.tensor(list(values), dtype=torch.float64)
+    g = _PATIENT["group"]
+    if g is not None:
+        dist.all_reduce(t, group=g)
+    else:                                              # no gloo group: go through the default backend's device
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = t.to(dev)
+        dist.all_reduce(t)
+        t = t.cpu()
+    return t.tolist()
+
+
 def shutdown() -> None:
     if dist.is_available() and dist.is_initialized():
         _PATIENT["group"] = None

@@ -12,7 +12,7 @@ and checkpoint formats - on a different execution stack:
 * data parallelism = flat gradient arena + bucketed mean all-reduce overlapped with backward
   (own NVLink kernels or NCCL) + cross-replica BN statistics through the same communicator;
   static graph: no unused parameters, no buffer broadcast (SURVEY 2.4 N5/N8/N9);
-* exact resume (step, epoch, scheduler, RNG); evaluation on rank 0 while the other ranks wait at a host-side barrier.
+* exact resume (step, epoch, scheduler, RNG); evaluation sharded over the ranks (meters reduced on a host-side group).
 """
 from __future__ import annotations
 
@@ -554,11 +554,19 @@ class SynthesisTask:
         return True
 
     def _eval_and_checkpoint(self, val_data_loader):
-        """All ranks arrive here at the same step.  Rank 0 evaluates (BN in eval mode does not
-        communicate); the others wait at a barrier - no rank runs ahead into a collective
-        (the reference relies on accidental pairing, SURVEY 2.4 'rank-asymmetric control flow')."""
-        if self._is_main() and val_data_loader is not None and len(val_data_loader) > 0:
-            self.run_eval(val_data_loader)
+        """All ranks arrive here at the same step.  With ``training.all_rank_eval`` (default) and more than one rank the
+        validation batches are dealt round-robin to the ranks and the meters are summed over ranks (BN in eval mode does not
+        communicate, so the ranks evaluate independently); otherwise rank 0 evaluates alone.  Either way every rank then
+        waits at the host-side barrier - no rank runs ahead into a collective (the reference relies on accidental
+        pairing, SURVEY 2.4 'rank-asymmetric control flow')."""
+        has_val = val_data_loader is not None and len(val_data_loader) > 0
+        world = bootstrap.world_size()
+        sharded = has_val and world > 1 and bool(self.config.get("training.all_rank_eval", True))
+        if sharded:
+            self.run_eval(val_data_loader, shard=(bootstrap.rank(), world))
+        if self._is_main() and has_val:
+            if not sharded:
+                self.run_eval(val_data_loader)
             path = self.save_checkpoint("checkpoint_%012d.pth" % self.global_step, with_optimizer=False)
             if "hdfs_workspace" in self.config and path:
                 tb = sorted(glob.glob(os.path.join(self.config["local_workspace"], "events.out.tfevents.*")))
@@ -625,7 +633,9 @@ class SynthesisTask:
     # ------------------------------------------------------------------------------------------
     # evaluation / logging
     # ------------------------------------------------------------------------------------------
-    def run_eval(self, val_data_loader):
+    def run_eval(self, val_data_loader, shard=None):
+        """Validation pass.  ``shard = (rank, world)``: this rank evaluates batches ``rank, rank + world, ...`` and the
+        meter sums / counts are added up over all ranks at the end (every rank then holds the global averages)."""
         self.logger.info("Start running evaluation on validation set:")
         self.backbone.eval()
         self.decoder.eval()
@@ -635,9 +645,17 @@ class SynthesisTask:
             for step, items in enumerate(val_data_loader):
                 if (step + 1) % 20 == 0:
                     self.logger.info("    Eval progress: {}/{}".format(step + 1, len(val_data_loader)))
+                if shard is not None and step % shard[1] != shard[0]:
+                    continue
                 self.set_data(items)
                 loss_dict, vis = self.loss_fcn(is_val=True)
                 self.log_val(step, loss_dict, vis)
+            if shard is not None:
+                meters = list(self.val_losses.values())
+                tot = bootstrap.allreduce_host_sum([m.sum for m in meters] + [float(m.count) for m in meters])
+                for i, m in enumerate(meters):
+                    m.sum, m.count = tot[i], int(round(tot[len(meters) + i]))
+                    m.avg = m.sum / max(m.count, 1)
             self.logger.info("Evaluation finished, average losses: ")
             for v in self.val_losses.values():
                 self.logger.info("    {}".format(v))

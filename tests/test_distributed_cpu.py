@@ -100,3 +100,36 @@ def test_single_node_detection_for_peer_memory_collectives():
     assert single_node(8, {"LOCAL_WORLD_SIZE": "8"}) and single_node(8, {})
     assert not single_node(16, {"LOCAL_WORLD_SIZE": "8"})
     assert not single_node(16, {"LOCAL_WORLD_SIZE": "16", "GROUP_WORLD_SIZE": "2"})
+
+
+def _eval_worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
+                       "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank)})
+    torch.set_num_threads(2)
+    from mine_b200.parallel import bootstrap
+    bootstrap.init_distributed(device="cpu")                      # creates the host-side (patient) group as train.py does
+    from mine_b200.data.synthetic import synthetic_batch
+    task, _ = _make_task(1, rank)
+    loader = [synthetic_batch(1, 96, 128, 32, seed=10 + i) for i in range(5)]     # odd count: ranks get 3 and 2 batches
+    task.run_eval(loader, shard=(rank, world))
+    torch.save({k: (m.avg, m.count) for k, m in task.val_losses.items()}, os.path.join(out_dir, f"eval{rank}.pt"))
+    bootstrap.patient_barrier()
+    bootstrap.shutdown()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_evaluation_equals_single_process(tmp_path):
+    """``training.all_rank_eval``: validation batches dealt round-robin to the ranks + meter sums over ranks == one process
+    evaluating everything (evaluation-mode BatchNorm does not communicate, so the ranks are independent)."""
+    world, port = 2, _free_port()
+    mp.spawn(_eval_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "eval0.pt"), torch.load(tmp_path / "eval1.pt")
+    assert r0 == r1, "ranks disagree on the reduced meters"
+    from mine_b200.data.synthetic import synthetic_batch
+    task, _ = _make_task(1)
+    task.run_eval([synthetic_batch(1, 96, 128, 32, seed=10 + i) for i in range(5)])
+    for k, m in task.val_losses.items():
+        avg, count = r0[k]
+        assert count == m.count == 5, (k, count, m.count)
+        assert abs(avg - m.avg) <= 1e-4 * max(1.0, abs(m.avg)), (k, avg, m.avg)
