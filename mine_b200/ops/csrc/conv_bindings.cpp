@@ -557,12 +557,22 @@ void bn_update_running_multi(const std::vector<at::Tensor>& stats, std::vector<a
                                        mom.data(), cur_stream());
 }
 
+// host-side evaluation of the launcher-made multiply-high division (conv_engine.h::make_fastdiv; the device code is
+// ``__umulhi(n, mul) >> shr``): lets the CPU test tier check the constants for every divisor the launchers can produce
+int64_t fastdiv_host(int64_t n, int64_t d) {
+  TORCH_CHECK(n >= 0 && n < (1ll << 31) && d >= 1 && d < (1ll << 31), "fastdiv_host: 0 <= n < 2^31, 1 <= d < 2^31");
+  const mine::FastDiv f = mine::make_fastdiv((int)d);
+  if (f.d == 1u) return n;
+  return (int64_t)((uint32_t)(((uint64_t)(uint32_t)n * (uint64_t)f.mul) >> 32) >> f.shr);
+}
+
 }  // namespace
 
 void register_conv(pybind11::module_& m) {
   m.def("set_operand_size", &set_operand_size);
   m.def("get_operand_size", &get_operand_size);
   m.def("set_output_rounding", &set_output_rounding);
+  m.def("fastdiv_host", &fastdiv_host);
   m.def("set_deterministic", &set_deterministic);
   m.def("get_deterministic", &get_deterministic);
   m.def("conv_taps", &conv_taps);
