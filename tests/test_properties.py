@@ -1,6 +1,8 @@
 """Property tests of the specification layer (hypothesis): invariants the kernels are tested against."""
 import math
 
+import pytest
+
 import torch
 from hypothesis import given, settings
 from hypothesis import strategies as st
